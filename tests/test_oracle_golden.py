@@ -1,0 +1,177 @@
+"""Pins the oracle (NumPy and C restatements) against the reference's own known-answer tests.
+
+Transcribed from /root/reference/test/*.jl and the jldoctests in /root/reference/src/*.jl (see
+tests/golden_cases.py for per-case citations).  CPU only.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_c as oc
+from oracle import oracle_np as onp
+from tests import golden_cases as gc
+
+BACKENDS = {"numpy": onp, "c": oc}
+
+
+@pytest.mark.parametrize("backend", sorted(BACKENDS))
+@pytest.mark.parametrize("case", gc.ALL_OPERATOR_CASES, ids=lambda c: c.__name__)
+def test_operator_known_answers(case, backend):
+    case(BACKENDS[backend])
+
+
+def test_power_broad():
+    gc.case_power_broad()
+
+
+def test_cospi_exact_points():
+    assert onp.cospi(0.0) == 1.0 and onp.cospi(0.5) == 0.0 and onp.cospi(1.0) == -1.0
+    assert onp.cospi(1 / 3) == pytest.approx(0.5, abs=1e-16)
+    assert onp.cospi(1 / 9) == pytest.approx(0.9396926207859084, abs=2e-16)
+
+
+@pytest.mark.parametrize("backend", sorted(BACKENDS))
+def test_thermal_statistics(backend):
+    """test/forcing.jl:141-164 with NumPy normals standing in for Julia's randn! (statistical only)."""
+    B = BACKENDS[backend]
+    rng = np.random.default_rng(1234)
+
+    def draw(kb):
+        kx, ky = onp.zeros(50, 50), onp.zeros(50, 50)
+        nx = np.asfortranarray(rng.standard_normal((50, 50)))
+        ny = np.asfortranarray(rng.standard_normal((50, 50)))
+        B.thermal(kx, ky, onp.ones(50, 50), kb, 1 / 6, 1.0, nx, ny)
+        return kx, ky
+
+    gc.case_thermal_statistics(B, draw)
+
+
+# ------------------------------------------------------------------------------------------------
+# NumPy and C restatements must agree bit for bit (they were written independently from Appendix A)
+
+
+def _random_state(Lx, Ly, seed, thermal=False):
+    rng = np.random.default_rng(seed)
+    st = onp.State(Lx, Ly, thermal=thermal)
+    st.height[...] = 1.0 + 0.3 * rng.standard_normal((Lx, Ly))
+    st.height[...] = np.abs(st.height) + 0.06
+    st.velx[...] = 0.05 * rng.standard_normal((Lx, Ly))
+    st.vely[...] = 0.05 * rng.standard_normal((Lx, Ly))
+    st.ftemp[...] = 0.1 * rng.random((Lx, Ly, 9))
+    return st
+
+
+def _copy_state(st):
+    c = onp.State(st.Lx, st.Ly, thermal=hasattr(st, "kbtx"))
+    for k, v in vars(st).items():
+        if isinstance(v, np.ndarray):
+            getattr(c, k)[...] = v
+    return c
+
+
+FIELDS = ("fout", "ftemp", "feq", "height", "velx", "vely", "vsq", "pressure", "Fx", "Fy", "slipx", "slipy",
+          "hgradpx", "hgradpy", "dgrad")
+
+
+@pytest.mark.parametrize("Lx,Ly", [(5, 5), (25, 26), (33, 7)])
+@pytest.mark.parametrize("tau", [1.0, 0.75])
+@pytest.mark.parametrize("nm,pvariant", [((9, 3), "power_broad"), ((3, 2), "fast"), ((9, 3), "fast"),
+                                          ((4, 2), "power_broad")])
+def test_c_matches_numpy_bitwise(Lx, Ly, tau, nm, pvariant):
+    p = onp.Params(tau=tau, n=nm[0], m=nm[1], g=-0.001, gamma=0.01, delta=1.5, hmin=0.07)
+    a = _random_state(Lx, Ly, seed=Lx * 100 + Ly)
+    b = _copy_state(a)
+    rng = np.random.default_rng(7)
+    ct_field = np.asfortranarray(np.cos(np.pi * (1 / 9 + 1 / 36 * rng.random((Lx, Ly)))))
+    for it, (ct, sv, incl) in enumerate([(None, 0, None), (ct_field, 1, None), (0.5, 2, ([1e-4, -2e-4], 0.75))]):
+        for _ in range(3):
+            onp.step(a, p, cospi_theta=ct, pvariant=pvariant, slip_variant=sv, incl=incl)
+            oc.step(b, p, cospi_theta=ct, pvariant=pvariant, slip_variant=sv, incl=incl)
+        for name in FIELDS:
+            x, y = getattr(a, name), getattr(b, name)
+            assert np.array_equal(x, y, equal_nan=True), (it, name, np.abs(x - y).max())
+
+
+def test_c_threads_do_not_change_bits():
+    p = onp.Params(g=0.002, hmin=0.07, n=3, m=2)
+    a = _random_state(40, 37, seed=3)
+    b = _copy_state(a)
+    oc.time_loop(a, p, nsteps=20, threads=1)
+    oc.time_loop(b, p, nsteps=20, threads=4)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+
+
+# ------------------------------------------------------------------------------------------------
+# test/simulate.jl -- whole-loop known answers
+
+
+def test_flat_film_stays_exactly_flat():  # test/simulate.jl:4-7
+    p = onp.Params(Tmax=200, tdump=100)
+    for B in (onp, oc):
+        st = onp.State(25, 25)
+        st.height[...] = 1.0
+        B.time_loop(st, p)
+        assert np.all(st.height == 1.0)
+        assert st.height.sum() == 25 * 25
+
+
+def test_random_interface_flattens():  # test/simulate.jl:17-21 (run_random: theta = 1/9 via time_loop(...,θ))
+    p = onp.Params(Tmax=10000, tdump=5000)
+    st = onp.State(25, 25)
+    st.height[...] = onp.randinterface(25, 25, 1.0, 0.1, np.random.default_rng(42))
+    onp.equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, p.g)
+    oc.time_loop(st, p, cospi_theta=onp.cospi(1 / 9))
+    assert st.height.max() - st.height.min() < 0.1
+
+
+def test_rayleigh_taylor_grows():  # test/simulate.jl:33-35
+    p = onp.Params(Tmax=1000, tdump=500, g=-0.002)
+    st = onp.State(100, 100)
+    st.height[...] = onp.rayleightaylor_ic(100, 100, kx=4, ky=5, eps=0.01)
+    onp.equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, p.g)
+    dh, _ = oc.time_loop(st, p, log_dh=True)
+    assert dh[0] < dh[-1]
+    # the NumPy restatement walks the same trajectory bit for bit (first 50 steps)
+    st2 = onp.State(100, 100)
+    st2.height[...] = onp.rayleightaylor_ic(100, 100, kx=4, ky=5, eps=0.01)
+    dh2 = onp.time_loop(st2, p, nsteps=50)
+    assert np.array_equal(np.asarray(dh2), dh[:50])
+
+
+def _droplet_checks(h, rads=35):
+    cospi = onp.cospi
+    vol = np.pi / 3 * rads ** 3 * (2 + cospi(1 / 6)) * (1 - cospi(1 / 6)) ** 2
+    R1 = np.cbrt((rads ** 3 * (2 + cospi(1 / 6)) * (1 - cospi(1 / 6)) ** 2) / ((2 + cospi(1 / 9)) * (1 - cospi(1 / 9)) ** 2))
+    r1 = np.sin(np.pi / 9) * R1
+    drop1d = np.nonzero(h[74, :] > 0.055)[0]
+    droprad = len(drop1d) / 2
+    droph = h.max()
+    vnum = 1 / 6 * np.pi * droph * (3 * droprad ** 2 + droph ** 2)
+    assert abs(vol - vnum) < vol / 100 * 10
+    assert abs(r1 - droprad) < r1 / 100 * 10
+
+
+def test_relaxing_droplet():  # test/simulate.jl:44-60
+    p = onp.Params(Tmax=10000, delta=3.0)
+    st = onp.State(150, 150)
+    st.height[...] = onp.singledroplet(150, 150, 35, 1 / 6, (75, 75))
+    onp.equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, p.g)
+    mass0 = st.height.sum()
+    _, wet = oc.time_loop(st, p, log_wetted=True, threads=oc.max_threads())
+    _droplet_checks(st.height)
+    assert wet[0] < wet[-1]
+    assert abs(st.height.sum() - mass0) / mass0 < 1e-12  # mass conserved to round-off
+
+
+def test_sliding_droplet():  # test/simulate.jl:147-155 (inclination! in the callback slot, factor(t=1000)=1)
+    import math
+
+    p = onp.Params(Tmax=5000, delta=2.0)
+    st = onp.State(150, 150)
+    st.height[...] = onp.singledroplet(150, 150, 35, 1 / 6, (75, 75))
+    onp.equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, p.g)
+    factor = 0.5 + 0.5 * math.tanh((1000 - 0) / 1)
+    oc.time_loop(st, p, incl=([1e-4, 0.0], factor), threads=oc.max_threads())
+    i, j = np.unravel_index(np.argmax(st.height), st.height.shape)
+    assert i + 1 != 75 and j + 1 == 75
+    assert np.all(st.velx < 0.1) and np.all(st.vely < 0.1)
