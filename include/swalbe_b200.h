@@ -1,0 +1,201 @@
+/* libswalbe_b200 -- C ABI of the B200-native (sm_100a) thin-film D2Q9 lattice-Boltzmann step.
+ *
+ * This header is the drop-in boundary for ONE path of Swalbe.jl: the 2-D time step
+ *   filmpressure! -> h∇p! -> slippage! -> force sum -> equilibrium! -> BGKandStream! -> moments!
+ * (src/simulate.jl:15-22 of the reference).  Swalbe itself is pure Julia and has no FFI; each entry
+ * point below is what a `ccall((:sym, "libswalbe_b200"), Cint, (...), ...)` method on Swalbe's GPU
+ * state types (CuState / CuState_thermal, src/initialize.jl:214-256) would bind.  The reference
+ * function every symbol replaces is cited as file:line into the reference tree; INTEGRATION.md shows
+ * the Julia-side glue.
+ *
+ * Conventions
+ *  - All field pointers are DEVICE pointers to Float64 arrays in Julia's native column-major layout,
+ *    un-padded: A[i,j,k] (0-based) at i + Lx*(j + Ly*k); populations are nine contiguous Lx*Ly planes
+ *    (SoA), plane k = population k with the D2Q9 velocity set c0=(0,0) c1=(1,0) c2=(0,1) c3=(-1,0)
+ *    c4=(0,-1) c5=(1,1) c6=(-1,1) c7=(-1,-1) c8=(1,-1)   (src/collide.jl:92-100, :270-282).
+ *  - Zero-copy: the library never frees or retains caller pointers beyond a call.
+ *  - Every call is asynchronous on the caller's `stream` (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream), so it is ordered with the caller's own device work.  No hidden
+ *    cudaDeviceSynchronize.
+ *  - Every function returns 0 on success or a swalbe_status code; swalbe_last_error() gives the
+ *    message (thread-local).  Nothing throws across the ABI.
+ *  - Arithmetic is IEEE-754 double with NO fused multiply-add contraction and the reference's exact
+ *    evaluation order, so results equal the Julia CPU path operation for
+ *    operation.  cospi(theta) is evaluated by the caller and passed in as data.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point returns
+ *    SWALBE_ERR_CUDA.
+ */
+#ifndef SWALBE_B200_H
+#define SWALBE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWALBE_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum swalbe_status {
+  SWALBE_OK = 0,
+  SWALBE_ERR_DOMAIN = 1, /* unsupported (n,m) for the array-form pressure == Julia DomainError, src/pressure.jl:101-107 */
+  SWALBE_ERR_EXTENT = 2, /* Lx or Ly < 1, or too large */
+  SWALBE_ERR_CUDA = 3,   /* CUDA runtime error (message holds cudaGetErrorString) */
+  SWALBE_ERR_NCCL = 4,   /* NCCL error / libnccl.so.2 not loadable */
+  SWALBE_ERR_ARG = 5     /* NULL pointer or inconsistent arguments */
+} swalbe_status;
+
+int swalbe_version(void);
+const char *swalbe_last_error(void);
+/* number of kernels launched by this library in this process (for bench.py's gpu_launches claim) */
+unsigned long long swalbe_launch_count(void);
+
+/* pressure_variant */
+#define SWALBE_PRESSURE_POWER_BROAD 0 /* state form, src/pressure.jl:119-155 (any n,m) */
+#define SWALBE_PRESSURE_FAST 1        /* array form, src/pressure.jl:72-115 ((9,3) or (3,2) only) */
+/* slip_variant */
+#define SWALBE_SLIP_STANDARD 0 /* slippage!          src/forcing.jl:42-46  */
+#define SWALBE_SLIP_HCRIT 1    /* slippage2!         src/forcing.jl:85-99  */
+#define SWALBE_SLIP_RING_RIV 2 /* slippage_ring_riv! src/forcing.jl:107-111 */
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-operator entry points (array forms; the state forms of the reference only unpack fields).
+ * ------------------------------------------------------------------------------------------- */
+
+/* equilibrium!(feq, height, velx, vely, vsq, g)              src/equilibrium.jl:63-116 */
+int swalbe_equilibrium_d2q9(double *feq, const double *height, const double *velx, const double *vely, double *vsq,
+                            double g, int Lx, int Ly, void *stream);
+
+/* BGKandStream!(fout, feq, ftemp, Fx, Fy, tau)               src/collide.jl:70-105
+ * On return fout == ftemp == streamed post-collision populations (src/collide.jl:103). */
+int swalbe_bgk_stream_d2q9(double *fout, const double *feq, double *ftemp, const double *Fx, const double *Fy,
+                           double tau, int Lx, int Ly, void *stream);
+
+/* moments!(height, velx, vely, fout)                         src/moments.jl:43-52 */
+int swalbe_moments_d2q9(double *height, double *velx, double *vely, const double *fout, int Lx, int Ly, void *stream);
+
+/* filmpressure!(output, f, dgrad, gamma, theta, n, m, hmin, hcrit)   src/pressure.jl:72-115 (variant FAST)
+ * filmpressure!(state, sys; theta, gamma, n, m, hmin, hcrit)         src/pressure.jl:119-155 (variant POWER_BROAD)
+ * cospi_theta_field: NULL -> the scalar cospi_theta is used; else an Lx*Ly device field of cospi.(theta).
+ * dgrad is the reference's 8-plane scratch; it is accepted for signature parity and never touched. */
+int swalbe_filmpressure(double *pressure, const double *height, double *dgrad, double gamma, double cospi_theta,
+                        const double *cospi_theta_field, int n, int m, double hmin, double hcrit, int pressure_variant,
+                        int Lx, int Ly, void *stream);
+
+/* h∇p!(state)                                                src/forcing.jl:168-187
+ * == ∇f!(outx, outy, f, dgrad, a) with f = pressure, a = height      src/differences.jl:189-206 */
+int swalbe_hgradp(double *hgradpx, double *hgradpy, const double *pressure, const double *height, int Lx, int Ly,
+                  void *stream);
+
+/* ∇f!(outx, outy, f [, a])                                   src/differences.jl:153-187 (a == NULL: 3-arg form) */
+int swalbe_grad9(double *outx, double *outy, const double *f, const double *a, int Lx, int Ly, void *stream);
+
+/* ∇²f!(output, f, gamma)                                     src/differences.jl:57-75 */
+int swalbe_lap9(double *output, const double *f, double gamma, int Lx, int Ly, void *stream);
+
+/* slippage! / slippage2! / slippage_ring_riv!                src/forcing.jl:42-46, 85-99, 107-111 */
+int swalbe_slippage(double *slipx, double *slipy, const double *height, const double *velx, const double *vely,
+                    double delta, double mu, double hcrit, int slip_variant, int Lx, int Ly, void *stream);
+
+/* the inline force sum of every driver ("update!")           src/simulate.jl:18-19
+ * kbtx/kbty NULL -> F = -h∇p - slip; else F = -h∇p - slip - kbt     scripts/Rivulet_stability.jl:123-124 */
+int swalbe_force_sum(double *Fx, double *Fy, const double *hgradpx, const double *hgradpy, const double *slipx,
+                     const double *slipy, const double *kbtx, const double *kbty, int Lx, int Ly, void *stream);
+
+/* thermal!(kbtx, kbty, height, kbt, mu, delta)               src/forcing.jl:297-311
+ * The N(0,1) draws come from a counter-based Philox4x32-10 keyed on (seed, step, cell index) so the field is
+ * independent of any domain decomposition (Julia's randn! stream is not reproducible outside Julia). */
+int swalbe_thermal(double *kbtx, double *kbty, const double *height, double kbt, double mu, double delta,
+                   unsigned long long seed, unsigned long long step, int Lx, int Ly, void *stream);
+
+/* inclination!(alpha, state; t, tstart, tsmooth)             src/forcing.jl:363-368
+ * factor = 0.5 + 0.5*tanh((t - tstart)/tsmooth), evaluated by the caller. F += h*alpha*factor. */
+int swalbe_inclination(double *Fx, double *Fy, const double *height, double alpha_x, double alpha_y, double factor,
+                       int Lx, int Ly, void *stream);
+
+/* diagnostics used inside the drivers' loops, computed on the device, result written to out[] (device):
+ * out[0] = min(f), out[1] = max(f), out[2] = sum(f) (fixed-order two-pass sum), out[3] = count(f > thresh).
+ * sum(state.height) src/simulate.jl:8-14; maximum-minimum :56; wetted! src/measures.jl:13-17. */
+int swalbe_field_stats(double *out4, const double *f, double thresh, int Lx, int Ly, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused time loop (what time_loop / run_* call when the device string is "GPU").
+ * ------------------------------------------------------------------------------------------- */
+
+/* State / CuState / CuState_thermal  src/initialize.jl:149-168, 214-256 (x/y split fields as in the reference) */
+typedef struct swalbe_state {
+  double *fout, *ftemp, *feq;                       /* Lx*Ly*9 */
+  double *height, *velx, *vely, *vsq, *pressure;    /* Lx*Ly   */
+  double *Fx, *Fy, *slipx, *slipy, *hgradpx, *hgradpy;
+  double *dgrad;                                    /* Lx*Ly*8 scratch of the reference; unused, may be NULL */
+  double *kbtx, *kbty;                              /* thermal states only; may be NULL */
+} swalbe_state;
+
+/* Taumucs  src/initialize.jl:43-60 (+ the per-call keyword overrides of filmpressure!) */
+typedef struct swalbe_params {
+  double tau, mu, delta, kbt, gamma, hmin, hcrit, g;
+  int n, m;
+  double cospi_theta;              /* cospi(theta) */
+  const double *cospi_theta_field; /* device Lx*Ly field of cospi.(theta), or NULL */
+  int pressure_variant;            /* SWALBE_PRESSURE_* */
+  int slip_variant;                /* SWALBE_SLIP_* */
+  int use_inclination;             /* adds h*alpha*factor to F between force sum and equilibrium! (src/simulate.jl:89) */
+  double incl_ax, incl_ay, incl_factor;
+  int use_thermal;                 /* thermal! before the force sum, F = -h∇p - slip - kbt */
+  unsigned long long seed;         /* Philox key for the thermal noise */
+} swalbe_params;
+
+/* loop flags */
+#define SWALBE_LOOP_DEFAULT 0
+/* tau == 1 only: populations are written on the LAST step of the call only ("moments-only" steps, reported
+ * separately from the 144-B/LU accounting).  Field values on return are identical to the default mode. */
+#define SWALBE_LOOP_LAZY_POPULATIONS 1
+/* per-step device logs (see swalbe_time_loop) */
+typedef struct swalbe_loop_logs {
+  double *hmin, *hmax;        /* device, nsteps each: min/max of height BEFORE each step (src/simulate.jl:56); NULL = off */
+  unsigned long long *wetted; /* device, nsteps: count(height > hthresh) in the callback slot (src/simulate.jl:89); NULL = off */
+  double hthresh;             /* 0.055 in wetted!  src/measures.jl:13 */
+} swalbe_loop_logs;
+
+typedef struct swalbe_plan swalbe_plan; /* opaque: library-owned scratch (3 moment planes) + launch geometry */
+
+int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly);
+int swalbe_plan_destroy(swalbe_plan *plan);
+
+/* nsteps iterations of the loop body of time_loop (src/simulate.jl:15-22), fused into one kernel per step.
+ * `step0` is the index of the first step (only used as the thermal-noise counter).  On return (stream-ordered)
+ * EVERY field of `state` holds exactly what the reference's state holds after the same nsteps: height/velx/vely,
+ * fout == ftemp == streamed populations, and feq/vsq/pressure/h∇p/slip/F[/kbt] of the last step.  dgrad is scratch
+ * in the reference and is left untouched here. */
+int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *state, const swalbe_params *params, int nsteps,
+                     unsigned long long step0, int flags, const swalbe_loop_logs *logs, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: row-slab decomposition along j (Ly), one process per GPU, halo rows over NCCL send/recv.
+ * The reference has no multi-GPU path; this is new.  Rank r owns global rows
+ * [r*Ly/nranks, (r+1)*Ly/nranks) of every plane; Ly % nranks must be 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct swalbe_dist swalbe_dist; /* opaque: slabs with ghost rows, NCCL communicator, streams, events */
+
+#define SWALBE_NCCL_UNIQUE_ID_BYTES 128
+/* rank 0 calls this and ships the 128 bytes to the other ranks by any means (MPI / torch.distributed / file) */
+int swalbe_dist_unique_id(void *id128);
+int swalbe_dist_create(swalbe_dist **dist, const void *id128, int rank, int nranks, int Lx, int Ly_global,
+                       const swalbe_params *params);
+int swalbe_dist_destroy(swalbe_dist *dist);
+int swalbe_dist_local_rows(const swalbe_dist *dist, int *j_begin, int *j_count);
+/* upload this rank's rows of height/velx/vely (+ the nine ftemp planes when tau != 1; ftemp may be NULL at tau == 1)
+ * from DEVICE arrays holding only the local slab (Lx * j_count each), then exchange halos */
+int swalbe_dist_set_state(swalbe_dist *dist, const double *height, const double *velx, const double *vely,
+                          const double *ftemp, void *stream);
+/* nsteps fused steps with halo exchange overlapped with the interior update */
+int swalbe_dist_time_loop(swalbe_dist *dist, int nsteps, unsigned long long step0, void *stream);
+/* copy this rank's slab rows of height/velx/vely and (optional, may be NULL) the nine population planes out */
+int swalbe_dist_get_state(swalbe_dist *dist, double *height, double *velx, double *vely, double *fout, void *stream);
+/* device time (ms) spent in the last swalbe_dist_time_loop call, measured with CUDA events on its streams */
+int swalbe_dist_last_loop_ms(swalbe_dist *dist, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWALBE_B200_H */

@@ -1,0 +1,576 @@
+"""swalbe_b200 -- host-side mirror of Swalbe.jl's 2-D operator API on top of libswalbe_b200.so.
+
+Julia is not available in the build image, so the host side that the reference's scripts would run in
+Julia is mirrored here in Python with the same names, argument order and error behaviour
+(`SysConst`, `Taumucs`, `Sys(sys, "GPU"; kind)`, `equilibrium!`, `BGKandStream!`, `moments!`,
+`filmpressure!`, `h∇p!`, `∇f!`, `∇²f!`, `slippage!`, `slippage2!`, `slippage_ring_riv!`, `thermal!`,
+`inclination!`, `update!`, `time_loop`, `run_*`).  `!` and `∇` cannot appear in Python identifiers, so
+`equilibrium!` is `equilibrium`, `h∇p!` is `hgradp`, `∇f!` is `gradf`, `∇²f!` is `laplacianf`; the
+table ``JULIA_NAMES`` maps the exact Julia spellings.  The Julia glue that binds the same C ABI is in
+``julia/SwalbeB200.jl``.
+
+PyTorch is used only as the owner of device memory and streams: every field is a CUDA float64 tensor
+whose memory is Julia's column-major layout (x contiguous), handed to the C ABI as a raw pointer
+together with the current CUDA stream.  No arithmetic of the path happens in PyTorch or on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import DomainError, SwalbeError  # noqa: F401
+
+__all__ = [
+    "Taumucs", "SysConst", "Sys_const", "Sys", "CuState", "CuState_thermal", "Swalbe_state", "Field", "cospi",
+    "equilibrium", "BGKandStream", "moments", "filmpressure", "hgradp", "gradf", "laplacianf", "slippage",
+    "slippage2", "slippage_ring_riv", "thermal", "inclination", "update", "time_loop", "run_flat", "run_random",
+    "run_rayleightaylor", "run_dropletrelax", "run_dropletpatterned", "run_dropletforced", "wetted", "snapshot",
+    "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES",
+]
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SwalbeError("swalbe_b200 needs a CUDA device: the B200 path has no CPU fallback")
+    return torch
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def cospi(x: float) -> float:
+    """cos(pi x) with exact range reduction (stand-in for Base.cospi; evaluated once on the host)."""
+    x = math.fmod(abs(float(x)), 2.0)
+    if x > 1.0:
+        x = 2.0 - x
+    if x == 0.5:
+        return 0.0
+    if x <= 0.25:
+        return math.cos(math.pi * x)
+    if x < 0.75:
+        return math.sin(math.pi * (0.5 - x))
+    return -math.cos(math.pi * (1.0 - x))
+
+
+# ------------------------------------------------------------------------------------------------
+# constants  (src/initialize.jl:43-81)
+
+
+class Taumucs:
+    """Base.@kwdef struct Taumucs  src/initialize.jl:43-60 -- same fields and defaults (μ = cₛ²(τ-½))."""
+
+    def __init__(self, Tmax=1000, tdump=None, τ=None, cs=None, μ=None, δ=None, kbt=0.0, γ=None, n=9, m=3, hmin=0.1,
+                 hcrit=0.05, θ=None, g=0.0, *, tau=None, mu=None, delta=None, gamma=None, theta=None):
+        # (Julia's `cₛ` NFKC-normalises to `cs` in Python source, so `Taumucs(cₛ=...)` works as written)
+        pick = lambda a, b, d: d if (a is None and b is None) else (a if a is not None else b)  # noqa: E731
+        self.Tmax = int(Tmax)
+        self.tdump = int(tdump) if tdump is not None else self.Tmax // 10
+        self.tau = float(pick(τ, tau, 1.0))
+        self.cs = float(cs) if cs is not None else 1 / math.sqrt(3.0)
+        self.mu = float(pick(μ, mu, self.cs * self.cs * (self.tau - 0.5)))
+        self.delta = float(pick(δ, delta, 1.0))
+        self.kbt = float(kbt)
+        self.gamma = float(pick(γ, gamma, 0.01))
+        self.n, self.m = int(n), int(m)
+        self.hmin, self.hcrit = float(hmin), float(hcrit)
+        self.theta = float(pick(θ, theta, 1 / 9))
+        self.g = float(g)
+
+    # Julia spellings
+    τ = property(lambda s: s.tau)
+    μ = property(lambda s: s.mu)
+    δ = property(lambda s: s.delta)
+    γ = property(lambda s: s.gamma)
+    θ = property(lambda s: s.theta)
+
+
+class SysConst:
+    """Base.@kwdef struct SysConst  src/initialize.jl:76-81."""
+
+    def __init__(self, Lx=256, Ly=256, param: Taumucs | None = None):
+        if param is None:
+            raise TypeError("SysConst: keyword argument param not assigned")  # @kwdef field without default
+        self.Lx, self.Ly, self.param = int(Lx), int(Ly), param
+
+
+Sys_const = SysConst  # spelling used by BASELINE.json's north_star
+
+
+# ------------------------------------------------------------------------------------------------
+# device arrays
+
+
+class Field:
+    """A device Float64 array in Julia's column-major layout.
+
+    ``shape`` is Julia's (Lx, Ly) or (Lx, Ly, K).  ``t`` is the owning torch tensor, C-contiguous with the
+    reversed shape (K, Ly, Lx); ``jl`` is a permuted view indexed [i, j, k] like Julia (0-based).
+    """
+
+    def __init__(self, Lx, Ly, K=None, fill=0.0):
+        torch = _torch()
+        self.shape = (Lx, Ly) if K is None else (Lx, Ly, K)
+        tshape = (Ly, Lx) if K is None else (K, Ly, Lx)
+        self.t = torch.full(tshape, float(fill), dtype=torch.float64, device="cuda")
+        self.jl = self.t.permute(*reversed(range(self.t.dim())))
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return C.c_void_p(self.t.data_ptr())
+
+    def numpy(self) -> np.ndarray:
+        """Host copy as a Fortran-ordered NumPy array with the Julia shape (== Array(field))."""
+        return np.asfortranarray(self.t.cpu().numpy().transpose())
+
+    def set(self, a) -> "Field":
+        """field .= a   (a: scalar, NumPy array with the Julia shape, or another Field)."""
+        torch = _torch()
+        if isinstance(a, Field):
+            self.t.copy_(a.t)
+        elif np.isscalar(a):
+            self.t.fill_(float(a))
+        else:
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != self.shape:
+                raise ValueError(f"DimensionMismatch: {a.shape} vs {self.shape}")
+            self.t.copy_(torch.from_numpy(np.ascontiguousarray(a.transpose())))
+        return self
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, Field):
+        return x.ptr
+    raise TypeError(f"expected a swalbe_b200.Field device array, got {type(x).__name__} "
+                    "(host arrays are not accepted: there is no CPU path)")
+
+
+class CuState:
+    """CuState  src/initialize.jl:214-233 as built by Sys(sys, "GPU")  :513-535 (height = 1, rest 0)."""
+
+    thermal = False
+
+    def __init__(self, Lx, Ly):
+        self.Lx, self.Ly = Lx, Ly
+        self.fout, self.ftemp, self.feq = Field(Lx, Ly, 9), Field(Lx, Ly, 9), Field(Lx, Ly, 9)
+        self.height = Field(Lx, Ly, fill=1.0)
+        self.velx, self.vely, self.vsq, self.pressure = Field(Lx, Ly), Field(Lx, Ly), Field(Lx, Ly), Field(Lx, Ly)
+        self.Fx, self.Fy, self.slipx, self.slipy = Field(Lx, Ly), Field(Lx, Ly), Field(Lx, Ly), Field(Lx, Ly)
+        self.hgradpx, self.hgradpy = Field(Lx, Ly), Field(Lx, Ly)  # h∇px, h∇py
+        self.dgrad = Field(Lx, Ly, 8)
+        self._plan = None
+
+    def __getattr__(self, name):  # Julia field spellings
+        if name == "h∇px":
+            return self.hgradpx
+        if name == "h∇py":
+            return self.hgradpy
+        raise AttributeError(name)
+
+    def _c_state(self) -> _lib.CState:
+        s = _lib.CState()
+        for name, _ in _lib.CState._fields_:
+            f = getattr(self, name, None) if name not in ("kbtx", "kbty") or self.thermal else None
+            setattr(s, name, f.ptr if isinstance(f, Field) else None)
+        return s
+
+    def plan(self):
+        if self._plan is None:
+            h = C.c_void_p()
+            _lib.call("swalbe_plan_create", C.byref(h), self.Lx, self.Ly)
+            self._plan = _Plan(h)
+        return self._plan.handle
+
+
+class CuState_thermal(CuState):
+    """CuState_thermal  src/initialize.jl:235-256 (adds kbtx, kbty)."""
+
+    thermal = True
+
+    def __init__(self, Lx, Ly):
+        super().__init__(Lx, Ly)
+        self.kbtx, self.kbty = Field(Lx, Ly), Field(Lx, Ly)
+
+
+Swalbe_state = CuState  # spelling used by BASELINE.json's north_star
+
+
+class _Plan:
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            _lib.load().swalbe_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def Sys(sysc: SysConst, device: str, T=float, kind: str = "simple"):
+    """Sys(sysc, device; T, kind)  src/initialize.jl:491-572.  Only the "GPU" device string exists here."""
+    if device != "GPU":
+        raise SwalbeError(f'Sys(sys, "{device}"): swalbe_b200 implements the "GPU" path only (no CPU fallback)')
+    if T not in (float, np.float64, "Float64"):
+        raise SwalbeError("swalbe_b200 is Float64 only")
+    if kind == "simple":
+        return CuState(sysc.Lx, sysc.Ly)
+    if kind == "thermal":
+        return CuState_thermal(sysc.Lx, sysc.Ly)
+    return None  # the reference falls through and returns nothing for unknown kinds
+
+
+# ------------------------------------------------------------------------------------------------
+# operators: array form f(out..., in..., scalars...) and state form f(state, sys; kw...)
+
+
+def _dims(f: Field):
+    return f.shape[0], f.shape[1]
+
+
+def equilibrium(*args):
+    """equilibrium!(feq, height, velx, vely, vsq, g) | equilibrium!(state, sys)   src/equilibrium.jl:63-128"""
+    if isinstance(args[0], CuState):
+        st, sys_ = args
+        return equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, sys_.param.g)
+    feq, h, ux, uy, vsq, g = args
+    _lib.call("swalbe_equilibrium_d2q9", _ptr(feq), _ptr(h), _ptr(ux), _ptr(uy), _ptr(vsq), float(g), *_dims(h), _stream())
+
+
+def BGKandStream(*args, τ=None, tau=None):
+    """BGKandStream!(fout, feq, ftemp, Fx, Fy, τ) | BGKandStream!(state, sys; τ)   src/collide.jl:70-161"""
+    if isinstance(args[0], CuState):
+        st, sys_ = args
+        t = τ if τ is not None else (tau if tau is not None else sys_.param.tau)
+        return BGKandStream(st.fout, st.feq, st.ftemp, st.Fx, st.Fy, t)
+    fout, feq, ftemp, Fx, Fy, t = args
+    _lib.call("swalbe_bgk_stream_d2q9", _ptr(fout), _ptr(feq), _ptr(ftemp), _ptr(Fx), _ptr(Fy), float(t), *_dims(Fx), _stream())
+
+
+def moments(*args):
+    """moments!(height, velx, vely, fout) | moments!(state)   src/moments.jl:43-73"""
+    if isinstance(args[0], CuState):
+        st = args[0]
+        return moments(st.height, st.velx, st.vely, st.fout)
+    h, ux, uy, f = args
+    _lib.call("swalbe_moments_d2q9", _ptr(h), _ptr(ux), _ptr(uy), _ptr(f), *_dims(h), _stream())
+
+
+def _theta_args(θ):
+    """θ scalar -> (cospi θ, NULL); θ Field holding cospi.(θ)... the caller passes θ itself: a scalar, or a
+    Field of angles, for which cospi.(θ) is evaluated on the host once and cached on the Field."""
+    if isinstance(θ, Field):
+        c = getattr(θ, "_cospi", None)
+        if c is None or getattr(θ, "_cospi_version", None) != θ.t._version:
+            ang = θ.numpy()
+            c = Field(*θ.shape[:2]).set(np.vectorize(cospi)(ang))
+            θ._cospi, θ._cospi_version = c, θ.t._version
+        return 0.0, c.ptr
+    return cospi(θ), None
+
+
+def filmpressure(*args, θ=None, γ=None, n=None, m=None, hmin=None, hcrit=None, theta=None, gamma=None):
+    """filmpressure!(output, f, dgrad, γ, θ, n, m, hmin, hcrit)        src/pressure.jl:72-115 (fast_93/fast_32)
+    filmpressure!(state, sys; θ, γ, n, m, hmin, hcrit)                src/pressure.jl:119-155 (power_broad)
+    filmpressure!(state::CuState_thermal, sys)                         src/pressure.jl:117 (array form, no keywords)"""
+    θ = θ if θ is not None else theta
+    γ = γ if γ is not None else gamma
+    if isinstance(args[0], CuState):
+        st, sys_ = args
+        p = sys_.param
+        if isinstance(st, CuState_thermal):
+            if any(v is not None for v in (θ, γ, n, m, hmin, hcrit)):
+                raise TypeError("MethodError: filmpressure!(::CuState_thermal, ::SysConst) accepts no keyword arguments")
+            return filmpressure(st.pressure, st.height, st.dgrad, p.gamma, p.theta, p.n, p.m, p.hmin, p.hcrit)
+        ct, ctf = _theta_args(p.theta if θ is None else θ)
+        _lib.call("swalbe_filmpressure", st.pressure.ptr, st.height.ptr, st.dgrad.ptr,
+                  float(p.gamma if γ is None else γ), ct, ctf, int(p.n if n is None else n), int(p.m if m is None else m),
+                  float(p.hmin if hmin is None else hmin), float(p.hcrit if hcrit is None else hcrit),
+                  _lib.PRESSURE_POWER_BROAD, st.Lx, st.Ly, _stream())
+        return None
+    out, f, dgrad, γa, θa, na, ma, hmina, hcrita = args
+    ct, ctf = _theta_args(θa)
+    _lib.call("swalbe_filmpressure", _ptr(out), _ptr(f), _ptr(dgrad), float(γa), ct, ctf, int(na), int(ma), float(hmina),
+              float(hcrita), _lib.PRESSURE_FAST, *_dims(f), _stream())
+
+
+def hgradp(st: CuState):
+    """h∇p!(state)   src/forcing.jl:168-187"""
+    _lib.call("swalbe_hgradp", st.hgradpx.ptr, st.hgradpy.ptr, st.pressure.ptr, st.height.ptr, st.Lx, st.Ly, _stream())
+
+
+def gradf(outx, outy, f, *rest):
+    """∇f!(outx, outy, f) | ∇f!(outx, outy, f, a) | ∇f!(outx, outy, f, dgrad, a)   src/differences.jl:153-206"""
+    a = rest[-1] if rest else None
+    _lib.call("swalbe_grad9", _ptr(outx), _ptr(outy), _ptr(f), _ptr(a), *_dims(f), _stream())
+
+
+def laplacianf(out, f, γ):
+    """∇²f!(output, f, γ)   src/differences.jl:57-75"""
+    _lib.call("swalbe_lap9", _ptr(out), _ptr(f), float(γ), *_dims(f), _stream())
+
+
+def _slip(variant, args):
+    if isinstance(args[0], CuState):
+        st, sys_ = args
+        p = sys_.param
+        a = (st.slipx, st.slipy, st.height, st.velx, st.vely, p.delta, p.mu, p.hcrit)
+    else:
+        a = tuple(args) + ((0.0,) if len(args) == 7 else ())
+    sx, sy, h, ux, uy, δ, μ, hcrit = a
+    _lib.call("swalbe_slippage", _ptr(sx), _ptr(sy), _ptr(h), _ptr(ux), _ptr(uy), float(δ), float(μ), float(hcrit),
+              variant, *_dims(h), _stream())
+
+
+def slippage(*args):
+    """slippage!(slipx, slipy, height, velx, vely, δ, μ) | slippage!(state, sys)   src/forcing.jl:42-56"""
+    _slip(_lib.SLIP_STANDARD, args)
+
+
+def slippage2(st, sys_):
+    """slippage2!(state, sys)   src/forcing.jl:85-99"""
+    _slip(_lib.SLIP_HCRIT, (st, sys_))
+
+
+def slippage_ring_riv(*args):
+    """slippage_ring_riv!(slipx, slipy, height, velx, vely, δ, μ, hcrit) | (state, sys)   src/forcing.jl:107-122"""
+    _slip(_lib.SLIP_RING_RIV, args)
+
+
+def thermal(*args, seed=0, step=0):
+    """thermal!(kbtx, kbty, height, kbt, μ, δ) | thermal!(state, sys)   src/forcing.jl:297-320
+    (counter-based Philox normals keyed on (seed, step, cell) instead of Julia's randn! stream)."""
+    if isinstance(args[0], CuState):
+        st, sys_ = args
+        p = sys_.param
+        args = (st.kbtx, st.kbty, st.height, p.kbt, p.mu, p.delta)
+    kx, ky, h, kbt, μ, δ = args
+    _lib.call("swalbe_thermal", _ptr(kx), _ptr(ky), _ptr(h), float(kbt), float(μ), float(δ), int(seed), int(step),
+              *_dims(h), _stream())
+
+
+def inclination(α, st: CuState, t=1000, tstart=0, tsmooth=1):
+    """inclination!(α, state; t, tstart, tsmooth)   src/forcing.jl:363-368"""
+    factor = 0.5 + 0.5 * math.tanh((t - tstart) / tsmooth)
+    _lib.call("swalbe_inclination", st.Fx.ptr, st.Fy.ptr, st.height.ptr, float(α[0]), float(α[1]), factor, st.Lx, st.Ly,
+              _stream())
+
+
+def update(st: CuState):
+    """The inline force sum of the drivers, `state.Fx .= -state.h∇px .- state.slipx` (src/simulate.jl:18-19);
+    for thermal states `... .- state.kbtx` (scripts/Rivulet_stability.jl:123-124).  north_star calls it update!."""
+    kx, ky = (st.kbtx.ptr, st.kbty.ptr) if st.thermal else (None, None)
+    _lib.call("swalbe_force_sum", st.Fx.ptr, st.Fy.ptr, st.hgradpx.ptr, st.hgradpy.ptr, st.slipx.ptr, st.slipy.ptr, kx, ky,
+              st.Lx, st.Ly, _stream())
+
+
+def field_stats(f: Field, thresh=0.055):
+    """(min, max, sum, count(f > thresh)) computed on the device; one 32-byte read-back."""
+    torch = _torch()
+    out = torch.empty(4, dtype=torch.float64, device="cuda")
+    _lib.call("swalbe_field_stats", C.c_void_p(out.data_ptr()), f.ptr, float(thresh), *_dims(f), _stream())
+    mn, mx, sm, cnt = out.cpu().tolist()
+    return mn, mx, sm, int(cnt)
+
+
+def wetted(area_size: list, st: CuState, hthresh=0.055):
+    """wetted!(area_size, state; hthresh)   src/measures.jl:13-17"""
+    area_size.append(field_stats(st.height, hthresh)[3])
+
+
+def snapshot(snap: np.ndarray, field: Field, t: int, dumping=1000):
+    """snapshot!(snap, field, t; dumping)   src/measures.jl:99-105"""
+    if t % dumping == 0:
+        snap[t // dumping - 1, :] = field.numpy().reshape(-1, order="F")
+
+
+# ------------------------------------------------------------------------------------------------
+# drivers  (src/simulate.jl)
+
+
+def _c_params(p: Taumucs, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None, thermal_seed=None,
+              pressure_variant=_lib.PRESSURE_POWER_BROAD):
+    q = _lib.CParams()
+    q.tau, q.mu, q.delta, q.kbt, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.kbt, p.gamma, p.hmin, p.hcrit, p.g
+    q.n, q.m = p.n, p.m
+    ct, ctf = _theta_args(p.theta if θ is None else θ)
+    q.cospi_theta, q.cospi_theta_field = ct, ctf
+    q.pressure_variant, q.slip_variant = pressure_variant, slip_variant
+    if incl is not None:
+        α, factor = incl
+        q.use_inclination, q.incl_ax, q.incl_ay, q.incl_factor = 1, float(α[0]), float(α[1]), float(factor)
+    if thermal_seed is not None:
+        q.use_thermal, q.seed = 1, int(thermal_seed)
+    return q
+
+
+def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None,
+                thermal_seed=None, step0=0, lazy_populations=False, log_minmax=False, log_wetted=False, hthresh=0.055,
+                pressure_variant=None):
+    """nsteps iterations of the loop body src/simulate.jl:15-22 through swalbe_time_loop (one fused kernel/step).
+
+    Returns (hmin[nsteps], hmax[nsteps], wetted[nsteps]) device tensors for the requested logs (else None)."""
+    torch = _torch()
+    if pressure_variant is None:  # CuState_thermal goes through the array form (src/pressure.jl:117)
+        pressure_variant = _lib.PRESSURE_FAST if isinstance(st, CuState_thermal) else _lib.PRESSURE_POWER_BROAD
+    q = _c_params(sys_.param, θ, slip_variant, incl, thermal_seed, pressure_variant)
+    cs = st._c_state()
+    logs = _lib.CLogs()
+    mn = mx = wet = None
+    if log_minmax:
+        mn = torch.empty(nsteps, dtype=torch.float64, device="cuda")
+        mx = torch.empty(nsteps, dtype=torch.float64, device="cuda")
+        logs.hmin, logs.hmax = mn.data_ptr(), mx.data_ptr()
+    if log_wetted:
+        wet = torch.empty(nsteps, dtype=torch.int64, device="cuda")
+        logs.wetted = wet.data_ptr()
+    logs.hthresh = hthresh
+    flags = _lib.LOOP_LAZY_POPULATIONS if lazy_populations else _lib.LOOP_DEFAULT
+    _lib.call("swalbe_time_loop", st.plan(), C.byref(cs), C.byref(q), int(nsteps), int(step0), flags,
+              C.byref(logs) if (log_minmax or log_wetted) else None, _stream())
+    return mn, mx, wet
+
+
+def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None):
+    """The four 2-D time_loop methods  src/simulate.jl:6-96:
+
+    time_loop(sys, state)                       plain                          :6-25
+    time_loop(sys, state, θ)                    θ scalar or Field              :26-45
+    time_loop(sys, state, Δh::list)             logs max-min every step        :47-67
+    time_loop(sys, state, f, measure::list)     callback slot; f ∈ {wetted, inclination}  :69-96
+
+    The loop body runs as fused kernels in chunks of `tdump` steps; the mass print happens at the same
+    steps as in the reference (t % tdump == 0, before that step's update)."""
+    p = sys_.param
+    θ, dh, cb, measure = None, None, None, None
+    if len(extra) == 1 and isinstance(extra[0], list):
+        dh = extra[0]
+    elif len(extra) == 1:
+        θ = extra[0]
+    elif len(extra) == 2:
+        cb, measure = extra
+        if cb not in (wetted, inclination):
+            raise SwalbeError("time_loop: only Swalbe.wetted! and Swalbe.inclination! callbacks are fused on the device")
+    elif extra:
+        raise TypeError("MethodError: no method matching time_loop with these arguments")
+    incl = (measure, 0.5 + 0.5 * math.tanh((1000 - 0) / 1)) if cb is inclination else None  # defaults of :363
+    t = 1
+    tdump = max(1, p.tdump)
+    while t <= p.Tmax:
+        if t % tdump == 0:
+            mass = field_stats(st.height)[2]
+            if verbose:
+                print(f"Time step {t} mass is {round(mass, 3)}")
+        nxt = min(p.Tmax + 1, (t // tdump + 1) * tdump)  # run up to (not including) the next dump step
+        if chunk:
+            nxt = min(nxt, t + chunk)
+        n = nxt - t
+        mn, mx, wet = fused_steps(st, sys_, n, θ=θ, incl=incl, log_minmax=dh is not None, log_wetted=cb is wetted)
+        if dh is not None:
+            dh.extend((mx - mn).cpu().tolist())
+        if cb is wetted:
+            measure.extend(wet.cpu().tolist())
+        t = nxt
+    return st if cb is None else (st, measure)
+
+
+def run_flat(sys_: SysConst, device: str, verbos=True):
+    """run_flat  src/simulate.jl:236-245"""
+    print("Simulating a flat interface without driving forces (nothing should happen) in two dimensions")
+    st = Sys(sys_, device)
+    st.height.set(1.0)
+    time_loop(sys_, st, verbose=verbos)
+    return st.height
+
+
+def run_random(sys_: SysConst, device: str, h0=1.0, ϵ=0.01, verbos=True, rng=None):
+    """run_random  src/simulate.jl:286-294 (randinterface! src/initialvalues.jl:23-33 with a NumPy generator)"""
+    print("Simulating a random undulated interface in two dimensions")
+    st = Sys(sys_, device)
+    rng = rng if rng is not None else np.random.default_rng()
+    st.height.set(h0 * (1.0 + ϵ * rng.standard_normal((sys_.Lx, sys_.Ly))))
+    equilibrium(st, sys_)
+    time_loop(sys_, st, 1 / 9, verbose=verbos)
+    return st.height
+
+
+def run_rayleightaylor(sys_: SysConst, device: str, kx=15, ky=18, h0=1.0, ϵ=0.001, verbos=True):
+    """run_rayleightaylor  src/simulate.jl:338-358 (divides by Lx-1, Ly-1 like the reference)"""
+    print("Simulating the Rayleigh Taylor instability in two dimensions")
+    st = Sys(sys_, device)
+    i = np.arange(1, sys_.Lx + 1, dtype=np.float64)[:, None]
+    j = np.arange(1, sys_.Ly + 1, dtype=np.float64)[None, :]
+    st.height.set(h0 * (1 + ϵ * np.sin(2 * np.pi * kx * i / (sys_.Lx - 1)) * np.sin(2 * np.pi * ky * j / (sys_.Ly - 1))))
+    diff: list = []
+    equilibrium(st, sys_)
+    time_loop(sys_, st, diff, verbose=verbos)
+    return st.height, diff
+
+
+def singledroplet(Lx, Ly, radius, θ, center):
+    """singledroplet  src/initialvalues.jl:203-224 (host-side initial condition, precursor 0.05)"""
+    i = np.arange(1, Lx + 1, dtype=np.float64)[:, None]
+    j = np.arange(1, Ly + 1, dtype=np.float64)[None, :]
+    circ = np.sqrt((i - center[0]) ** 2 + (j - center[1]) ** 2)
+    inside = circ <= radius
+    cap = (np.cos(np.arcsin(np.where(inside, circ / radius, 0.0))) - cospi(θ)) * radius
+    h = np.where(inside, cap, 0.05)
+    return np.where(h < 0, 0.05, h)
+
+
+def run_dropletrelax(sys_: SysConst, device: str, radius=20, θ0=1 / 6, center=None, verbos=True):
+    """run_dropletrelax  src/simulate.jl:384-399"""
+    print("Simulating an out of equilibrium droplet in two dimensions")
+    center = center or (sys_.Lx // 2, sys_.Ly // 2)
+    st = Sys(sys_, device)
+    st.height.set(singledroplet(sys_.Lx, sys_.Ly, radius, θ0, center))
+    equilibrium(st, sys_)
+    area: list = []
+    time_loop(sys_, st, wetted, area, verbose=verbos)
+    return st.height, area
+
+
+def run_dropletpatterned(sys_: SysConst, device: str, radius=20, θ0=1 / 6, center=None, θs=None, verbos=True):
+    """run_dropletpatterned  src/simulate.jl:422-439 (θₛ: Lx x Ly NumPy array or Field of angles)"""
+    print("Simulating a droplet on a patterned substrate in two dimensions")
+    center = center or (sys_.Lx // 2, sys_.Ly // 2)
+    st = Sys(sys_, device)
+    st.height.set(singledroplet(sys_.Lx, sys_.Ly, radius, θ0, center))
+    equilibrium(st, sys_)
+    if θs is None:
+        θs = np.full((sys_.Lx, sys_.Ly), 1 / 9)
+    if not isinstance(θs, Field):
+        θs = Field(sys_.Lx, sys_.Ly).set(θs)
+    time_loop(sys_, st, θs, verbose=verbos)
+    return st.height
+
+
+def run_dropletforced(sys_: SysConst, device: str, radius=20, θ0=1 / 6, center=None, fx=0.0, fy=0.0, verbos=True):
+    """run_dropletforced  src/simulate.jl:462-484"""
+    bodyforce = [fx, fy]
+    print("Simulating a sliding droplet in two dimensions")
+    center = center or (sys_.Lx // 2, sys_.Ly // 2)
+    st = Sys(sys_, device)
+    st.height.set(singledroplet(sys_.Lx, sys_.Ly, radius, θ0, center))
+    equilibrium(st, sys_)
+    print("Starting the lattice Boltzmann time loop")
+    time_loop(sys_, st, inclination, bodyforce, verbose=verbos)
+    return st.height, st.velx, st.vely
+
+
+JULIA_NAMES = {
+    "equilibrium!": equilibrium, "BGKandStream!": BGKandStream, "moments!": moments, "filmpressure!": filmpressure,
+    "h∇p!": hgradp, "∇f!": gradf, "∇²f!": laplacianf, "slippage!": slippage, "slippage2!": slippage2,
+    "slippage_ring_riv!": slippage_ring_riv, "thermal!": thermal, "inclination!": inclination, "update!": update,
+    "wetted!": wetted, "snapshot!": snapshot, "time_loop": time_loop, "run_flat": run_flat, "run_random": run_random,
+    "run_rayleightaylor": run_rayleightaylor, "run_dropletrelax": run_dropletrelax,
+    "run_dropletpatterned": run_dropletpatterned, "run_dropletforced": run_dropletforced, "Sys": Sys,
+    "SysConst": SysConst, "Sys_const": Sys_const, "Taumucs": Taumucs, "CuState": CuState,
+    "CuState_thermal": CuState_thermal, "Swalbe_state": Swalbe_state,
+}

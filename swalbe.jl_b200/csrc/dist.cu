@@ -1,0 +1,301 @@
+// Multi-GPU slab runtime: row-slab decomposition along j, one process per GPU, periodic halo rows exchanged
+// with NCCL send/recv on a high-priority communication stream while the interior rows are updated.
+// The reference has no multi-GPU path -- this is new.
+//
+// Slab layout.  Every moment plane (h, ux, uy) of a rank is a (Ly_loc + 2*GH) x Lx array with GH = 3 ghost
+// rows below row 0 and above row Ly_loc-1: one fused step has dependency radius 3 in h (p <- h, ∇p <- p,
+// streaming <- f*), 1 in u.  For tau != 1 the population planes carry one ghost row on either side.
+// A halo "row" is a contiguous run of Lx doubles, so every message is one contiguous chunk.
+//
+// Per step:   (1) edge strips  [0,GH) and [Ly_loc-GH, Ly_loc)   on the compute stream
+//             (2) event -> NCCL group {send top/bottom edge rows, recv both ghost strips} on the comm stream
+//             (3) interior rows [GH, Ly_loc-GH)                 on the compute stream, overlapping (2)
+//             (4) next step's edge strips wait for (2).
+// With nranks == 1 the exchange degenerates to two device-to-device copies (self-neighbour), which also lets
+// the ghost-row kernel path be tested on a single GPU.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include "fused.cuh"
+#include "launch.h"
+
+namespace swalbe {
+
+constexpr int GH = 3;
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.handle) return 0;
+  // RTLD_NOLOAD first: inside a torch process this returns torch's already-loaded libnccl.so.2
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return set_error(SWALBE_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SW_SYM(name)                                                                      \
+  *(void **)(&g_nccl.name) = dlsym(h, "nccl" #name);                                      \
+  if (!g_nccl.name) return set_error(SWALBE_ERR_NCCL, "libnccl.so.2 lacks symbol nccl" #name)
+  SW_SYM(GetUniqueId); SW_SYM(CommInitRank); SW_SYM(CommDestroy); SW_SYM(Send); SW_SYM(Recv);
+  SW_SYM(GroupStart); SW_SYM(GroupEnd); SW_SYM(GetErrorString);
+#undef SW_SYM
+  g_nccl.handle = h;
+  return 0;
+}
+
+#define SW_NCCL(expr)                                                                                       \
+  do {                                                                                                      \
+    ncclResult_t _r = (expr);                                                                               \
+    if (_r != ncclSuccess)                                                                                  \
+      return set_error(SWALBE_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(_r), __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace swalbe
+
+using namespace swalbe;
+
+struct swalbe_dist {
+  int rank, nranks, Lx, Ly_global, Ly_loc, j_begin;
+  swalbe_params prm;
+  bool tau1, thermal;
+  size_t mplane;          // elements of one moment plane incl. ghosts
+  size_t fplane;          // elements of one population plane incl. ghosts
+  int gh_f;
+  double *m[2][3];        // ping-pong sets of (h, ux, uy)
+  double *f[2];           // population sets (tau == 1: only f[0], no ghosts)
+  int cur;                // index of the set holding the current moments
+  int fcur;               // index of the set holding the current populations (tau != 1)
+  ncclComm_t comm;
+  cudaStream_t s_comp, s_comm;
+  cudaEvent_t ev_edges, ev_halo, ev_t0, ev_t1, ev_user;
+  LaunchGeom g_int, g_edge;
+  FusedArgs base;
+  float last_ms;
+};
+
+static int exchange_rows(swalbe_dist *d, double *plane, int gh, size_t rows_total) {
+  // plane has rows [-gh, Ly_loc+gh) stored at physical rows [0, Ly_loc+2gh); send the gh top/bottom owned rows,
+  // receive the gh ghost rows on both sides.  up = rank+1 owns larger j, down = rank-1.
+  (void)rows_total;
+  const size_t n = (size_t)gh * d->Lx;
+  double *ghost_lo = plane;                                       // rows [-gh, 0)
+  double *own_lo = plane + (size_t)gh * d->Lx;                    // rows [0, gh)
+  double *own_hi = plane + (size_t)d->Ly_loc * d->Lx;             // rows [Ly_loc-gh, Ly_loc)
+  double *ghost_hi = plane + (size_t)(d->Ly_loc + gh) * d->Lx;    // rows [Ly_loc, Ly_loc+gh)
+  if (d->nranks == 1) {
+    SW_CUDA(cudaMemcpyAsync(ghost_lo, own_hi, n * sizeof(double), cudaMemcpyDeviceToDevice, d->s_comm));
+    SW_CUDA(cudaMemcpyAsync(ghost_hi, own_lo, n * sizeof(double), cudaMemcpyDeviceToDevice, d->s_comm));
+    return 0;
+  }
+  const int up = (d->rank + 1) % d->nranks, down = (d->rank + d->nranks - 1) % d->nranks;
+  SW_NCCL(g_nccl.Send(own_hi, n, ncclDouble, up, d->comm, d->s_comm));
+  SW_NCCL(g_nccl.Send(own_lo, n, ncclDouble, down, d->comm, d->s_comm));
+  SW_NCCL(g_nccl.Recv(ghost_lo, n, ncclDouble, down, d->comm, d->s_comm));
+  SW_NCCL(g_nccl.Recv(ghost_hi, n, ncclDouble, up, d->comm, d->s_comm));
+  return 0;
+}
+
+// halo exchange of moment set `set` (and population set `fset` when tau != 1) on the comm stream
+static int exchange_halos(swalbe_dist *d, int set, int fset) {
+  if (d->nranks > 1) SW_NCCL(g_nccl.GroupStart());
+  for (int q = 0; q < 3; ++q)
+    if (int e = exchange_rows(d, d->m[set][q], GH, d->Ly_loc + 2 * GH)) return e;
+  if (!d->tau1)
+    for (int k = 0; k < 9; ++k)
+      if (int e = exchange_rows(d, d->f[fset] + k * d->fplane, 1, d->Ly_loc + 2)) return e;
+  if (d->nranks > 1) SW_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
+extern "C" {
+
+int swalbe_dist_unique_id(void *id128) {
+  if (!id128) return set_error(SWALBE_ERR_ARG, "id buffer is NULL");
+  if (int e = load_nccl()) return e;
+  static_assert(sizeof(ncclUniqueId) == SWALBE_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  SW_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nranks, int Lx, int Ly_global,
+                       const swalbe_params *prm) {
+  if (!out || !prm) return set_error(SWALBE_ERR_ARG, "swalbe_dist_create: NULL argument");
+  if (int e = check_extent(Lx, Ly_global)) return e;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(SWALBE_ERR_ARG, "bad rank %d / nranks %d", rank, nranks);
+  if (Ly_global % nranks) return set_error(SWALBE_ERR_EXTENT, "Ly=%d is not divisible by nranks=%d", Ly_global, nranks);
+  const int Ly_loc = Ly_global / nranks;
+  if (Ly_loc < 2 * GH) return set_error(SWALBE_ERR_EXTENT, "slab of %d rows is thinner than 2x the halo depth %d", Ly_loc, GH);
+  if (nranks > 1 && !id128) return set_error(SWALBE_ERR_ARG, "nranks > 1 needs a NCCL unique id");
+  swalbe_dist *d = new swalbe_dist();
+  memset(d, 0, sizeof(*d));
+  d->rank = rank; d->nranks = nranks; d->Lx = Lx; d->Ly_global = Ly_global; d->Ly_loc = Ly_loc; d->j_begin = rank * Ly_loc;
+  d->prm = *prm;
+  d->tau1 = prm->tau == 1.0; d->thermal = prm->use_thermal != 0;
+  if (prm->cospi_theta_field) { delete d; return set_error(SWALBE_ERR_ARG, "theta fields are not supported by the slab runtime yet"); }
+  d->base = FusedArgs{};
+  if (int e = fill_consts(d->base, *prm)) { delete d; return e; }
+  d->mplane = (size_t)(Ly_loc + 2 * GH) * Lx;
+  d->gh_f = d->tau1 ? 0 : 1;
+  d->fplane = (size_t)(Ly_loc + 2 * d->gh_f) * Lx;
+  for (int s = 0; s < 2; ++s)
+    for (int q = 0; q < 3; ++q) {
+      SW_CUDA(cudaMalloc((void **)&d->m[s][q], d->mplane * sizeof(double)));
+      SW_CUDA(cudaMemset(d->m[s][q], 0, d->mplane * sizeof(double)));
+    }
+  for (int s = 0; s < (d->tau1 ? 1 : 2); ++s) {
+    SW_CUDA(cudaMalloc((void **)&d->f[s], 9 * d->fplane * sizeof(double)));
+    SW_CUDA(cudaMemset(d->f[s], 0, 9 * d->fplane * sizeof(double)));
+  }
+  int lo = 0, hi = 0;
+  SW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  SW_CUDA(cudaStreamCreateWithPriority(&d->s_comp, cudaStreamNonBlocking, lo));
+  SW_CUDA(cudaStreamCreateWithPriority(&d->s_comm, cudaStreamNonBlocking, hi));
+  SW_CUDA(cudaEventCreateWithFlags(&d->ev_edges, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&d->ev_user, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreate(&d->ev_t0));
+  SW_CUDA(cudaEventCreate(&d->ev_t1));
+  if (nranks > 1) {
+    if (int e = load_nccl()) return e;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    SW_NCCL(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
+  }
+  if (int e = choose_geometry(Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->tau1, d->thermal, &d->g_int)) return e;
+  if (int e = choose_geometry(Lx, GH, d->tau1, d->thermal, &d->g_edge)) return e;
+  d->cur = 0; d->fcur = 0;
+  *out = d;
+  return 0;
+}
+
+int swalbe_dist_destroy(swalbe_dist *d) {
+  if (!d) return 0;
+  cudaDeviceSynchronize();
+  if (d->comm) g_nccl.CommDestroy(d->comm);
+  for (int s = 0; s < 2; ++s) {
+    for (int q = 0; q < 3; ++q) cudaFree(d->m[s][q]);
+    cudaFree(d->f[s]);
+  }
+  cudaStreamDestroy(d->s_comp); cudaStreamDestroy(d->s_comm);
+  cudaEventDestroy(d->ev_edges); cudaEventDestroy(d->ev_halo); cudaEventDestroy(d->ev_user);
+  cudaEventDestroy(d->ev_t0); cudaEventDestroy(d->ev_t1);
+  delete d;
+  return 0;
+}
+
+int swalbe_dist_local_rows(const swalbe_dist *d, int *j_begin, int *j_count) {
+  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
+  if (j_begin) *j_begin = d->j_begin;
+  if (j_count) *j_count = d->Ly_loc;
+  return 0;
+}
+
+int swalbe_dist_set_state(swalbe_dist *d, const double *height, const double *velx, const double *vely,
+                          const double *ftemp, void *stream_) {
+  if (!d || !height || !velx || !vely) return set_error(SWALBE_ERR_ARG, "swalbe_dist_set_state: NULL argument");
+  if (!d->tau1 && !ftemp) return set_error(SWALBE_ERR_ARG, "tau != 1 needs the ftemp populations of the slab");
+  cudaStream_t user = (cudaStream_t)stream_;
+  const size_t n = (size_t)d->Ly_loc * d->Lx;
+  const double *src[3] = {height, velx, vely};
+  d->cur = 0; d->fcur = 0;
+  for (int q = 0; q < 3; ++q)
+    SW_CUDA(cudaMemcpyAsync(d->m[0][q] + (size_t)GH * d->Lx, src[q], n * sizeof(double), cudaMemcpyDeviceToDevice, user));
+  if (ftemp)
+    for (int k = 0; k < 9; ++k)
+      SW_CUDA(cudaMemcpyAsync(d->f[0] + k * d->fplane + (size_t)d->gh_f * d->Lx, ftemp + k * n, n * sizeof(double),
+                              cudaMemcpyDeviceToDevice, user));
+  SW_CUDA(cudaEventRecord(d->ev_user, user));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_user, 0));
+  if (int e = exchange_halos(d, 0, 0)) return e;
+  SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+  SW_CUDA(cudaStreamWaitEvent(user, d->ev_halo, 0));
+  return 0;
+}
+
+int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, void *stream_) {
+  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
+  if (nsteps <= 0) return 0;
+  cudaStream_t user = (cudaStream_t)stream_;
+  SW_CUDA(cudaEventRecord(d->ev_user, user));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_user, 0));
+  SW_CUDA(cudaEventRecord(d->ev_t0, d->s_comp));
+  const int Ly = d->Ly_loc;
+  for (int s = 0; s < nsteps; ++s) {
+    const int src = d->cur, dst = d->cur ^ 1;
+    FusedArgs a = d->base;
+    a.Lx = d->Lx; a.Ly = Ly; a.wrap_y = 0; a.gh_m = GH; a.gh_f = d->gh_f;
+    a.jglobal0 = d->j_begin; a.Ly_global = d->Ly_global;
+    a.h_in = d->m[src][0]; a.ux_in = d->m[src][1]; a.uy_in = d->m[src][2];
+    a.h_out = d->m[dst][0]; a.ux_out = d->m[dst][1]; a.uy_out = d->m[dst][2];
+    int fdst = 0;
+    if (d->tau1) { a.f_in = nullptr; a.f_out = d->f[0]; }
+    else { fdst = d->fcur ^ 1; a.f_in = d->f[d->fcur]; a.f_out = d->f[fdst]; }
+    a.fstride_in = a.fstride_out = a.fstride_out2 = d->fplane;
+    a.step = step0 + (unsigned long long)s;
+    // (1) edge strips -- they need the ghost rows of `src`, i.e. the previous exchange
+    SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+    a.W = d->g_edge.W; a.rows_per_cta = d->g_edge.rows_per_cta;
+    a.jbeg = 0; a.jend = GH;
+    if (int e = launch_fused(d->g_edge, a, d->tau1, d->thermal, d->s_comp)) return e;
+    a.jbeg = Ly - GH; a.jend = Ly;
+    if (int e = launch_fused(d->g_edge, a, d->tau1, d->thermal, d->s_comp)) return e;
+    SW_CUDA(cudaEventRecord(d->ev_edges, d->s_comp));
+    // (2) halo exchange of the freshly written edge rows of `dst`
+    SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_edges, 0));
+    if (int e = exchange_halos(d, dst, fdst)) return e;
+    SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
+    // (3) interior rows, overlapping the exchange
+    if (Ly > 2 * GH) {
+      a.W = d->g_int.W; a.rows_per_cta = d->g_int.rows_per_cta;
+      a.jbeg = GH; a.jend = Ly - GH;
+      if (int e = launch_fused(d->g_int, a, d->tau1, d->thermal, d->s_comp)) return e;
+    }
+    d->cur = dst;
+    if (!d->tau1) d->fcur = fdst;
+  }
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+  SW_CUDA(cudaEventRecord(d->ev_t1, d->s_comp));
+  SW_CUDA(cudaStreamWaitEvent(user, d->ev_t1, 0));
+  return 0;
+}
+
+int swalbe_dist_get_state(swalbe_dist *d, double *height, double *velx, double *vely, double *fout, void *stream_) {
+  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
+  cudaStream_t user = (cudaStream_t)stream_;
+  const size_t n = (size_t)d->Ly_loc * d->Lx;
+  double *dstp[3] = {height, velx, vely};
+  for (int q = 0; q < 3; ++q)
+    if (dstp[q])
+      SW_CUDA(cudaMemcpyAsync(dstp[q], d->m[d->cur][q] + (size_t)GH * d->Lx, n * sizeof(double), cudaMemcpyDeviceToDevice, user));
+  if (fout) {
+    const double *fs = d->tau1 ? d->f[0] : d->f[d->fcur];
+    for (int k = 0; k < 9; ++k)
+      SW_CUDA(cudaMemcpyAsync(fout + k * n, fs + k * d->fplane + (size_t)d->gh_f * d->Lx, n * sizeof(double),
+                              cudaMemcpyDeviceToDevice, user));
+  }
+  return 0;
+}
+
+int swalbe_dist_last_loop_ms(swalbe_dist *d, float *ms) {
+  if (!d || !ms) return set_error(SWALBE_ERR_ARG, "NULL argument");
+  SW_CUDA(cudaEventSynchronize(d->ev_t1));
+  SW_CUDA(cudaEventElapsedTime(ms, d->ev_t0, d->ev_t1));
+  d->last_ms = *ms;
+  return 0;
+}
+
+}  // extern "C"

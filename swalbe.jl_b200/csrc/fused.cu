@@ -1,0 +1,239 @@
+// Host side of the fused time loop: plan (scratch + launch geometry) and swalbe_time_loop.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "fused.cuh"
+#include "launch.h"
+
+namespace swalbe {
+
+__global__ void k_init_logs(double *mn, double *mx, unsigned long long *wet, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mn) { mn[i] = INFINITY; mx[i] = -INFINITY; }
+  if (wet) wet[i] = 0ull;
+}
+
+// ---- kernel variant table ------------------------------------------------------------------------
+typedef void (*fused_fn)(const FusedArgs);
+
+struct Variant {
+  int nt, minb;
+  fused_fn fn[2][2];  // [tau1][thermal]
+};
+
+#define SW_VARIANT(NT, MINB)                                                                         \
+  {                                                                                                  \
+    NT, MINB, {                                                                                      \
+      {k_fused_step<NT, MINB, false, false>, k_fused_step<NT, MINB, false, true>}, {                 \
+        k_fused_step<NT, MINB, true, false>, k_fused_step<NT, MINB, true, true>                      \
+      }                                                                                              \
+    }                                                                                                \
+  }
+
+static const Variant g_variants[] = {SW_VARIANT(128, 3), SW_VARIANT(192, 2), SW_VARIANT(256, 2)};
+static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
+
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+int choose_geometry(int Lx, int nrows, bool tau1, bool thermal, LaunchGeom *g) {
+  int dev = 0, nsm = 148;
+  SW_CUDA(cudaGetDevice(&dev));
+  SW_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int force_nt = env_int("SWALBE_NT", 0);
+  const int rmax = std::max(16, env_int("SWALBE_RMAX", 256));
+  double best_cost = 1e300;
+  for (int v = 0; v < g_nvariants; ++v) {
+    const Variant &var = g_variants[v];
+    if (force_nt && var.nt != force_nt) continue;
+    fused_fn fn = var.fn[tau1 ? 1 : 0][thermal ? 1 : 0];
+    int bps = 0;
+    SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, var.nt, 0));
+    if (bps < 1) continue;
+    const int wmax = var.nt - 8;
+    const int nstrips = (Lx + wmax - 1) / wmax;
+    int W = (Lx + nstrips - 1) / nstrips;
+    W = std::min(wmax, (W + 3) & ~3);
+    // rows per CTA: fill an integer number of waves of (nsm*bps) CTA slots, R <= rmax
+    const long long slots = (long long)nsm * bps;
+    int nchunks = std::max(1, (nrows + rmax - 1) / rmax);
+    for (int w = 1; w < 1024; ++w) {
+      const long long c = (w * slots) / nstrips;
+      if (c < 1) continue;
+      if (c >= nchunks) { nchunks = (int)std::min<long long>(c, nrows); break; }
+    }
+    int R = (nrows + nchunks - 1) / nchunks;
+    if (R < 16 && nrows >= 16) R = 16;
+    nchunks = (nrows + R - 1) / R;
+    // cost model: thread-rows executed (incl. halo columns and the 9-row pipeline fill) x wave quantisation
+    const long long ctas = (long long)nstrips * nchunks;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double cost = (double)waves * (double)bps * (double)var.nt * (double)(R + 9);  // thread-rows per SM
+    if (cost < best_cost) {
+      best_cost = cost;
+      g->nt = var.nt; g->variant = v; g->W = W; g->nstrips = nstrips; g->rows_per_cta = R; g->nchunks = nchunks;
+      g->blocks_per_sm = bps;
+    }
+  }
+  if (best_cost == 1e300) return set_error(SWALBE_ERR_CUDA, "no fused-kernel variant fits on this device");
+  if (int r = env_int("SWALBE_ROWS", 0)) { g->rows_per_cta = r; g->nchunks = (nrows + r - 1) / r; }
+  return 0;
+}
+
+int launch_fused(const LaunchGeom &g, const FusedArgs &a, bool tau1, bool thermal, cudaStream_t stream) {
+  const Variant &var = g_variants[g.variant];
+  fused_fn fn = var.fn[tau1 ? 1 : 0][thermal ? 1 : 0];
+  const int nrows = a.jend - a.jbeg;
+  if (nrows <= 0) return 0;
+  dim3 grid(g.nstrips, (nrows + a.rows_per_cta - 1) / a.rows_per_cta);
+  fn<<<grid, g.nt, 0, stream>>>(a);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int fill_consts(FusedArgs &a, const swalbe_params &p) {
+  if (int e = resolve_pmode(p.pressure_variant, p.n, p.m, &a.pc.pmode)) return e;
+  if (p.slip_variant < 0 || p.slip_variant > 2) return set_error(SWALBE_ERR_ARG, "unknown slip_variant %d", p.slip_variant);
+  if (!(p.tau > 0.0)) return set_error(SWALBE_ERR_ARG, "tau must be positive");
+  a.pc.gamma = p.gamma;
+  a.pc.kappa = host_kappa(p.cospi_theta, p.n, p.m, p.hmin);
+  a.pc.nm1 = (double)(p.n - 1); a.pc.mm1 = (double)(p.m - 1); a.pc.kden = (double)(p.n - p.m) * p.hmin;
+  a.pc.hmin = p.hmin; a.pc.hcrit = p.hcrit; a.pc.n = p.n; a.pc.m = p.m;
+  a.sc = make_slip(p.delta, p.mu, p.hcrit, p.slip_variant);
+  a.ec = make_eq(p.g);
+  a.tc = make_thermal(p.kbt, p.mu, p.delta);
+  volatile double it = 1.0 / p.tau;
+  volatile double om = 1.0 - it;
+  a.invtau = it; a.omega = om;
+  a.use_incl = p.use_inclination; a.incl_ax = p.incl_ax; a.incl_ay = p.incl_ay; a.incl_factor = p.incl_factor;
+  a.seed = p.seed;
+  return 0;
+}
+
+}  // namespace swalbe
+
+using namespace swalbe;
+
+struct swalbe_plan {
+  int Lx, Ly;
+  double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
+  LaunchGeom geom[2][2];
+  bool geom_ok[2][2];
+};
+
+extern "C" {
+
+int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly) {
+  if (!plan) return set_error(SWALBE_ERR_ARG, "plan is NULL");
+  if (int e = check_extent(Lx, Ly)) return e;
+  swalbe_plan *p = new swalbe_plan();
+  p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr;
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) p->geom_ok[i][j] = false;
+  cudaError_t e = cudaMalloc((void **)&p->scratch, sizeof(double) * 3 * (size_t)Lx * Ly);
+  if (e != cudaSuccess) {
+    delete p;
+    return set_error(SWALBE_ERR_CUDA, "cudaMalloc(plan scratch) failed: %s", cudaGetErrorString(e));
+  }
+  *plan = p;
+  return 0;
+}
+
+int swalbe_plan_destroy(swalbe_plan *plan) {
+  if (!plan) return 0;
+  cudaFree(plan->scratch);
+  delete plan;
+  return 0;
+}
+
+int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_params *prm, int nsteps,
+                     unsigned long long step0, int flags, const swalbe_loop_logs *logs, void *stream_) {
+  if (!plan || !st || !prm) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop: NULL plan/state/params");
+  if (nsteps < 0) return set_error(SWALBE_ERR_ARG, "nsteps < 0");
+  if (nsteps == 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int Lx = plan->Lx, Ly = plan->Ly;
+  const size_t N = (size_t)Lx * Ly;
+#define NEED(f) if (!st->f) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop: state." #f " is NULL")
+  NEED(fout); NEED(ftemp); NEED(feq); NEED(height); NEED(velx); NEED(vely); NEED(vsq); NEED(pressure);
+  NEED(Fx); NEED(Fy); NEED(slipx); NEED(slipy); NEED(hgradpx); NEED(hgradpy);
+#undef NEED
+  const bool tau1 = prm->tau == 1.0;
+  const bool thermal = prm->use_thermal != 0;
+  if (thermal && (!st->kbtx || !st->kbty)) return set_error(SWALBE_ERR_ARG, "thermal loop needs state.kbtx/kbty");
+  const bool lazy = (flags & SWALBE_LOOP_LAZY_POPULATIONS) != 0;
+  if (lazy && !tau1) return set_error(SWALBE_ERR_ARG, "SWALBE_LOOP_LAZY_POPULATIONS requires tau == 1");
+
+  FusedArgs a = {};
+  if (int e = fill_consts(a, *prm)) return e;
+  LaunchGeom &g = plan->geom[tau1][thermal];
+  if (!plan->geom_ok[tau1][thermal]) {
+    if (int e = choose_geometry(Lx, Ly, tau1, thermal, &g)) return e;
+    plan->geom_ok[tau1][thermal] = true;
+  }
+  a.Lx = Lx; a.Ly = Ly; a.jbeg = 0; a.jend = Ly; a.rows_per_cta = g.rows_per_cta; a.W = g.W;
+  a.wrap_y = 1; a.gh_m = 0; a.gh_f = 0; a.jglobal0 = 0; a.Ly_global = Ly;
+  a.fstride_in = a.fstride_out = a.fstride_out2 = N;
+  a.ct_field = prm->cospi_theta_field;
+
+  const bool log_mm = logs && logs->hmin && logs->hmax;
+  const bool log_wet = logs && logs->wetted;
+  if (logs && ((logs->hmin == nullptr) != (logs->hmax == nullptr)))
+    return set_error(SWALBE_ERR_ARG, "logs.hmin and logs.hmax must both be set or both NULL");
+  if (log_mm || log_wet) {
+    k_init_logs<<<(nsteps + 255) / 256, 256, 0, stream>>>(log_mm ? logs->hmin : nullptr, log_mm ? logs->hmax : nullptr,
+                                                            log_wet ? logs->wetted : nullptr, nsteps);
+    SW_LAUNCH_CHECK();
+    a.hthresh = logs->hthresh;
+  }
+
+  // moment ping-pong: the caller's planes (A) and the plan's scratch (B); arrange for the LAST step to land in A
+  double *A[3] = {st->height, st->velx, st->vely};
+  double *B[3] = {plan->scratch, plan->scratch + N, plan->scratch + 2 * N};
+  bool src_is_A = true;
+  if (nsteps & 1) {
+    for (int q = 0; q < 3; ++q) SW_CUDA(cudaMemcpyAsync(B[q], A[q], sizeof(double) * N, cudaMemcpyDeviceToDevice, stream));
+    src_is_A = false;
+  }
+  // population ping-pong (tau != 1): the reference reads ftemp; streamed result alternates fout/ftemp
+  bool fsrc_is_ftemp = true;
+
+  for (int s = 0; s < nsteps; ++s) {
+    const bool last = s == nsteps - 1;
+    double **src = src_is_A ? A : B, **dst = src_is_A ? B : A;
+    a.h_in = src[0]; a.ux_in = src[1]; a.uy_in = src[2];
+    a.h_out = dst[0]; a.ux_out = dst[1]; a.uy_out = dst[2];
+    if (tau1) {
+      a.f_in = nullptr;
+      a.f_out = (!lazy || last) ? st->fout : nullptr;
+      a.f_out2 = last ? st->ftemp : nullptr;  // fout == ftemp on return (src/collide.jl:103)
+    } else {
+      a.f_in = fsrc_is_ftemp ? st->ftemp : st->fout;
+      a.f_out = fsrc_is_ftemp ? st->fout : st->ftemp;
+      a.f_out2 = nullptr;
+    }
+    if (last) {  // materialise every intermediate field the reference's state would hold
+      a.pressure = st->pressure; a.hgx = st->hgradpx; a.hgy = st->hgradpy; a.slipx = st->slipx; a.slipy = st->slipy;
+      a.Fx = st->Fx; a.Fy = st->Fy; a.feq = st->feq; a.vsq = st->vsq;
+      a.kbtx = thermal ? st->kbtx : nullptr; a.kbty = thermal ? st->kbty : nullptr;
+    }
+    a.step = step0 + (unsigned long long)s;
+    a.log_min = log_mm ? logs->hmin + s : nullptr;
+    a.log_max = log_mm ? logs->hmax + s : nullptr;
+    a.log_wet = log_wet ? logs->wetted + s : nullptr;
+    if (int e = launch_fused(g, a, tau1, thermal, stream)) return e;
+    src_is_A = !src_is_A;
+    fsrc_is_ftemp = !fsrc_is_ftemp;
+  }
+  if (!tau1) {  // make fout == ftemp: the newest populations are in the array written last
+    double *newest = fsrc_is_ftemp ? st->ftemp : st->fout;  // (flag already flipped: source of the NEXT step)
+    double *other = fsrc_is_ftemp ? st->fout : st->ftemp;
+    SW_CUDA(cudaMemcpyAsync(other, newest, sizeof(double) * 9 * N, cudaMemcpyDeviceToDevice, stream));
+  }
+  return 0;
+}
+
+}  // extern "C"

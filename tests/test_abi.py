@@ -1,0 +1,96 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports exactly the symbols
+include/swalbe_b200.h declares, error codes work without a GPU, and the host mirror refuses a CPU path."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from swalbe_b200 import _lib
+
+    return _lib.load()
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "swalbe_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(swalbe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from swalbe_b200 import _lib
+
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/swalbe_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes table and header disagree"
+
+
+def test_version_and_error_string(lib):
+    assert lib.swalbe_version() == 100
+    assert isinstance(lib.swalbe_last_error(), bytes)
+
+
+def test_argument_errors_need_no_gpu(lib):
+    from swalbe_b200 import _lib
+
+    # bad extents / NULL pointers are rejected before any CUDA call
+    assert lib.swalbe_moments_d2q9(None, None, None, None, 0, 5, None) == _lib.ERR_EXTENT
+    assert lib.swalbe_moments_d2q9(None, None, None, None, 5, 5, None) == _lib.ERR_ARG
+    assert b"NULL" in lib.swalbe_last_error()
+    # DomainError for exponents the array-form pressure does not know (src/pressure.jl:101-107)
+    one = C.c_void_p(8)
+    rc = lib.swalbe_filmpressure(one, C.c_void_p(16), None, 1.0, 1.0, None, 4, 2, 0.1, 0.1, _lib.PRESSURE_FAST, 5, 5, None)
+    assert rc == _lib.ERR_DOMAIN and b"DomainError((4, 2))" in lib.swalbe_last_error()
+    with pytest.raises(_lib.DomainError):
+        _lib.check(rc)
+
+
+def test_struct_layouts_match_header():
+    from swalbe_b200 import _lib
+
+    assert C.sizeof(_lib.CState) == 17 * 8
+    assert C.sizeof(_lib.CParams) == 8 * 8 + 2 * 4 + 8 + 8 + 2 * 4 + 4 + 4 + 3 * 8 + 4 + 4 + 8
+    assert C.sizeof(_lib.CLogs) == 32
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    import swalbe_b200 as sw
+
+    sysc = sw.SysConst(Lx=5, Ly=5, param=sw.Taumucs())
+    with pytest.raises(sw.SwalbeError):
+        sw.Sys(sysc, "CPU")
+    if not torch.cuda.is_available():
+        with pytest.raises(sw.SwalbeError):
+            sw.Sys(sysc, "GPU")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "swalbe.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "oracle" not in text.lower() or f == "README.md", f"{f} mentions the oracle"
+
+
+def test_taumucs_defaults():
+    import swalbe_b200 as sw
+
+    p = sw.Taumucs()
+    assert p.Tmax == 1000 and p.tdump == 100 and p.tau == 1.0 and p.n == 9 and p.m == 3
+    assert p.mu.hex() == "0x1.5555555555557p-3"  # cs^2*(tau-0.5) is 2 ulp above 1/6 (src/initialize.jl:49)
+    assert p.theta == 1 / 9 and p.hmin == 0.1 and p.hcrit == 0.05 and p.gamma == 0.01 and p.delta == 1.0
+    with pytest.raises(TypeError):
+        sw.SysConst(Lx=5, Ly=5)

@@ -1,0 +1,266 @@
+"""Parity of the fused time loop (swalbe_time_loop, one fused kernel per step) with the oracle: every field of
+the state, bit for bit (numerically equal doubles), after N steps -- plus the reference's whole-loop known answers
+(test/simulate.jl) and size-independent properties at BASELINE sizes."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle_c as oc
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+STATE_FIELDS = ("height", "velx", "vely", "fout", "ftemp", "feq", "vsq", "pressure", "hgradpx", "hgradpy", "slipx",
+                "slipy", "Fx", "Fy")
+
+
+@pytest.fixture(scope="module")
+def sw():
+    import swalbe_b200
+
+    return swalbe_b200
+
+
+def _mk(sw, Lx, Ly, seed, prm_kw, tau_pops=False):
+    rng = np.random.default_rng(seed)
+    h0 = np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06)
+    ux0 = np.asfortranarray(0.01 * rng.standard_normal((Lx, Ly)))
+    uy0 = np.asfortranarray(0.01 * rng.standard_normal((Lx, Ly)))
+    ft0 = np.asfortranarray(0.1 + 0.01 * rng.random((Lx, Ly, 9)))
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = h0; ref.velx[...] = ux0; ref.vely[...] = uy0
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(**prm_kw))
+    st = sw.Sys(sysc, "GPU")
+    st.height.set(h0); st.velx.set(ux0); st.vely.set(uy0)
+    if tau_pops:
+        ref.ftemp[...] = ft0
+        st.ftemp.set(ft0)
+    okw = {{"γ": "gamma", "δ": "delta", "τ": "tau", "μ": "mu", "θ": "theta"}.get(k, k): v for k, v in prm_kw.items()}
+    return st, sysc, ref, onp.Params(**okw)
+
+
+def _compare(st, ref, fields=STATE_FIELDS, what=""):
+    for name in fields:
+        got, want = getattr(st, name).numpy(), getattr(ref, name)
+        assert np.array_equal(got, want, equal_nan=True), \
+            f"{what}{name}: {np.count_nonzero(got != want)} sites differ, max abs {np.nanmax(np.abs(got - want)):.3e}"
+
+
+@pytest.mark.parametrize("Lx,Ly", [(5, 5), (25, 26), (150, 200), (100, 96), (257, 19), (600, 40), (7, 300)])
+@pytest.mark.parametrize("nsteps", [1, 2, 7])
+def test_fused_loop_bitwise_default_params(sw, Lx, Ly, nsteps):
+    st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx * 1000 + Ly, prm_kw=dict(g=-0.001, γ=0.0005))
+    sw.fused_steps(st, sysc, nsteps)
+    oc.time_loop(ref, p, nsteps=nsteps)
+    _compare(st, ref)
+
+
+@pytest.mark.parametrize("prm_kw", [
+    dict(n=3, m=2, hmin=0.07, γ=0.01),
+    dict(n=4, m=2, δ=2.0),
+    dict(τ=0.75, g=0.002),
+    dict(τ=1.3, n=3, m=2),
+    dict(μ=1 / 12, δ=0.25, θ=1 / 6),
+], ids=lambda d: ",".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in d.items()))
+@pytest.mark.parametrize("nsteps", [1, 4, 5])
+def test_fused_loop_bitwise_param_sets(sw, prm_kw, nsteps):
+    st, sysc, ref, p = _mk(sw, 70, 45, seed=11, prm_kw=prm_kw, tau_pops="τ" in prm_kw)
+    sw.fused_steps(st, sysc, nsteps)
+    oc.time_loop(ref, p, nsteps=nsteps)
+    _compare(st, ref)
+
+
+def test_fused_loop_variants_theta_field_slip_inclination(sw):
+    Lx, Ly = 64, 50
+    rng = np.random.default_rng(3)
+    theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))
+    ct = np.asfortranarray(np.vectorize(sw.cospi)(theta))
+    for sv in (0, 1, 2):
+        st, sysc, ref, p = _mk(sw, Lx, Ly, seed=sv, prm_kw=dict(n=3, m=2, hmin=0.07))
+        thf = sw.Field(Lx, Ly).set(theta)
+        factor = 0.5 + 0.5 * math.tanh(1.0)
+        sw.fused_steps(st, sysc, 5, θ=thf, slip_variant=sv, incl=([1e-4, -2e-5], factor))
+        oc.time_loop(ref, p, nsteps=5, cospi_theta=ct, slip_variant=sv, incl=([1e-4, -2e-5], factor))
+        _compare(st, ref, what=f"slip{sv}:")
+    # array-form (fast_93) pressure through the fused loop, as CuState_thermal uses it (src/pressure.jl:117)
+    st, sysc, ref, p = _mk(sw, Lx, Ly, seed=9, prm_kw=dict())
+    from swalbe_b200 import _lib
+
+    sw.fused_steps(st, sysc, 3, pressure_variant=_lib.PRESSURE_FAST)
+    oc.time_loop(ref, p, nsteps=3, pvariant="fast")
+    _compare(st, ref, what="fast93:")
+
+
+def test_fused_equals_operator_by_operator_on_gpu(sw):
+    """The fused kernel against the seven per-operator kernels run in the reference's order (both on the GPU)."""
+    st, sysc, _, _ = _mk(sw, 130, 61, seed=21, prm_kw=dict(g=0.001))
+    st2, _, _, _ = _mk(sw, 130, 61, seed=21, prm_kw=dict(g=0.001))
+    sw.fused_steps(st, sysc, 6)
+    for _ in range(6):  # src/simulate.jl:15-22
+        sw.filmpressure(st2, sysc)
+        sw.hgradp(st2)
+        sw.slippage(st2, sysc)
+        sw.update(st2)
+        sw.equilibrium(st2, sysc)
+        sw.BGKandStream(st2, sysc)
+        sw.moments(st2)
+    for name in STATE_FIELDS:
+        assert np.array_equal(getattr(st, name).numpy(), getattr(st2, name).numpy()), name
+
+
+def test_lazy_populations_same_result(sw):
+    st, sysc, ref, p = _mk(sw, 90, 70, seed=5, prm_kw=dict())
+    sw.fused_steps(st, sysc, 9, lazy_populations=True)
+    oc.time_loop(ref, p, nsteps=9)
+    _compare(st, ref)
+    st3, sysc3, _, _ = _mk(sw, 20, 20, seed=5, prm_kw=dict(τ=0.8))
+    with pytest.raises(ValueError):
+        sw.fused_steps(st3, sysc3, 2, lazy_populations=True)
+
+
+def test_logs_minmax_wetted(sw):
+    st, sysc, ref, p = _mk(sw, 150, 33, seed=8, prm_kw=dict(g=-0.002))
+    mn, mx, wet = sw.fused_steps(st, sysc, 12, log_minmax=True, log_wetted=True, hthresh=1.0)
+    dh, w = oc.time_loop(ref, p, nsteps=12, log_dh=True, log_wetted=True, hthresh=1.0)
+    assert np.array_equal((mx - mn).cpu().numpy(), dh)
+    assert np.array_equal(wet.cpu().numpy(), w)
+
+
+def test_geometry_overrides_do_not_change_bits(sw, monkeypatch):
+    """Every CTA width / rows-per-CTA choice must give identical fields (tiling is not allowed to matter)."""
+    base = None
+    for nt, rows in [(128, 16), (192, 7), (256, 64), (128, 1000)]:
+        monkeypatch.setenv("SWALBE_NT", str(nt))
+        monkeypatch.setenv("SWALBE_ROWS", str(rows))
+        st, sysc, _, _ = _mk(sw, 300, 90, seed=2, prm_kw=dict(g=-0.001))
+        sw.fused_steps(st, sysc, 3)
+        cur = {n: getattr(st, n).numpy() for n in STATE_FIELDS}
+        if base is None:
+            base = cur
+        for n in STATE_FIELDS:
+            assert np.array_equal(base[n], cur[n]), (nt, rows, n)
+
+
+# ---- reference whole-loop known answers (test/simulate.jl) through the drop-in drivers ---------------------
+
+
+def test_run_flat_stays_exactly_flat(sw):  # test/simulate.jl:4-7
+    sysc = sw.SysConst(Lx=25, Ly=25, param=sw.Taumucs(Tmax=200, tdump=100))
+    h = sw.run_flat(sysc, "GPU", verbos=False).numpy()
+    assert np.all(h == 1.0) and h.sum() == 25 * 25
+
+
+def test_run_random_flattens(sw):  # test/simulate.jl:17-21
+    sysc = sw.SysConst(Lx=25, Ly=25, param=sw.Taumucs(Tmax=10000, tdump=5000))
+    h = sw.run_random(sysc, "GPU", ϵ=0.1, verbos=False, rng=np.random.default_rng(42)).numpy()
+    assert h.max() - h.min() < 0.1
+
+
+def test_run_rayleightaylor_grows_and_matches_oracle(sw):  # test/simulate.jl:33-35 + BASELINE config 1 (README)
+    sysc = sw.SysConst(Lx=100, Ly=100, param=sw.Taumucs(Tmax=1000, tdump=500, g=-0.002))
+    h, diff = sw.run_rayleightaylor(sysc, "GPU", kx=4, ky=5, ϵ=0.01, verbos=False)
+    assert len(diff) == 1000 and diff[0] < diff[-1]
+    p = onp.Params(Tmax=1000, tdump=500, g=-0.002)
+    ref = onp.State(100, 100)
+    ref.height[...] = onp.rayleightaylor_ic(100, 100, kx=4, ky=5, eps=0.01)
+    oc.equilibrium(ref.feq, ref.height, ref.velx, ref.vely, ref.vsq, p.g)
+    dh, _ = oc.time_loop(ref, p, log_dh=True)
+    assert np.array_equal(np.asarray(diff), dh)
+    assert np.array_equal(h.numpy(), ref.height)  # 0 ulp after 1000 steps
+
+
+def test_readme_rayleightaylor_config(sw):  # BASELINE.json configs[0]: Lx=Ly=100, g=-0.001, γ=0.0005, Tmax=1000
+    sysc = sw.SysConst(Lx=100, Ly=100, param=sw.Taumucs(Tmax=1000, g=-0.001, γ=0.0005))
+    h, diff = sw.run_rayleightaylor(sysc, "GPU", h0=1.0, ϵ=0.01, verbos=False)
+    p = onp.Params(Tmax=1000, g=-0.001, gamma=0.0005)
+    ref = onp.State(100, 100)
+    ref.height[...] = onp.rayleightaylor_ic(100, 100, kx=15, ky=18, eps=0.01)
+    oc.time_loop(ref, p)
+    hg = h.numpy()
+    rel = np.abs(hg - ref.height).max() / np.abs(ref.height).max()
+    assert rel <= 1e-12, rel            # north_star tolerance
+    assert np.array_equal(hg, ref.height)  # and in fact 0 ulp
+    assert abs(hg.sum() - 1e4) / 1e4 < 1e-12
+
+
+def test_run_dropletrelax(sw):  # test/simulate.jl:44-60 (shortened to 2000 steps for volume/area checks vs oracle)
+    sysc = sw.SysConst(Lx=150, Ly=150, param=sw.Taumucs(Tmax=2000, δ=3.0))
+    h, area = sw.run_dropletrelax(sysc, "GPU", radius=35, verbos=False)
+    p = onp.Params(Tmax=2000, delta=3.0)
+    ref = onp.State(150, 150)
+    ref.height[...] = onp.singledroplet(150, 150, 35, 1 / 6, (75, 75))
+    _, wet = oc.time_loop(ref, p, log_wetted=True, threads=oc.max_threads())
+    assert area == wet.tolist() and area[0] < area[-1]
+    assert np.array_equal(h.numpy(), ref.height)
+    m0 = onp.singledroplet(150, 150, 35, 1 / 6, (75, 75)).sum()
+    assert abs(h.numpy().sum() - m0) / m0 < 1e-12
+
+
+def test_run_dropletforced_moves_in_x_only(sw):  # test/simulate.jl:147-155
+    sysc = sw.SysConst(Lx=150, Ly=150, param=sw.Taumucs(Tmax=5000, δ=2.0))
+    h, ux, uy = sw.run_dropletforced(sysc, "GPU", radius=35, fx=1e-4, verbos=False)
+    hn = h.numpy()
+    i, j = np.unravel_index(np.argmax(hn), hn.shape)
+    assert i + 1 != 75 and j + 1 == 75
+    assert np.all(ux.numpy() < 0.1) and np.all(uy.numpy() < 0.1)
+
+
+def test_run_dropletpatterned(sw):  # test/simulate.jl:97-112 (radius/volume within 10 % after 10^4 steps)
+    sysc = sw.SysConst(Lx=150, Ly=150, param=sw.Taumucs(Tmax=10000, δ=3.0))
+    h = sw.run_dropletpatterned(sysc, "GPU", radius=35, θs=np.full((150, 150), 1 / 9), verbos=False).numpy()
+    c = sw.cospi
+    vol = np.pi / 3 * 35 ** 3 * (2 + c(1 / 6)) * (1 - c(1 / 6)) ** 2
+    R1 = np.cbrt((35 ** 3 * (2 + c(1 / 6)) * (1 - c(1 / 6)) ** 2) / ((2 + c(1 / 9)) * (1 - c(1 / 9)) ** 2))
+    r1 = np.sin(np.pi / 9) * R1
+    droprad = np.count_nonzero(h[74, :] > 0.055) / 2
+    droph = h.max()
+    vnum = 1 / 6 * np.pi * droph * (3 * droprad ** 2 + droph ** 2)
+    assert abs(vol - vnum) < vol / 10 and abs(r1 - droprad) < r1 / 10
+
+
+# ---- BASELINE sizes: oracle at 1024^2 for a few steps, size-independent properties at 4096^2 / 8192^2 --------
+
+
+def test_1024_droplet_bitwise_20_steps(sw):  # BASELINE configs[1] shape
+    Lx = Ly = 1024
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(n=3, m=2, hmin=0.07, δ=1.0))
+    st = sw.Sys(sysc, "GPU")
+    h0 = onp.singledroplet(Lx, Ly, 256, 1 / 6, (512, 512))
+    st.height.set(h0)
+    sw.equilibrium(st, sysc)
+    sw.fused_steps(st, sysc, 20)
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = h0
+    oc.time_loop(ref, onp.Params(n=3, m=2, hmin=0.07, delta=1.0), nsteps=20, threads=oc.max_threads())
+    _compare(st, ref, fields=("height", "velx", "vely", "pressure", "fout"))
+
+
+@pytest.mark.parametrize("L", [4096, 8192])
+def test_large_grid_properties(sw, L):
+    """Mass conservation to round-off, translation equivariance (periodic shift of the input == shift of the output,
+    bit for bit, which exercises every CTA seam) and flat-film invariance at BASELINE sizes."""
+    import torch
+
+    sysc = sw.SysConst(Lx=L, Ly=L, param=sw.Taumucs())
+    st = sw.Sys(sysc, "GPU")
+    i = torch.arange(L, device="cuda", dtype=torch.float64)
+    h0 = 1.0 + 1e-3 * torch.sin(2 * math.pi * i / L)[None, :] * torch.sin(2 * math.pi * i / L)[:, None]
+    h0 += 1e-4 * torch.rand((L, L), device="cuda", dtype=torch.float64, generator=torch.Generator("cuda").manual_seed(1))
+    st.height.t.copy_(h0)
+    m0 = st.height.t.sum().item()
+    sw.fused_steps(st, sysc, 10)
+    h1 = st.height.t.clone()
+    assert abs(h1.sum().item() - m0) / m0 < 1e-13
+    # shifted run
+    sx, sy = 1237, 411
+    st.height.t.copy_(torch.roll(h0, (sy, sx), (0, 1)))
+    st.velx.t.zero_(); st.vely.t.zero_()
+    sw.fused_steps(st, sysc, 10)
+    assert torch.equal(st.height.t, torch.roll(h1, (sy, sx), (0, 1)))
+    # flat film
+    st.height.t.fill_(1.0); st.velx.t.zero_(); st.vely.t.zero_()
+    sw.fused_steps(st, sysc, 5)
+    assert torch.all(st.height.t == 1.0)
+    del st
+    torch.cuda.empty_cache()
