@@ -237,13 +237,14 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
   for (int s = 0; s < nsteps; ++s) {
     const int src = d->cur, dst = d->cur ^ 1;
     FusedArgs a = d->base;
-    a.Lx = d->Lx; a.Ly = Ly; a.wrap_y = 0; a.gh_m = GH; a.gh_f = d->gh_f;
+    a.Lx = d->Lx; a.Ly = Ly; a.wrap_y = 0;  // ghost rows: pointers are handed over at logical row 0
     a.jglobal0 = d->j_begin; a.Ly_global = d->Ly_global;
-    a.h_in = d->m[src][0]; a.ux_in = d->m[src][1]; a.uy_in = d->m[src][2];
-    a.h_out = d->m[dst][0]; a.ux_out = d->m[dst][1]; a.uy_out = d->m[dst][2];
+    const size_t mo = (size_t)GH * d->Lx, fo = (size_t)d->gh_f * d->Lx;
+    a.h_in = d->m[src][0] + mo; a.ux_in = d->m[src][1] + mo; a.uy_in = d->m[src][2] + mo;
+    a.h_out = d->m[dst][0] + mo; a.ux_out = d->m[dst][1] + mo; a.uy_out = d->m[dst][2] + mo;
     int fdst = 0;
     if (d->tau1) { a.f_in = nullptr; a.f_out = d->f[0]; }
-    else { fdst = d->fcur ^ 1; a.f_in = d->f[d->fcur]; a.f_out = d->f[fdst]; }
+    else { fdst = d->fcur ^ 1; a.f_in = d->f[d->fcur] + fo; a.f_out = d->f[fdst] + fo; }
     a.fstride_in = a.fstride_out = a.fstride_out2 = d->fplane;
     a.step = step0 + (unsigned long long)s;
     // (1) edge strips -- they need the ghost rows of `src`, i.e. the previous exchange

@@ -23,16 +23,17 @@ struct Variant {
   fused_fn fn[2][2];  // [tau1][thermal]
 };
 
-#define SW_VARIANT(NT, MINB)                                                                         \
+// MB1: minimum CTAs/SM requested for the lean tau == 1 kernels, MB0: for the general-tau kernels (18 more registers)
+#define SW_VARIANT(NT, MB1, MB0)                                                                     \
   {                                                                                                  \
-    NT, MINB, {                                                                                      \
-      {k_fused_step<NT, MINB, false, false>, k_fused_step<NT, MINB, false, true>}, {                 \
-        k_fused_step<NT, MINB, true, false>, k_fused_step<NT, MINB, true, true>                      \
+    NT, MB1, {                                                                                       \
+      {k_fused_step<NT, MB0, false, false>, k_fused_step<NT, MB0, false, true>}, {                   \
+        k_fused_step<NT, MB1, true, false>, k_fused_step<NT, MB1, true, true>                        \
       }                                                                                              \
     }                                                                                                \
   }
 
-static const Variant g_variants[] = {SW_VARIANT(128, 3), SW_VARIANT(192, 2), SW_VARIANT(256, 2)};
+static const Variant g_variants[] = {SW_VARIANT(128, 4, 3), SW_VARIANT(192, 3, 2), SW_VARIANT(256, 2, 2)};
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static int env_int(const char *name, int dflt) {
@@ -52,7 +53,9 @@ int choose_geometry(int Lx, int nrows, bool tau1, bool thermal, LaunchGeom *g) {
     if (force_nt && var.nt != force_nt) continue;
     fused_fn fn = var.fn[tau1 ? 1 : 0][thermal ? 1 : 0];
     int bps = 0;
-    SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, var.nt, 0));
+    const size_t smem = fused_smem_doubles(var.nt) * sizeof(double);
+    SW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, var.nt, smem));
     if (bps < 1) continue;
     const int wmax = var.nt - 8;
     const int nstrips = (Lx + wmax - 1) / wmax;
@@ -90,7 +93,7 @@ int launch_fused(const LaunchGeom &g, const FusedArgs &a, bool tau1, bool therma
   const int nrows = a.jend - a.jbeg;
   if (nrows <= 0) return 0;
   dim3 grid(g.nstrips, (nrows + a.rows_per_cta - 1) / a.rows_per_cta);
-  fn<<<grid, g.nt, 0, stream>>>(a);
+  fn<<<grid, g.nt, fused_smem_doubles(g.nt) * sizeof(double), stream>>>(a);
   SW_LAUNCH_CHECK();
   return 0;
 }
@@ -175,7 +178,7 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
     plan->geom_ok[tau1][thermal] = true;
   }
   a.Lx = Lx; a.Ly = Ly; a.jbeg = 0; a.jend = Ly; a.rows_per_cta = g.rows_per_cta; a.W = g.W;
-  a.wrap_y = 1; a.gh_m = 0; a.gh_f = 0; a.jglobal0 = 0; a.Ly_global = Ly;
+  a.wrap_y = 1; a.jglobal0 = 0; a.Ly_global = Ly;
   a.fstride_in = a.fstride_out = a.fstride_out2 = N;
   a.ct_field = prm->cospi_theta_field;
 
