@@ -80,6 +80,7 @@ struct swalbe_dist {
   cudaStream_t s_comp, s_comm;
   cudaEvent_t ev_edges, ev_halo, ev_t0, ev_t1, ev_user;
   LaunchGeom g_int, g_edge;
+  KernelKey key;
   FusedArgs base;
   float last_ms;
 };
@@ -174,8 +175,9 @@ int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nrank
     memcpy(&id, id128, sizeof(id));
     SW_NCCL(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
   }
-  if (int e = choose_geometry(Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->tau1, d->thermal, &d->g_int)) return e;
-  if (int e = choose_geometry(Lx, GH, d->tau1, d->thermal, &d->g_edge)) return e;
+  d->key = make_key(*prm, d->base.pc.pmode, true);
+  if (int e = choose_geometry(Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
+  if (int e = choose_geometry(Lx, GH, d->key, &d->g_edge)) return e;
   d->cur = 0; d->fcur = 0;
   *out = d;
   return 0;
@@ -251,9 +253,9 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
     a.W = d->g_edge.W; a.rows_per_cta = d->g_edge.rows_per_cta;
     a.jbeg = 0; a.jend = GH;
-    if (int e = launch_fused(d->g_edge, a, d->tau1, d->thermal, d->s_comp)) return e;
+    if (int e = launch_fused(d->g_edge, a, d->key, d->s_comp)) return e;
     a.jbeg = Ly - GH; a.jend = Ly;
-    if (int e = launch_fused(d->g_edge, a, d->tau1, d->thermal, d->s_comp)) return e;
+    if (int e = launch_fused(d->g_edge, a, d->key, d->s_comp)) return e;
     SW_CUDA(cudaEventRecord(d->ev_edges, d->s_comp));
     // (2) halo exchange of the freshly written edge rows of `dst`
     SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_edges, 0));
@@ -263,7 +265,7 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     if (Ly > 2 * GH) {
       a.W = d->g_int.W; a.rows_per_cta = d->g_int.rows_per_cta;
       a.jbeg = GH; a.jend = Ly - GH;
-      if (int e = launch_fused(d->g_int, a, d->tau1, d->thermal, d->s_comp)) return e;
+      if (int e = launch_fused(d->g_int, a, d->key, d->s_comp)) return e;
     }
     d->cur = dst;
     if (!d->tau1) d->fcur = fdst;

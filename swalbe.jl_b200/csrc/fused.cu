@@ -19,39 +19,49 @@ __global__ void k_init_logs(double *mn, double *mx, unsigned long long *wet, int
 typedef void (*fused_fn)(const FusedArgs);
 
 struct Variant {
-  int nt, minb;
-  fused_fn fn[2][2];  // [tau1][thermal]
+  int nt;
+  fused_fn full[2][2];     // [tau1][thermal]           PM = -1: every option at run time
+  fused_fn lean[2][5];     // [thermal][pmode]          tau == 1 only, pmode in PM_BROAD_93..PM_FAST_32 (index 0 unused)
 };
 
-// MB1: minimum CTAs/SM requested for the lean tau == 1 kernels, MB0: for the general-tau kernels (18 more registers)
-#define SW_VARIANT(NT, MB1, MB0)                                                                     \
-  {                                                                                                  \
-    NT, MB1, {                                                                                       \
-      {k_fused_step<NT, MB0, false, false>, k_fused_step<NT, MB0, false, true>}, {                   \
-        k_fused_step<NT, MB1, true, false>, k_fused_step<NT, MB1, true, true>                        \
-      }                                                                                              \
-    }                                                                                                \
+// MB1: minimum CTAs/SM requested for the tau == 1 kernels, MB0: for the general-tau kernels (18 more registers)
+#define SW_VARIANT(NT, MB1, MB0)                                                                              \
+  {                                                                                                           \
+    NT,                                                                                                       \
+        {{k_fused_step<NT, MB0, false, false, -1>, k_fused_step<NT, MB0, false, true, -1>},                    \
+         {k_fused_step<NT, MB1, true, false, -1>, k_fused_step<NT, MB1, true, true, -1>}},                     \
+    {                                                                                                         \
+      {nullptr, k_fused_step<NT, MB1, true, false, PM_BROAD_93>, k_fused_step<NT, MB1, true, false, PM_BROAD_32>, \
+       k_fused_step<NT, MB1, true, false, PM_FAST_93>, k_fused_step<NT, MB1, true, false, PM_FAST_32>},        \
+      {nullptr, k_fused_step<NT, MB1, true, true, PM_BROAD_93>, k_fused_step<NT, MB1, true, true, PM_BROAD_32>, \
+       k_fused_step<NT, MB1, true, true, PM_FAST_93>, k_fused_step<NT, MB1, true, true, PM_FAST_32>}           \
+    }                                                                                                         \
   }
 
 static const Variant g_variants[] = {SW_VARIANT(128, 4, 3), SW_VARIANT(192, 3, 2), SW_VARIANT(256, 2, 2)};
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
+
+static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
+  if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm];
+  return var.full[k.tau1 ? 1 : 0][k.thermal ? 1 : 0];
+}
 
 static int env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return s && *s ? atoi(s) : dflt;
 }
 
-int choose_geometry(int Lx, int nrows, bool tau1, bool thermal, LaunchGeom *g) {
+int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   int dev = 0, nsm = 148;
   SW_CUDA(cudaGetDevice(&dev));
   SW_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int force_nt = env_int("SWALBE_NT", 0);
-  const int rmax = std::max(16, env_int("SWALBE_RMAX", 256));
+  const int rmax = std::max(16, env_int("SWALBE_RMAX", 128));
   double best_cost = 1e300;
   for (int v = 0; v < g_nvariants; ++v) {
     const Variant &var = g_variants[v];
     if (force_nt && var.nt != force_nt) continue;
-    fused_fn fn = var.fn[tau1 ? 1 : 0][thermal ? 1 : 0];
+    fused_fn fn = pick_kernel(var, key);
     int bps = 0;
     const size_t smem = fused_smem_doubles(var.nt) * sizeof(double);
     SW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -64,7 +74,7 @@ int choose_geometry(int Lx, int nrows, bool tau1, bool thermal, LaunchGeom *g) {
     // rows per CTA: fill an integer number of waves of (nsm*bps) CTA slots, R <= rmax
     const long long slots = (long long)nsm * bps;
     int nchunks = std::max(1, (nrows + rmax - 1) / rmax);
-    for (int w = 1; w < 1024; ++w) {
+    for (int w = 1; w < 4096; ++w) {
       const long long c = (w * slots) / nstrips;
       if (c < 1) continue;
       if (c >= nchunks) { nchunks = (int)std::min<long long>(c, nrows); break; }
@@ -72,10 +82,13 @@ int choose_geometry(int Lx, int nrows, bool tau1, bool thermal, LaunchGeom *g) {
     int R = (nrows + nchunks - 1) / nchunks;
     if (R < 16 && nrows >= 16) R = 16;
     nchunks = (nrows + R - 1) / R;
-    // cost model: thread-rows executed (incl. halo columns and the 9-row pipeline fill) x wave quantisation
+    // cost model: thread-rows executed per SM (incl. halo columns and the 10-row pipeline fill) x wave quantisation,
+    // discounted by the latency hiding that more resident warps buy (measured: 16-18 warps/SM is the sweet spot)
     const long long ctas = (long long)nstrips * nchunks;
     const long long waves = (ctas + slots - 1) / slots;
-    const double cost = (double)waves * (double)bps * (double)var.nt * (double)(R + 9);  // thread-rows per SM
+    const int warps = bps * var.nt / 32;
+    const double occ_penalty = warps >= 16 ? 1.0 : 16.0 / warps;
+    const double cost = (double)waves * (double)bps * (double)var.nt * (double)(R + 10) * occ_penalty;
     if (cost < best_cost) {
       best_cost = cost;
       g->nt = var.nt; g->variant = v; g->W = W; g->nstrips = nstrips; g->rows_per_cta = R; g->nchunks = nchunks;
@@ -87,15 +100,26 @@ int choose_geometry(int Lx, int nrows, bool tau1, bool thermal, LaunchGeom *g) {
   return 0;
 }
 
-int launch_fused(const LaunchGeom &g, const FusedArgs &a, bool tau1, bool thermal, cudaStream_t stream) {
-  const Variant &var = g_variants[g.variant];
-  fused_fn fn = var.fn[tau1 ? 1 : 0][thermal ? 1 : 0];
+int launch_fused(const LaunchGeom &g, const FusedArgs &a, const KernelKey &key, cudaStream_t stream) {
+  fused_fn fn = pick_kernel(g_variants[g.variant], key);
   const int nrows = a.jend - a.jbeg;
   if (nrows <= 0) return 0;
   dim3 grid(g.nstrips, (nrows + a.rows_per_cta - 1) / a.rows_per_cta);
   fn<<<grid, g.nt, fused_smem_doubles(g.nt) * sizeof(double), stream>>>(a);
   SW_LAUNCH_CHECK();
   return 0;
+}
+
+// the lean kernels cover: tau == 1, scalar theta, standard slip, no inclination, a known (n, m) pressure mode
+KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
+  KernelKey k;
+  k.tau1 = p.tau == 1.0;
+  k.thermal = p.use_thermal != 0;
+  k.lean_pm = 0;
+  if (want_lean && k.tau1 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
+      pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
+    k.lean_pm = pmode;
+  return k;
 }
 
 int fill_consts(FusedArgs &a, const swalbe_params &p) {
@@ -124,9 +148,19 @@ using namespace swalbe;
 struct swalbe_plan {
   int Lx, Ly;
   double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
-  LaunchGeom geom[2][2];
-  bool geom_ok[2][2];
+  LaunchGeom geom[2][2][5];  // [tau1][thermal][lean_pm]
+  bool geom_ok[2][2][5];
 };
+
+static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
+  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm];
+  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm]) {
+    if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
+    plan->geom_ok[k.tau1][k.thermal][k.lean_pm] = true;
+  }
+  *g = &gg;
+  return 0;
+}
 
 extern "C" {
 
@@ -135,7 +169,7 @@ int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly) {
   if (int e = check_extent(Lx, Ly)) return e;
   swalbe_plan *p = new swalbe_plan();
   p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr;
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) p->geom_ok[i][j] = false;
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 5; ++k) p->geom_ok[i][j][k] = false;
   cudaError_t e = cudaMalloc((void **)&p->scratch, sizeof(double) * 3 * (size_t)Lx * Ly);
   if (e != cudaSuccess) {
     delete p;
@@ -172,12 +206,13 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
 
   FusedArgs a = {};
   if (int e = fill_consts(a, *prm)) return e;
-  LaunchGeom &g = plan->geom[tau1][thermal];
-  if (!plan->geom_ok[tau1][thermal]) {
-    if (int e = choose_geometry(Lx, Ly, tau1, thermal, &g)) return e;
-    plan->geom_ok[tau1][thermal] = true;
-  }
-  a.Lx = Lx; a.Ly = Ly; a.jbeg = 0; a.jend = Ly; a.rows_per_cta = g.rows_per_cta; a.W = g.W;
+  const KernelKey key_full = make_key(*prm, a.pc.pmode, false);
+  const bool logs_on = logs && (logs->hmin || logs->wetted);
+  const KernelKey key_mid = make_key(*prm, a.pc.pmode, !logs_on);  // lean kernel for the steps before the last
+  LaunchGeom *g_full = nullptr, *g_mid = nullptr;
+  if (int e = plan_geometry(plan, key_full, &g_full)) return e;
+  if (int e = plan_geometry(plan, key_mid, &g_mid)) return e;
+  a.Lx = Lx; a.Ly = Ly; a.jbeg = 0; a.jend = Ly;
   a.wrap_y = 1; a.jglobal0 = 0; a.Ly_global = Ly;
   a.fstride_in = a.fstride_out = a.fstride_out2 = N;
   a.ct_field = prm->cospi_theta_field;
@@ -227,7 +262,9 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
     a.log_min = log_mm ? logs->hmin + s : nullptr;
     a.log_max = log_mm ? logs->hmax + s : nullptr;
     a.log_wet = log_wet ? logs->wetted + s : nullptr;
-    if (int e = launch_fused(g, a, tau1, thermal, stream)) return e;
+    const LaunchGeom &g = last ? *g_full : *g_mid;
+    a.rows_per_cta = g.rows_per_cta; a.W = g.W;
+    if (int e = launch_fused(g, a, last ? key_full : key_mid, stream)) return e;
     src_is_A = !src_is_A;
     fsrc_is_ftemp = !fsrc_is_ftemp;
   }

@@ -10,20 +10,27 @@
 // `rows_per_cta` rows.  The three dependent stencils are software-pipelined over rows through shared-memory
 // rings, one __syncthreads per row:
 //
-//   iteration t:  prefetch  h row N(t+D), u rows F(t+D)   global -> smem with cp.async (LDGSTS), D rows ahead,
+//   iteration t:  prefetch  h row N(t+1), u rows F(t+1)   global -> smem with cp.async (LDGSTS) one row ahead,
 //                                                          so no thread ever waits on a global load
 //                 B: film pressure   row P = j0-5+t        reads h rows P-1..P+1 from the h ring     -> p ring
 //                 C: forces, feq, f* row F = j0-7+t        reads p rows F-1..F+1, h and u of row F   -> f* rings
 //                 D: pull + moments  row O = j0-9+t        reads f* rows O-1..O+1 (x-shifted)        -> HBM
 //
-// B, C and D of one iteration read only rows written in EARLIER iterations, so the three instruction streams are
-// independent and interleave freely (ILP); nothing but addresses lives in registers across iterations except the
-// three own-column populations f*0, f*2, f*4.  Redundant work: the 8 halo columns per CTA and the 9-row pipeline
-// fill per chunk of rows; nothing is recomputed in y inside a chunk.
+// B, C and D of one iteration read only rows written in EARLIER iterations, so in the steady state (rows 9..R+5
+// of a chunk, instantiated without any stage predicate) the three instruction streams form one basic block and
+// interleave freely (ILP); nothing but addresses lives in registers across iterations.  Redundant work: the 8
+// halo columns per CTA and the 9-row pipeline fill per chunk of rows; nothing is recomputed in y inside a chunk.
+//
+// Two flavours per (NT, tau==1, thermal): PM >= 0 is the LEAN kernel for the steps in the middle of a
+// swalbe_time_loop call (scalar theta, standard slip, no inclination, no logs, no materialisation, pressure mode
+// PM fixed at compile time); PM == -1 is the FULL kernel with every option decided at run time (used for the
+// last step of a call, which materialises the reference's intermediate fields, and for all uncommon options).
 //
 // All arithmetic comes from common.cuh (reference evaluation order, no FMA contraction).
 #pragma once
 #include <limits.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -82,7 +89,7 @@ __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
 
 // 8-byte asynchronous global -> shared copy (LDGSTS); completion is tracked per thread by commit/wait groups,
 // not by the register scoreboard.
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+__device__ __forceinline__ void cp_async8(double *smem_dst, const void *gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
@@ -92,44 +99,45 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// A row cursor: logical row -> element offset of its first column, advanced one row per iteration with the
-// periodic wrap folded in (no integer division in the loop).  All of it is CTA-uniform.
+// A row cursor: BYTE offset of (row, own column) inside a plane, advanced one row per iteration with the periodic
+// wrap folded in (no integer division and no index->byte scaling inside the loop).
 struct RowCursor {
-  int r;          // physical row
-  long long off;  // r * Lx
-  __device__ __forceinline__ void init(int logical, int Lx, int Ly, int wrap_y) {
+  int r;          // physical row (CTA-uniform)
+  long long off;  // (r * Lx + ci) * 8
+  __device__ __forceinline__ void init(int logical, int Lx, int Ly, int wrap_y, int ci) {
     r = wrap_y ? wrapi(logical, Ly) : logical;
-    off = (long long)r * Lx;
+    off = ((long long)r * Lx + ci) * 8;
   }
-  __device__ __forceinline__ void advance(int Lx, int wrapLy) {
+  __device__ __forceinline__ void advance(long long row_bytes, int wrapLy, long long col_bytes) {
     ++r;
-    off += Lx;
-    if (r == wrapLy) { r = 0; off = 0; }
+    off += row_bytes;
+    if (r == wrapLy) { r = 0; off = col_bytes; }
   }
 };
+__device__ __forceinline__ const double *at(const double *base, long long byte_off) {
+  return (const double *)((const char *)base + byte_off);
+}
+__device__ __forceinline__ double *at(double *base, long long byte_off) { return (double *)((char *)base + byte_off); }
 
-constexpr int FUSED_D = 3;   // cp.async prefetch distance in rows
-constexpr int FUSED_SH = 8;  // h ring slots (rows N(t-3) .. N(t+D) are live: D+4 <= 8)
-constexpr int FUSED_SU = 4;  // u ring slots (rows F(t) .. F(t+D): D+1 <= 4)
-
+// shared-memory layout (in lines of LW = NT+2 doubles; every line has one pad cell on either side)
+//   h ring   : 8 slots x 1 line                         row N(t)  <-> slot t & 7
+//   ring-4   : 4 slots x 7 lines  P F1 F3 F5 F6 F0 F2   row P(t) / F(t) <-> slot t & 3
+//   ring-2   : 2 slots x 5 lines  F7 F8 F4 UX UY        row F(t) <-> slot t & 1
+constexpr int R4_P = 0, R4_F1 = 1, R4_F3 = 2, R4_F5 = 3, R4_F6 = 4, R4_F0 = 5, R4_F2 = 6, R4_LINES = 7;
+constexpr int R2_F7 = 0, R2_F8 = 1, R2_F4 = 2, R2_UX = 3, R2_UY = 4, R2_LINES = 5;
+constexpr int FUSED_H_SLOTS = 8;
 constexpr size_t fused_smem_doubles(int NT) {
-  // h ring + p ring + (f1,f3)[4] + (f5,f6)[4] + (f7,f8)[2] + u ring
-  return (size_t)(FUSED_SH + 4 + 8 + 8 + 4) * (NT + 2) + (size_t)FUSED_SU * 2 * NT;
+  return (size_t)(FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES) * (NT + 2);
 }
 
-template <int NT, int MINB, bool TAU1, bool THERMAL>
+template <int NT, int MINB, bool TAU1, bool THERMAL, int PM>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int D = FUSED_D, SH = FUSED_SH, SU = FUSED_SU, LW = NT + 2;
-  double *const s_h = smem;               // [SH][LW]   row N(t)  <-> slot t & 7
-  double *const s_p = s_h + SH * LW;      // [4][LW]    row P(t)  <-> slot t & 3
-  double *const s_f13 = s_p + 4 * LW;     // [4][2][LW] f*1,f*3 of row F(t) <-> slot t & 3   (read at t+2)
-  double *const s_f56 = s_f13 + 8 * LW;   // [4][2][LW] f*5,f*6             <-> slot t & 3   (read at t+3)
-  double *const s_f78 = s_f56 + 8 * LW;   // [2][2][LW] f*7,f*8             <-> slot t & 1   (read at t+1)
-  double *const s_u = s_f78 + 4 * LW;     // [SU][2][NT] ux,uy of row F(t)  <-> slot t & 3
+  constexpr bool LEAN = PM >= 0;
+  constexpr int LW = NT + 2;
+  constexpr int R4S = R4_LINES * LW, R2S = R2_LINES * LW;  // slot strides in doubles
 
   const int tid = threadIdx.x;
-  const int sm = tid + 1;
   const int s0 = blockIdx.x * a.W;
   const int Lx = a.Lx;
   const int ci = wrapi(s0 - 4 + tid, Lx);
@@ -137,86 +145,105 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   const int j0 = a.jbeg + blockIdx.y * a.rows_per_cta;
   const int R = min(a.rows_per_cta, a.jend - j0);
   const int wrapLy = a.wrap_y ? a.Ly : INT_MAX;
+  const long long row_bytes = (long long)Lx * 8, col_bytes = (long long)ci * 8;
+
+  double *const sh = smem + tid + 1;               // own column, h ring slot 0
+  double *const s4 = sh + FUSED_H_SLOTS * LW;      // own column, ring-4 slot 0, line 0
+  double *const s2 = s4 + 4 * R4S;                 // own column, ring-2 slot 0, line 0
 
   if (tid < 2) {  // the two pad cells of every line are never written by the pipeline; keep them finite
     const int e = tid ? NT + 1 : 0;
-    for (int q = 0; q < SH + 4 + 8 + 8 + 4; ++q) smem[q * LW + e] = 0.0;
+    for (int q = 0; q < FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES; ++q) smem[q * LW + e] = 0.0;
   }
 
   RowCursor cN, cU, cO, cC, cT;
-  cN.init(j0 - 4 - D + D, Lx, a.Ly, a.wrap_y);      // first prefetched h row: N(-D + D) = j0-4
-  cU.init(j0 - 7 - D + D, Lx, a.Ly, a.wrap_y);      // first prefetched u row: F(-D + D) = j0-7
-  cO.init(j0 - 9, Lx, a.Ly, a.wrap_y);              // output row O(0)
-  cC.init(j0 - 5, Lx, a.Ly, a.wrap_y);              // cospi(theta) field row P(0)
-  cT.init(j0 - 6, Lx, a.Ly, a.wrap_y);              // old populations (tau != 1): row F(1)
+  cN.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // h row N(0); prefetched one iteration ahead, starting at t = -1
+  cU.init(j0 - 7, Lx, a.Ly, a.wrap_y, ci);  // u row F(0)
+  cO.init(j0 - 9, Lx, a.Ly, a.wrap_y, ci);  // output row O(0)
+  cC.init(j0 - 5, Lx, a.Ly, a.wrap_y, ci);  // cospi(theta) field row P(0)
+  cT.init(j0 - 6, Lx, a.Ly, a.wrap_y, ci);  // old populations (tau != 1): row F(1)
 
-  // own-column populations that move along y only
-  double f0_a = 0, f0_b = 0, f2_a = 0, f2_b = 0, f2_c = 0, f4_a = 0;
   double ft_c[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) ft_c[k] = 0.0;
 
   double d_min = INFINITY, d_max = -INFINITY;
   unsigned int d_wet = 0;
-  const bool logging = a.log_min != nullptr || a.log_wet != nullptr;
-  const bool theta_field = a.ct_field != nullptr;
+  const bool logging = !LEAN && (a.log_min != nullptr || a.log_wet != nullptr);
+  const bool theta_field = !LEAN && a.ct_field != nullptr;
+  const bool aux = !LEAN && a.pressure != nullptr;
+  const int pmode = LEAN ? PM : a.pc.pmode;
+  const int slipv = LEAN ? SWALBE_SLIP_STANDARD : a.sc.variant;
+  const long long fs_in8 = (long long)a.fstride_in * 8, fs_out8 = (long long)a.fstride_out * 8,
+                  fs_out2_8 = (long long)a.fstride_out2 * 8;
 
-  const int t_end = R + 8;
-  for (int t = -D; t <= t_end; ++t) {
-    // ---- asynchronous prefetch, D rows ahead -------------------------------------------------------
+  // one pipeline iteration; `steady` is a compile-time tag: std::true_type drops every stage predicate
+  auto iter = [&](const int t, auto steady) {
+    constexpr bool S = decltype(steady)::value;
+    // ---- asynchronous prefetch of the next row ----------------------------------------------------------
     {
-      const int tn = t + D;               // h row N(tn) = j0-4+tn is needed for tn in [1, R+6]
-      if (tn >= 1 && tn <= R + 6) cp_async8(s_h + (tn & (SH - 1)) * LW + sm, a.h_in + cN.off + ci);
-      cN.advance(Lx, wrapLy);
-      if (tn >= 6 && tn <= R + 7) {       // u rows F(tn) = j0-7+tn in [j0-1, j0+R]
-        double *dst = s_u + (tn & (SU - 1)) * 2 * NT + tid;
-        cp_async8(dst, a.ux_in + cU.off + ci);
-        cp_async8(dst + NT, a.uy_in + cU.off + ci);
+      const int tn = t + 1;  // h row N(tn) = j0-4+tn is needed for tn in [1, R+6]; u rows F(tn) for tn in [6, R+7]
+      if (S || (tn >= 1 && tn <= R + 6)) cp_async8(sh + (tn & 7) * LW, at(a.h_in, cN.off));
+      cN.advance(row_bytes, wrapLy, col_bytes);
+      if (S || (tn >= 6 && tn <= R + 7)) {
+        double *dst = s2 + (tn & 1) * R2S;
+        cp_async8(dst + R2_UX * LW, at(a.ux_in, cU.off));
+        cp_async8(dst + R2_UY * LW, at(a.uy_in, cU.off));
       }
-      cU.advance(Lx, wrapLy);
+      cU.advance(row_bytes, wrapLy, col_bytes);
       cp_async_commit();
     }
-    if (t >= 0) {
-      // ---- register prefetch of data that is not staged through smem ----------------------------------
+    if (S || t >= 0) {
+      // ring slots of this iteration
+      double *const w4 = s4 + (t & 3) * R4S;               // written now: P(t), F(t)
+      const double *const a1 = s4 + ((t - 1) & 3) * R4S;   // age 1
+      const double *const a2 = s4 + ((t - 2) & 3) * R4S;   // age 2
+      const double *const a3 = s4 + ((t - 3) & 3) * R4S;   // age 3
+      double *const w2 = s2 + (t & 1) * R2S;               // written now: F7 F8 F4 of F(t); holds u of F(t)
+      const double *const o2 = s2 + ((t + 1) & 1) * R2S;   // age 1
+
+      // ---- register prefetch of data that is not staged through smem ------------------------------------
       double ct_c = 0.0;
-      const bool doB = t >= 3 && t <= R + 6;   // row P(t) = j0-5+t in [j0-2, j0+R+1]
-      if (theta_field && doB) ct_c = __ldg(a.ct_field + cC.off + ci);
-      cC.advance(Lx, wrapLy);
+      const bool doB = S || (t >= 3 && t <= R + 6);   // row P(t) = j0-5+t in [j0-2, j0+R+1]
+      if (!LEAN) {
+        if (theta_field && doB) ct_c = __ldg(at(a.ct_field, cC.off));
+        cC.advance(row_bytes, wrapLy, col_bytes);
+      }
       double ft_n[9];
       if (!TAU1) {
-        if (t >= 5 && t <= R + 6) {  // row F(t+1) = j0-6+t in [j0-1, j0+R]
+        if (S || (t >= 5 && t <= R + 6)) {  // row F(t+1) = j0-6+t in [j0-1, j0+R]
 #pragma unroll
-          for (int k = 0; k < 9; ++k) ft_n[k] = __ldg(a.f_in + k * a.fstride_in + cT.off + ci);
+          for (int k = 0; k < 9; ++k) ft_n[k] = __ldg(at(a.f_in, cT.off + k * fs_in8));
         }
-        cT.advance(Lx, wrapLy);
+        cT.advance(row_bytes, wrapLy, col_bytes);
       }
 
-      // ---- stage B: film pressure at row P(t) ----------------------------------------------------------
+      // ---- stage B: film pressure at row P(t) ------------------------------------------------------------
       if (doB) {
-        const double *r0 = s_h + ((t - 2) & (SH - 1)) * LW + sm;  // row P-1
-        const double *r1 = s_h + ((t - 1) & (SH - 1)) * LW + sm;  // row P
-        const double *r2 = s_h + (t & (SH - 1)) * LW + sm;        // row P+1
+        const double *r0 = sh + ((t - 2) & 7) * LW;  // row P-1
+        const double *r1 = sh + ((t - 1) & 7) * LW;  // row P
+        const double *r2 = sh + (t & 7) * LW;        // row P+1
         const double hc = r1[0];
         const double lap = lap9_bracket(hc, r1[-1], r0[0], r1[1], r2[0], r0[-1], r0[1], r2[1], r2[-1]);
         const double kappa = theta_field ? kappa_from_field(ct_c, a.pc) : a.pc.kappa;
-        s_p[(t & 3) * LW + sm] = film_pressure(hc, lap, kappa, a.pc);
+        const double x = a.pc.hmin / (hc + a.pc.hcrit);
+        const double pw = disjoining_powers(x, pmode, a.pc.n, a.pc.m);
+        w4[R4_P * LW] = (-a.pc.gamma * (kappa * pw)) - a.pc.gamma * lap;  // == film_pressure()
       }
 
       // ---- stage C: forces, equilibrium, collision at row F(t) = j0-7+t -----------------------------------
-      double fs0 = 0.0, fs2 = 0.0, fs4 = 0.0;
-      if (t >= 6 && t <= R + 7) {
-        const double *q0 = s_p + ((t - 3) & 3) * LW + sm;  // row F-1
-        const double *q1 = s_p + ((t - 2) & 3) * LW + sm;  // row F
-        const double *q2 = s_p + ((t - 1) & 3) * LW + sm;  // row F+1
-        const double hc = s_h[((t - 3) & (SH - 1)) * LW + sm];
-        const double ux_c = s_u[(t & (SU - 1)) * 2 * NT + tid];
-        const double uy_c = s_u[(t & (SU - 1)) * 2 * NT + NT + tid];
+      if (S || (t >= 6 && t <= R + 7)) {
+        const double *q0 = a3 + R4_P * LW;  // p row F-1
+        const double *q1 = a2 + R4_P * LW;  // p row F
+        const double *q2 = a1 + R4_P * LW;  // p row F+1
+        const double hc = sh[((t - 3) & 7) * LW];
+        const double ux_c = w2[R2_UX * LW], uy_c = w2[R2_UY * LW];
         const double pipjp = q0[-1], pimjp = q0[1], pimjm = q2[1], pipjm = q2[-1];
         const double gx = grad9_x(q1[-1], q1[1], pipjp, pimjp, pimjm, pipjm);
         const double gy = grad9_y(q0[0], q2[0], pipjp, pimjp, pimjm, pipjm);
         const double hgx = hc * gx, hgy = hc * gy;
         double sx, sy;
-        slip_terms(hc, ux_c, uy_c, a.sc, sx, sy);
+        slip_terms(hc, ux_c, uy_c, a.sc, slipv, sx, sy);
         double Fx = (-hgx) - sx, Fy = (-hgy) - sy;
         double kx = 0.0, ky = 0.0;
         const int rF = j0 - 7 + t;
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
           Fx = Fx - kx;
           Fy = Fy - ky;
         }
-        if (a.use_incl) {
+        if (!LEAN && a.use_incl) {
           Fx = Fx + (hc * a.incl_ax) * a.incl_factor;
           Fy = Fy + (hc * a.incl_ay) * a.incl_factor;
         }
@@ -239,71 +266,72 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         equilibrium_site(hc, ux_c, uy_c, a.ec, fe, vsq);
         if (TAU1) collide_site_tau1(fe, Fx, Fy, fs);
         else collide_site(ft_c, fe, Fx, Fy, a.omega, a.invtau, fs);
-        double *w13 = s_f13 + (t & 3) * 2 * LW + sm, *w56 = s_f56 + (t & 3) * 2 * LW + sm;
-        double *w78 = s_f78 + (t & 1) * 2 * LW + sm;
-        w13[0] = fs[1]; w13[LW] = fs[3];
-        w56[0] = fs[5]; w56[LW] = fs[6];
-        w78[0] = fs[7]; w78[LW] = fs[8];
-        fs0 = fs[0]; fs2 = fs[2]; fs4 = fs[4];
+        w4[R4_F0 * LW] = fs[0]; w4[R4_F1 * LW] = fs[1]; w4[R4_F2 * LW] = fs[2]; w4[R4_F3 * LW] = fs[3];
+        w4[R4_F5 * LW] = fs[5]; w4[R4_F6 * LW] = fs[6];
+        w2[R2_F4 * LW] = fs[4]; w2[R2_F7 * LW] = fs[7]; w2[R2_F8 * LW] = fs[8];
 
-        const bool own = col_out && t >= 7 && t <= R + 6;  // row F(t) in [j0, j0+R-1]
-        if (own) {
-          if (logging) {
-            d_min = fmin(d_min, hc);
-            d_max = fmax(d_max, hc);
-            d_wet += hc > a.hthresh;
-          }
-          if (a.pressure != nullptr) {  // materialise the reference's intermediate fields (last step of a call)
-            const size_t o = (size_t)rF * Lx + ci;
-            const size_t N = (size_t)Lx * a.Ly;
-            a.pressure[o] = q1[0];
-            a.hgx[o] = hgx; a.hgy[o] = hgy;
-            a.slipx[o] = sx; a.slipy[o] = sy;
-            a.Fx[o] = Fx; a.Fy[o] = Fy;
-            a.vsq[o] = vsq;
+        if (!LEAN) {
+          const bool own = col_out && t >= 7 && t <= R + 6;  // row F(t) in [j0, j0+R-1]
+          if (own) {
+            if (logging) {
+              d_min = fmin(d_min, hc);
+              d_max = fmax(d_max, hc);
+              d_wet += hc > a.hthresh;
+            }
+            if (aux) {  // materialise the reference's intermediate fields (last step of a call)
+              const size_t o = (size_t)rF * Lx + ci;
+              const size_t N = (size_t)Lx * a.Ly;
+              a.pressure[o] = q1[0];
+              a.hgx[o] = hgx; a.hgy[o] = hgy;
+              a.slipx[o] = sx; a.slipy[o] = sy;
+              a.Fx[o] = Fx; a.Fy[o] = Fy;
+              a.vsq[o] = vsq;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a.feq[o + k * N] = fe[k];
-            if (THERMAL && a.kbtx != nullptr) { a.kbtx[o] = kx; a.kbty[o] = ky; }
+              for (int k = 0; k < 9; ++k) a.feq[o + k * N] = fe[k];
+              if (THERMAL && a.kbtx != nullptr) { a.kbtx[o] = kx; a.kbty[o] = ky; }
+            }
           }
         }
       }
 
-      // ---- stage D: pull-stream + moments at row O(t) = j0-9+t ---------------------------------------------
-      if (t >= 9 && col_out) {
-        const double *m = s_f13 + ((t - 2) & 3) * 2 * LW + sm;  // row O
-        const double *b = s_f56 + ((t - 3) & 3) * 2 * LW + sm;  // row O-1 (moving +y)
-        const double *u = s_f78 + ((t - 1) & 1) * 2 * LW + sm;  // row O+1 (moving -y)
+      // ---- stage D: pull-stream + moments at row O(t) = j0-9+t --------------------------------------------
+      if (S || t >= 9) {
         double fn[9];
-        fn[0] = f0_b;      fn[1] = m[-1];      fn[3] = m[LW + 1];
-        fn[2] = f2_c;      fn[5] = b[-1];      fn[6] = b[LW + 1];
-        fn[4] = f4_a;      fn[7] = u[1];       fn[8] = u[LW - 1];
+        fn[0] = a2[R4_F0 * LW];      fn[1] = a2[R4_F1 * LW - 1];  fn[3] = a2[R4_F3 * LW + 1];  // row O
+        fn[2] = a3[R4_F2 * LW];      fn[5] = a3[R4_F5 * LW - 1];  fn[6] = a3[R4_F6 * LW + 1];  // row O-1, moving +y
+        fn[4] = o2[R2_F4 * LW];      fn[7] = o2[R2_F7 * LW + 1];  fn[8] = o2[R2_F8 * LW - 1];  // row O+1, moving -y
         double hn, uxn, uyn;
         moments_site(fn, hn, uxn, uyn);
-        const long long o = cO.off + ci;
-        a.h_out[o] = hn; a.ux_out[o] = uxn; a.uy_out[o] = uyn;
-        if (a.f_out != nullptr) {
+        if (col_out) {
+          *at(a.h_out, cO.off) = hn; *at(a.ux_out, cO.off) = uxn; *at(a.uy_out, cO.off) = uyn;
+          if (a.f_out != nullptr) {
 #pragma unroll
-          for (int k = 0; k < 9; ++k) a.f_out[(long long)(k * a.fstride_out) + o] = fn[k];
-          if (a.f_out2 != nullptr) {
+            for (int k = 0; k < 9; ++k) *at(a.f_out, cO.off + k * fs_out8) = fn[k];
+            if (!LEAN && a.f_out2 != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a.f_out2[(long long)(k * a.fstride_out2) + o] = fn[k];
+              for (int k = 0; k < 9; ++k) *at(a.f_out2, cO.off + k * fs_out2_8) = fn[k];
+            }
           }
         }
       }
-      cO.advance(Lx, wrapLy);
-      f0_b = f0_a; f0_a = fs0;
-      f2_c = f2_b; f2_b = f2_a; f2_a = fs2;
-      f4_a = fs4;
+      cO.advance(row_bytes, wrapLy, col_bytes);
       if (!TAU1) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) ft_c[k] = ft_n[k];
       }
     }
-    cp_async_wait<D - 1>();  // the group issued D-1 iterations ago (h row N(t+1), u rows F(t+1)) has landed
+    cp_async_wait<0>();  // this iteration's prefetch (h row N(t+1), u rows F(t+1)) has landed
     __syncthreads();
-  }
+  };
 
-  if (logging) {  // CTA reduction of the pre-step height statistics, one atomic per CTA
+  // pipeline fill (predicated), steady state (predicate-free), drain (predicated)
+  const int t_end = R + 8;
+  int t = -1;
+  for (; t < 9 && t <= t_end; ++t) iter(t, std::false_type{});
+  for (; t <= R + 5; ++t) iter(t, std::true_type{});
+  for (; t <= t_end; ++t) iter(t, std::false_type{});
+
+  if (!LEAN && logging) {  // CTA reduction of the pre-step height statistics, one atomic per CTA
     __shared__ double r_min[NT / 32], r_max[NT / 32];
     __shared__ unsigned int r_wet[NT / 32];
 #pragma unroll

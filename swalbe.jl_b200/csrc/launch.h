@@ -16,12 +16,19 @@ struct LaunchGeom {
   int blocks_per_sm;  // occupancy of the chosen variant
 };
 
-int choose_geometry(int Lx, int nrows, bool tau1, bool thermal, LaunchGeom *g);
-int launch_fused(const LaunchGeom &g, const FusedArgs &a, bool tau1, bool thermal, cudaStream_t stream);
+// which kernel instantiation: lean_pm > 0 selects the lean tau==1 kernel compiled for that pressure mode
+struct KernelKey {
+  bool tau1, thermal;
+  int lean_pm;
+};
+
+int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);
+int launch_fused(const LaunchGeom &g, const FusedArgs &a, const KernelKey &key, cudaStream_t stream);
 
 }  // namespace swalbe
 
 struct swalbe_params;
 namespace swalbe {
 int fill_consts(FusedArgs &a, const swalbe_params &p);
+KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean);
 }

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(BX *BY) k_slippage(double *__restrict__ sx, do
                                                       const double *__restrict__ uy, SlipConsts sc, int Lx, int Ly) {
   SITE_GUARD();
   double a, b;
-  slip_terms(h[c], ux[c], uy[c], sc, a, b);
+  slip_terms(h[c], ux[c], uy[c], sc, sc.variant, a, b);
   sx[c] = a; sy[c] = b;
 }
 
