@@ -38,7 +38,7 @@ struct Variant {
     }                                                                                                         \
   }
 
-static const Variant g_variants[] = {SW_VARIANT(128, 4, 3), SW_VARIANT(192, 3, 2), SW_VARIANT(256, 2, 2)};
+static const Variant g_variants[] = {SW_VARIANT(128, 5, 3), SW_VARIANT(192, 3, 2), SW_VARIANT(256, 2, 2)};
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {

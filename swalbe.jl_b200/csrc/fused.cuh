@@ -10,13 +10,13 @@
 // `rows_per_cta` rows.  The three dependent stencils are software-pipelined over rows through shared-memory
 // rings, one __syncthreads per row:
 //
-//   iteration t:  prefetch  h row N(t+1), u rows F(t+1)   global -> smem with cp.async (LDGSTS) one row ahead,
+//   iteration t:  prefetch  h row N(t+D), u rows F(t+D)   global -> smem with cp.async (LDGSTS) D rows ahead,
 //                                                          so no thread ever waits on a global load
 //                 B: film pressure   row P = j0-5+t        reads h rows P-1..P+1 from the h ring     -> p ring
 //                 C: forces, feq, f* row F = j0-7+t        reads p rows F-1..F+1, h and u of row F   -> f* rings
 //                 D: pull + moments  row O = j0-9+t        reads f* rows O-1..O+1 (x-shifted)        -> HBM
 //
-// B, C and D of one iteration read only rows written in EARLIER iterations, so in the steady state (rows 9..R+5
+// B, C and D of one iteration read only rows written in EARLIER iterations, so in the steady state (rows 9..R+4
 // of a chunk, instantiated without any stage predicate) the three instruction streams form one basic block and
 // interleave freely (ILP); nothing but addresses lives in registers across iterations.  Redundant work: the 8
 // halo columns per CTA and the 9-row pipeline fill per chunk of rows; nothing is recomputed in y inside a chunk.
@@ -120,22 +120,26 @@ __device__ __forceinline__ const double *at(const double *base, long long byte_o
 __device__ __forceinline__ double *at(double *base, long long byte_off) { return (double *)((char *)base + byte_off); }
 
 // shared-memory layout (in lines of LW = NT+2 doubles; every line has one pad cell on either side)
-//   h ring   : 8 slots x 1 line                         row N(t)  <-> slot t & 7
-//   ring-4   : 4 slots x 7 lines  P F1 F3 F5 F6 F0 F2   row P(t) / F(t) <-> slot t & 3
-//   ring-2   : 2 slots x 5 lines  F7 F8 F4 UX UY        row F(t) <-> slot t & 1
-constexpr int R4_P = 0, R4_F1 = 1, R4_F3 = 2, R4_F5 = 3, R4_F6 = 4, R4_F0 = 5, R4_F2 = 6, R4_LINES = 7;
-constexpr int R2_F7 = 0, R2_F8 = 1, R2_F4 = 2, R2_UX = 3, R2_UY = 4, R2_LINES = 5;
+//   h ring   : 8 slots x 1 line               row N(t) <-> slot t & 7   (rows N(t-3) .. N(t+D) are live)
+//   ring-4   : 4 slots x 5 lines  P F1 F3 F5 F6   row P(t) / F(t) <-> slot t & 3
+//   ring-2   : 2 slots x 2 lines  F7 F8           row F(t) <-> slot t & 1
+//   u ring   : 4 slots x 2 lines  UX UY           row F(t) <-> slot t & 3   (rows F(t) .. F(t+D) are live)
+// f*0, f*2, f*4 never leave their column and are parked in registers instead.
+constexpr int FUSED_D = 2;  // cp.async prefetch distance in rows (D+4 <= 8 h slots, D+1 <= 4 u slots)
+constexpr int R4_P = 0, R4_F1 = 1, R4_F3 = 2, R4_F5 = 3, R4_F6 = 4, R4_LINES = 5;
+constexpr int R2_F7 = 0, R2_F8 = 1, R2_LINES = 2;
+constexpr int RU_UX = 0, RU_UY = 1, RU_LINES = 2;
 constexpr int FUSED_H_SLOTS = 8;
-constexpr size_t fused_smem_doubles(int NT) {
-  return (size_t)(FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES) * (NT + 2);
-}
+constexpr int FUSED_LINES = FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES + 4 * RU_LINES;
+constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2); }
 
 template <int NT, int MINB, bool TAU1, bool THERMAL, int PM>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(16) double smem[];
   constexpr bool LEAN = PM >= 0;
   constexpr int LW = NT + 2;
-  constexpr int R4S = R4_LINES * LW, R2S = R2_LINES * LW;  // slot strides in doubles
+  constexpr int D = FUSED_D;
+  constexpr int R4S = R4_LINES * LW, R2S = R2_LINES * LW, RUS = RU_LINES * LW;  // slot strides in doubles
 
   const int tid = threadIdx.x;
   const int s0 = blockIdx.x * a.W;
@@ -150,19 +154,22 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   double *const sh = smem + tid + 1;               // own column, h ring slot 0
   double *const s4 = sh + FUSED_H_SLOTS * LW;      // own column, ring-4 slot 0, line 0
   double *const s2 = s4 + 4 * R4S;                 // own column, ring-2 slot 0, line 0
+  double *const su = s2 + 2 * R2S;                 // own column, u ring slot 0, line 0
 
   if (tid < 2) {  // the two pad cells of every line are never written by the pipeline; keep them finite
     const int e = tid ? NT + 1 : 0;
-    for (int q = 0; q < FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES; ++q) smem[q * LW + e] = 0.0;
+    for (int q = 0; q < FUSED_LINES; ++q) smem[q * LW + e] = 0.0;
   }
 
   RowCursor cN, cU, cO, cC, cT;
-  cN.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // h row N(0); prefetched one iteration ahead, starting at t = -1
+  cN.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // h row N(0); prefetched D iterations ahead, starting at t = -D
   cU.init(j0 - 7, Lx, a.Ly, a.wrap_y, ci);  // u row F(0)
   cO.init(j0 - 9, Lx, a.Ly, a.wrap_y, ci);  // output row O(0)
   cC.init(j0 - 5, Lx, a.Ly, a.wrap_y, ci);  // cospi(theta) field row P(0)
   cT.init(j0 - 6, Lx, a.Ly, a.wrap_y, ci);  // old populations (tau != 1): row F(1)
 
+  // own-column populations that move along y only: f*0 of rows F(t-1), F(t-2); f*2 of F(t-1..t-3); f*4 of F(t-1)
+  double f0_a = 0, f0_b = 0, f2_a = 0, f2_b = 0, f2_c = 0, f4_a = 0;
   double ft_c[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) ft_c[k] = 0.0;
@@ -182,13 +189,13 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     constexpr bool S = decltype(steady)::value;
     // ---- asynchronous prefetch of the next row ----------------------------------------------------------
     {
-      const int tn = t + 1;  // h row N(tn) = j0-4+tn is needed for tn in [1, R+6]; u rows F(tn) for tn in [6, R+7]
+      const int tn = t + D;  // h row N(tn) = j0-4+tn is needed for tn in [1, R+6]; u rows F(tn) for tn in [6, R+7]
       if (S || (tn >= 1 && tn <= R + 6)) cp_async8(sh + (tn & 7) * LW, at(a.h_in, cN.off));
       cN.advance(row_bytes, wrapLy, col_bytes);
       if (S || (tn >= 6 && tn <= R + 7)) {
-        double *dst = s2 + (tn & 1) * R2S;
-        cp_async8(dst + R2_UX * LW, at(a.ux_in, cU.off));
-        cp_async8(dst + R2_UY * LW, at(a.uy_in, cU.off));
+        double *dst = su + (tn & 3) * RUS;
+        cp_async8(dst + RU_UX * LW, at(a.ux_in, cU.off));
+        cp_async8(dst + RU_UY * LW, at(a.uy_in, cU.off));
       }
       cU.advance(row_bytes, wrapLy, col_bytes);
       cp_async_commit();
@@ -199,8 +206,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
       const double *const a1 = s4 + ((t - 1) & 3) * R4S;   // age 1
       const double *const a2 = s4 + ((t - 2) & 3) * R4S;   // age 2
       const double *const a3 = s4 + ((t - 3) & 3) * R4S;   // age 3
-      double *const w2 = s2 + (t & 1) * R2S;               // written now: F7 F8 F4 of F(t); holds u of F(t)
+      double *const w2 = s2 + (t & 1) * R2S;               // written now: F7 F8 of F(t)
       const double *const o2 = s2 + ((t + 1) & 1) * R2S;   // age 1
+      const double *const ur = su + (t & 3) * RUS;         // u of row F(t)
 
       // ---- register prefetch of data that is not staged through smem ------------------------------------
       double ct_c = 0.0;
@@ -232,12 +240,13 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
       }
 
       // ---- stage C: forces, equilibrium, collision at row F(t) = j0-7+t -----------------------------------
+      double fs0 = 0.0, fs2 = 0.0, fs4 = 0.0;
       if (S || (t >= 6 && t <= R + 7)) {
         const double *q0 = a3 + R4_P * LW;  // p row F-1
         const double *q1 = a2 + R4_P * LW;  // p row F
         const double *q2 = a1 + R4_P * LW;  // p row F+1
         const double hc = sh[((t - 3) & 7) * LW];
-        const double ux_c = w2[R2_UX * LW], uy_c = w2[R2_UY * LW];
+        const double ux_c = ur[RU_UX * LW], uy_c = ur[RU_UY * LW];
         const double pipjp = q0[-1], pimjp = q0[1], pimjm = q2[1], pipjm = q2[-1];
         const double gx = grad9_x(q1[-1], q1[1], pipjp, pimjp, pimjm, pipjm);
         const double gy = grad9_y(q0[0], q2[0], pipjp, pimjp, pimjm, pipjm);
@@ -266,9 +275,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         equilibrium_site(hc, ux_c, uy_c, a.ec, fe, vsq);
         if (TAU1) collide_site_tau1(fe, Fx, Fy, fs);
         else collide_site(ft_c, fe, Fx, Fy, a.omega, a.invtau, fs);
-        w4[R4_F0 * LW] = fs[0]; w4[R4_F1 * LW] = fs[1]; w4[R4_F2 * LW] = fs[2]; w4[R4_F3 * LW] = fs[3];
-        w4[R4_F5 * LW] = fs[5]; w4[R4_F6 * LW] = fs[6];
-        w2[R2_F4 * LW] = fs[4]; w2[R2_F7 * LW] = fs[7]; w2[R2_F8 * LW] = fs[8];
+        w4[R4_F1 * LW] = fs[1]; w4[R4_F3 * LW] = fs[3]; w4[R4_F5 * LW] = fs[5]; w4[R4_F6 * LW] = fs[6];
+        w2[R2_F7 * LW] = fs[7]; w2[R2_F8 * LW] = fs[8];
+        fs0 = fs[0]; fs2 = fs[2]; fs4 = fs[4];
 
         if (!LEAN) {
           const bool own = col_out && t >= 7 && t <= R + 6;  // row F(t) in [j0, j0+R-1]
@@ -297,9 +306,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
       // ---- stage D: pull-stream + moments at row O(t) = j0-9+t --------------------------------------------
       if (S || t >= 9) {
         double fn[9];
-        fn[0] = a2[R4_F0 * LW];      fn[1] = a2[R4_F1 * LW - 1];  fn[3] = a2[R4_F3 * LW + 1];  // row O
-        fn[2] = a3[R4_F2 * LW];      fn[5] = a3[R4_F5 * LW - 1];  fn[6] = a3[R4_F6 * LW + 1];  // row O-1, moving +y
-        fn[4] = o2[R2_F4 * LW];      fn[7] = o2[R2_F7 * LW + 1];  fn[8] = o2[R2_F8 * LW - 1];  // row O+1, moving -y
+        fn[0] = f0_b;  fn[1] = a2[R4_F1 * LW - 1];  fn[3] = a2[R4_F3 * LW + 1];  // row O   = F(t-2)
+        fn[2] = f2_c;  fn[5] = a3[R4_F5 * LW - 1];  fn[6] = a3[R4_F6 * LW + 1];  // row O-1 = F(t-3), moving +y
+        fn[4] = f4_a;  fn[7] = o2[R2_F7 * LW + 1];  fn[8] = o2[R2_F8 * LW - 1];  // row O+1 = F(t-1), moving -y
         double hn, uxn, uyn;
         moments_site(fn, hn, uxn, uyn);
         if (col_out) {
@@ -315,20 +324,23 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         }
       }
       cO.advance(row_bytes, wrapLy, col_bytes);
+      f0_b = f0_a; f0_a = fs0;
+      f2_c = f2_b; f2_b = f2_a; f2_a = fs2;
+      f4_a = fs4;
       if (!TAU1) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) ft_c[k] = ft_n[k];
       }
     }
-    cp_async_wait<0>();  // this iteration's prefetch (h row N(t+1), u rows F(t+1)) has landed
+    cp_async_wait<D - 1>();  // the group issued D-1 iterations ago (h row N(t+1), u rows F(t+1)) has landed
     __syncthreads();
   };
 
   // pipeline fill (predicated), steady state (predicate-free), drain (predicated)
   const int t_end = R + 8;
-  int t = -1;
+  int t = -D;
   for (; t < 9 && t <= t_end; ++t) iter(t, std::false_type{});
-  for (; t <= R + 5; ++t) iter(t, std::true_type{});
+  for (; t <= R + 6 - D; ++t) iter(t, std::true_type{});  // (the last prefetched h row is N(R+6))
   for (; t <= t_end; ++t) iter(t, std::false_type{});
 
   if (!LEAN && logging) {  // CTA reduction of the pre-step height statistics, one atomic per CTA

@@ -1,0 +1,44 @@
+"""torchrun worker for tests/test_gpu_dist.py: 2 ranks, one GPU each, NCCL halos; rank 0 saves the gathered height."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import swalbe_b200 as sw
+    from swalbe_b200.dist import DistSim, broadcast_unique_id_torch, slab_of
+
+    out, thermal = sys.argv[1], sys.argv[2] == "1"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl")
+    Lx, Ly = 520, 96
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(kbt=1e-6 if thermal else 0.0, g=-0.001))
+    sim = DistSim(sysc, rank, world, broadcast_unique_id_torch(), thermal_seed=77 if thermal else None)
+    rng = np.random.default_rng(5)
+    hg = np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06)
+    n = sim.j_count
+    h, z1, z2 = sw.Field(Lx, n).set(slab_of(hg, sim.decomp, rank)), sw.Field(Lx, n), sw.Field(Lx, n)
+    sim.set_state(h, z1, z2)
+    sim.time_loop(5)
+    sim.time_loop(4, step0=5)
+    sim.get_state(h)
+    parts = [torch.empty_like(h.t) for _ in range(world)]
+    dist.all_gather(parts, h.t)
+    if rank == 0:
+        full = torch.cat(parts, dim=0)  # torch layout is (rows, Lx)
+        np.save(out, np.asfortranarray(full.cpu().numpy().transpose()))
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
