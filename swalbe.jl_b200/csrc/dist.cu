@@ -7,10 +7,12 @@
 // streaming <- f*), 1 in u.  For tau != 1 the population planes carry one ghost row on either side.
 // A halo "row" is a contiguous run of Lx doubles, so every message is one contiguous chunk.
 //
-// Per step:   (1) edge strips  [0,GH) and [Ly_loc-GH, Ly_loc)   on the compute stream
-//             (2) event -> NCCL group {send top/bottom edge rows, recv both ghost strips} on the comm stream
-//             (3) interior rows [GH, Ly_loc-GH)                 on the compute stream, overlapping (2)
-//             (4) next step's edge strips wait for (2).
+// Per step s (three streams; src/dst are the ping-pong sets, dst(s) == src(s-1)):
+//   edge stream  : edge strips [0,GH) and [Ly_loc-GH, Ly_loc)      after halo(s-1) and interior(s-1)
+//   comm stream  : NCCL group {send both edge strips, recv both ghost strips} of dst   after edges(s)
+//   main stream  : interior rows [GH, Ly_loc-GH)                    after edges(s-1)  (needs no ghost row)
+// so the interior kernels run back to back while the thin edge kernels and the exchange of step s overlap
+// the interior update of the same step.
 // With nranks == 1 the exchange degenerates to two device-to-device copies (self-neighbour), which also lets
 // the ghost-row kernel path be tested on a single GPU.
 #include <dlfcn.h>
@@ -77,8 +79,8 @@ struct swalbe_dist {
   int cur;                // index of the set holding the current moments
   int fcur;               // index of the set holding the current populations (tau != 1)
   ncclComm_t comm;
-  cudaStream_t s_comp, s_comm;
-  cudaEvent_t ev_edges, ev_halo, ev_t0, ev_t1, ev_user;
+  cudaStream_t s_comp, s_comm, s_edge;
+  cudaEvent_t ev_edges, ev_halo, ev_int, ev_t0, ev_t1, ev_user;
   LaunchGeom g_int, g_edge;
   KernelKey key;
   FusedArgs base;
@@ -164,6 +166,8 @@ int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nrank
   SW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   SW_CUDA(cudaStreamCreateWithPriority(&d->s_comp, cudaStreamNonBlocking, lo));
   SW_CUDA(cudaStreamCreateWithPriority(&d->s_comm, cudaStreamNonBlocking, hi));
+  SW_CUDA(cudaStreamCreateWithPriority(&d->s_edge, cudaStreamNonBlocking, hi));
+  SW_CUDA(cudaEventCreateWithFlags(&d->ev_int, cudaEventDisableTiming));
   SW_CUDA(cudaEventCreateWithFlags(&d->ev_edges, cudaEventDisableTiming));
   SW_CUDA(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
   SW_CUDA(cudaEventCreateWithFlags(&d->ev_user, cudaEventDisableTiming));
@@ -191,7 +195,8 @@ int swalbe_dist_destroy(swalbe_dist *d) {
     for (int q = 0; q < 3; ++q) cudaFree(d->m[s][q]);
     cudaFree(d->f[s]);
   }
-  cudaStreamDestroy(d->s_comp); cudaStreamDestroy(d->s_comm);
+  cudaStreamDestroy(d->s_comp); cudaStreamDestroy(d->s_comm); cudaStreamDestroy(d->s_edge);
+  cudaEventDestroy(d->ev_int);
   cudaEventDestroy(d->ev_edges); cudaEventDestroy(d->ev_halo); cudaEventDestroy(d->ev_user);
   cudaEventDestroy(d->ev_t0); cudaEventDestroy(d->ev_t1);
   delete d;
@@ -224,7 +229,11 @@ int swalbe_dist_set_state(swalbe_dist *d, const double *height, const double *ve
   if (int e = exchange_halos(d, 0, 0)) return e;
   SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
   SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+  SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_halo, 0));
   SW_CUDA(cudaStreamWaitEvent(user, d->ev_halo, 0));
+  // "previous step" events of the first step: everything is ready once the halo exchange above is done
+  SW_CUDA(cudaEventRecord(d->ev_int, d->s_comp));
+  SW_CUDA(cudaEventRecord(d->ev_edges, d->s_edge));
   return 0;
 }
 
@@ -234,6 +243,7 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
   cudaStream_t user = (cudaStream_t)stream_;
   SW_CUDA(cudaEventRecord(d->ev_user, user));
   SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_user, 0));
+  SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_user, 0));
   SW_CUDA(cudaEventRecord(d->ev_t0, d->s_comp));
   const int Ly = d->Ly_loc;
   for (int s = 0; s < nsteps; ++s) {
@@ -249,28 +259,32 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     else { fdst = d->fcur ^ 1; a.f_in = d->f[d->fcur] + fo; a.f_out = d->f[fdst] + fo; }
     a.fstride_in = a.fstride_out = a.fstride_out2 = d->fplane;
     a.step = step0 + (unsigned long long)s;
-    // (1) edge strips -- they need the ghost rows of `src`, i.e. the previous exchange
-    SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+    // edge strips: need the ghost rows of `src` (previous exchange) and the rows the previous interior kernel wrote
+    SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_halo, 0));
+    SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_int, 0));
+    // interior rows: need the edge rows of `src` written by the previous step's edge kernels, no ghost row
+    SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_edges, 0));
     a.W = d->g_edge.W; a.rows_per_cta = d->g_edge.rows_per_cta;
     a.jbeg = 0; a.jend = GH;
-    if (int e = launch_fused(d->g_edge, a, d->key, d->s_comp)) return e;
+    if (int e = launch_fused(d->g_edge, a, d->key, d->s_edge)) return e;
     a.jbeg = Ly - GH; a.jend = Ly;
-    if (int e = launch_fused(d->g_edge, a, d->key, d->s_comp)) return e;
-    SW_CUDA(cudaEventRecord(d->ev_edges, d->s_comp));
-    // (2) halo exchange of the freshly written edge rows of `dst`
+    if (int e = launch_fused(d->g_edge, a, d->key, d->s_edge)) return e;
+    SW_CUDA(cudaEventRecord(d->ev_edges, d->s_edge));
+    // halo exchange of the freshly written edge rows of `dst`
     SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_edges, 0));
     if (int e = exchange_halos(d, dst, fdst)) return e;
     SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
-    // (3) interior rows, overlapping the exchange
     if (Ly > 2 * GH) {
       a.W = d->g_int.W; a.rows_per_cta = d->g_int.rows_per_cta;
       a.jbeg = GH; a.jend = Ly - GH;
       if (int e = launch_fused(d->g_int, a, d->key, d->s_comp)) return e;
     }
+    SW_CUDA(cudaEventRecord(d->ev_int, d->s_comp));
     d->cur = dst;
     if (!d->tau1) d->fcur = fdst;
   }
   SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_edges, 0));
   SW_CUDA(cudaEventRecord(d->ev_t1, d->s_comp));
   SW_CUDA(cudaStreamWaitEvent(user, d->ev_t1, 0));
   return 0;
