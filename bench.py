@@ -206,23 +206,33 @@ def main():
             # e2e: the call a user makes -- host initial condition in, time_loop, host result out
             h_host = torch.from_numpy(np.ascontiguousarray(h0.transpose())).pin_memory()
             out_host = torch.empty_like(h_host).pin_memory()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            st.height.t.copy_(h_host, non_blocking=True)
-            st.velx.t.zero_(); st.vely.t.zero_()
-            sw.equilibrium(st, sysc)
-            if thermal_seed is None:
-                sw.time_loop(sysc, st)
-            else:
-                sw.fused_steps(st, sysc, K, thermal_seed=thermal_seed)
-            out_host.copy_(st.height.t, non_blocking=True)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
+
+            def job():
+                st.height.t.copy_(h_host, non_blocking=True)
+                st.velx.t.zero_(); st.vely.t.zero_()
+                sw.equilibrium(st, sysc)
+                if thermal_seed is None:
+                    sw.time_loop(sysc, st)
+                else:
+                    sw.fused_steps(st, sysc, K, thermal_seed=thermal_seed)
+                out_host.copy_(st.height.t, non_blocking=True)
+                torch.cuda.synchronize()
+
+            sysc_warm = sw.SysConst(Lx=L, Ly=L, param=sw.Taumucs(kbt=prm.kbt, Tmax=min(K, 4), tdump=2))
+            sysc, sysc_keep = sysc_warm, sysc
+            job()  # untimed warm-up of the e2e path (first-use costs: module load of the operator kernels, async pool)
+            sysc = sysc_keep
+            dt = float("inf")
+            for _ in range(3):  # best of three whole jobs (host-side jitter: allocator, Python GC, nvidia-smi teardown)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                job()
+                dt = min(dt, time.perf_counter() - t0)
             plane = L * L * 8
             e2e = {"value": round(lu / dt / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": plane // K,
                    "d2h_bytes_per_step": (plane + 16 * 4) // K,
                    "what": f"pinned-host height -> H2D -> equilibrium! + time_loop({K} steps, mass read-back every tdump) -> D2H height; "
-                           "copies amortised over the steps of the job"}
+                           "copies amortised over the steps of the job; best of 3 jobs after one warm-up job"}
     else:
         import ctypes as C
         import torch.distributed as dist

@@ -1,7 +1,9 @@
 // Host side of the fused time loop: plan (scratch + launch geometry) and swalbe_time_loop.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "fused.cuh"
 #include "launch.h"
@@ -38,7 +40,8 @@ struct Variant {
     }                                                                                                         \
   }
 
-static const Variant g_variants[] = {SW_VARIANT(128, 5, 3), SW_VARIANT(192, 3, 2), SW_VARIANT(256, 2, 2)};
+static const Variant g_variants[] = {SW_VARIANT(128, 5, 3), SW_VARIANT(160, 4, 3), SW_VARIANT(192, 3, 2),
+                                     SW_VARIANT(224, 3, 2), SW_VARIANT(256, 2, 2)};
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
@@ -51,12 +54,22 @@ static int env_int(const char *name, int dflt) {
   return s && *s ? atoi(s) : dflt;
 }
 
+// Launch geometry.  Time model calibrated on B200: a CTA marching R rows runs R + 8 + D pipeline
+// iterations; one iteration (one row of every CTA resident on an SM) costs
+//   t_iter(n) = max(0.87 us, 0.56 us + 1.86 ns * n),   n = resident threads on the SM
+// (0.87 us: dependent-chain latency of a lone CTA, 100^2 grid; 1.09 us at n = 320, 2048^2; 1.63 us at n = 576, the
+// compute-bound moments-only rate at 8192^2), and the whole launch cannot beat the HBM floor of 120 B per lattice
+// update at 5.5 TB/s (tools/membench.cu).  Large grids therefore want whole waves of long chunks, small grids many
+// short chunks (latency bound).
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   int dev = 0, nsm = 148;
   SW_CUDA(cudaGetDevice(&dev));
   SW_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int force_nt = env_int("SWALBE_NT", 0);
-  const int rmax = std::max(16, env_int("SWALBE_RMAX", 128));
+  const int rmax = std::max(1, env_int("SWALBE_RMAX", 128));
+  auto t_iter = [](double n) { return std::max(0.87, 0.56 + 0.00186 * n); };
+  const double hbm_floor = (double)Lx * (double)nrows * 120.0 / 5.5e6;  // us
+  const int fill = 8 + FUSED_D;
   double best_cost = 1e300;
   for (int v = 0; v < g_nvariants; ++v) {
     const Variant &var = g_variants[v];
@@ -71,32 +84,44 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
     const int nstrips = (Lx + wmax - 1) / wmax;
     int W = (Lx + nstrips - 1) / nstrips;
     W = std::min(wmax, (W + 3) & ~3);
-    // rows per CTA: fill an integer number of waves of (nsm*bps) CTA slots, R <= rmax
     const long long slots = (long long)nsm * bps;
-    int nchunks = std::max(1, (nrows + rmax - 1) / rmax);
-    for (int w = 1; w < 4096; ++w) {
+    // candidate chunk counts: powers of two of rows, and the counts that fill 1..64 whole waves
+    int cand[160], nc = 0;
+    for (int c = 1; c <= nrows && nc < 40; c *= 2) cand[nc++] = c;
+    cand[nc++] = nrows;
+    for (int w = 1; w <= 64 && nc < 150; ++w) {
       const long long c = (w * slots) / nstrips;
-      if (c < 1) continue;
-      if (c >= nchunks) { nchunks = (int)std::min<long long>(c, nrows); break; }
+      if (c >= 1 && c <= nrows) cand[nc++] = (int)c;
+      const long long c2 = ((long long)w * nsm) / nstrips;  // one CTA per SM and multiples
+      if (c2 >= 1 && c2 <= nrows) cand[nc++] = (int)c2;
     }
-    int R = (nrows + nchunks - 1) / nchunks;
-    if (R < 16 && nrows >= 16) R = 16;
-    nchunks = (nrows + R - 1) / R;
-    // cost model: thread-rows executed per SM (incl. halo columns and the 10-row pipeline fill) x wave quantisation,
-    // discounted by the latency hiding that more resident warps buy (measured: 16-18 warps/SM is the sweet spot)
-    const long long ctas = (long long)nstrips * nchunks;
-    const long long waves = (ctas + slots - 1) / slots;
-    const int warps = bps * var.nt / 32;
-    const double occ_penalty = warps >= 16 ? 1.0 : 16.0 / warps;
-    const double cost = (double)waves * (double)bps * (double)var.nt * (double)(R + 10) * occ_penalty;
-    if (cost < best_cost) {
-      best_cost = cost;
-      g->nt = var.nt; g->variant = v; g->W = W; g->nstrips = nstrips; g->rows_per_cta = R; g->nchunks = nchunks;
-      g->blocks_per_sm = bps;
+    for (int q = 0; q < nc; ++q) {
+      int R = (nrows + cand[q] - 1) / cand[q];
+      if (R > rmax && nrows > rmax) continue;
+      const int nchunks = (nrows + R - 1) / R;
+      const long long ctas = (long long)nstrips * nchunks;
+      double cost;
+      if (ctas <= slots) {  // a single, possibly partial wave: c CTAs share an SM
+        const int c = (int)((ctas + nsm - 1) / nsm);
+        cost = (R + fill) * t_iter((double)c * var.nt);
+      } else {
+        const double waves = (double)ctas / (double)slots;  // CTAs are re-issued as slots free up
+        cost = std::ceil(waves - 1e-9) * (R + fill) * t_iter((double)bps * var.nt);
+      }
+      cost = std::max(cost, hbm_floor) + 0.01 * cost;
+      if (cost < best_cost) {
+        best_cost = cost;
+        g->nt = var.nt; g->variant = v; g->W = W; g->nstrips = nstrips; g->rows_per_cta = R; g->nchunks = nchunks;
+        g->blocks_per_sm = bps;
+      }
     }
   }
   if (best_cost == 1e300) return set_error(SWALBE_ERR_CUDA, "no fused-kernel variant fits on this device");
   if (int r = env_int("SWALBE_ROWS", 0)) { g->rows_per_cta = r; g->nchunks = (nrows + r - 1) / r; }
+  if (env_int("SWALBE_DEBUG", 0))
+    fprintf(stderr, "[swalbe] geometry Lx=%d rows=%d lean_pm=%d tau1=%d thermal=%d: NT=%d W=%d strips=%d rows/CTA=%d chunks=%d "
+            "CTAs/SM=%d model %.1f us\n", Lx, nrows, key.lean_pm, (int)key.tau1, (int)key.thermal, g->nt, g->W, g->nstrips,
+            g->rows_per_cta, g->nchunks, g->blocks_per_sm, best_cost);
   return 0;
 }
 
