@@ -43,44 +43,58 @@ def initial_height(L, Ly=None, j0=0, Ly_global=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms by a background process that is started BEFORE the
+    warm-up (nvidia-smi takes a while to come up); summary() keeps the samples that fall inside the timed window."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
-
-    def __enter__(self):
+        self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
-        return self
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def __enter__(self):  # the timed window
+        self.t0 = time.perf_counter()
+        return self
 
     def __exit__(self, *exc):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        if not sm:
+        self.stop()
+        ok = [(t, r) for t, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        inside = [r for t, r in ok if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: take the sample closest to it
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = [min(ok, key=lambda tr: abs(tr[0] - mid))[1]]
+            window = "nearest sample"
+        sm = sorted(float(r[0]) for r in inside)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7), "samples": len(sm)}
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in inside), "samples": len(sm), "window": window}
 
 
 def cpu_baseline_run(L, steps, threads, warmup=1):
@@ -181,16 +195,18 @@ def main():
         st.height.set(h0)
         run = lambda n, s0=0: sw.fused_steps(st, sysc, n, thermal_seed=thermal_seed, step0=s0,  # noqa: E731
                                              pressure_variant=_lib.PRESSURE_POWER_BROAD)
+        sampler = ClockSampler(local_rank)
         run(W)
         torch.cuda.synchronize()
         l0 = lib.swalbe_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clocks:
+        with sampler as clocks:
             e0.record()
             run(K, W)
             e1.record()
             torch.cuda.synchronize()
         launches = int(lib.swalbe_launch_count() - l0)
+        sampler.stop()
         ms = e0.elapsed_time(e1)
         mass_drift = abs(st.height.t.sum().item() - h0.sum()) / h0.sum()
         lu = L * L * K
@@ -253,18 +269,20 @@ def main():
         zero = sw.Field(L, L)
         stream = sw._stream()
         _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
+        sampler = ClockSampler(local_rank)
         _lib.call("swalbe_dist_time_loop", handle, W, 0, stream)
         torch.cuda.synchronize()
         dist.barrier()
         l0 = lib.swalbe_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clocks:
+        with sampler as clocks:
             e0.record()
             _lib.call("swalbe_dist_time_loop", handle, K, W, stream)
             e1.record()
             torch.cuda.synchronize()
         dist.barrier()
         launches = int(lib.swalbe_launch_count() - l0)
+        sampler.stop()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
