@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   double *const s2 = s4 + 4 * R4S;                 // own column, ring-2 slot 0, line 0
   double *const su = s2 + 2 * R2S;                 // own column, u ring slot 0, line 0
 
+  // Programmatic dependent launch: let the next step's grid start filling SMs as ours drains ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid < 2) {  // the two pad cells of every line are never written by the pipeline; keep them finite
     const int e = tid ? NT + 1 : 0;
     for (int q = 0; q < FUSED_LINES; ++q) smem[q * LW + e] = 0.0;
@@ -335,6 +337,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     cp_async_wait<D - 1>();  // the group issued D-1 iterations ago (h row N(t+1), u rows F(t+1)) has landed
     __syncthreads();
   };
+
+  // ... and do not touch global memory before the previous step's grid has completed and flushed its writes.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // pipeline fill (predicated), steady state (predicate-free), drain (predicated)
   const int t_end = R + 8;
