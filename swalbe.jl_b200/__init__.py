@@ -28,7 +28,8 @@ __all__ = [
     "equilibrium", "BGKandStream", "moments", "filmpressure", "hgradp", "gradf", "laplacianf", "slippage",
     "slippage2", "slippage_ring_riv", "thermal", "inclination", "update", "time_loop", "run_flat", "run_random",
     "run_rayleightaylor", "run_dropletrelax", "run_dropletpatterned", "run_dropletforced", "wetted", "snapshot",
-    "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES",
+    "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES", "viewdists", "viewneighbors", "power_broad", "power_2",
+    "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet",
 ]
 
 
@@ -391,6 +392,45 @@ def snapshot(snap: np.ndarray, field: Field, t: int, dumping=1000):
 
 
 # ------------------------------------------------------------------------------------------------
+# small helpers of the reference that user code calls directly
+
+
+def viewdists(f: Field):
+    """viewdists(f)   src/collide.jl:270-282 -- the nine population planes as views (torch tensors, [j, i] indexed)."""
+    return tuple(f.t[k] for k in range(9))
+
+
+def viewneighbors(f: Field):
+    """viewneighbors(f)   src/differences.jl:251-262 -- the eight planes of a dgrad-like array as views."""
+    return tuple(f.t[k] for k in range(8))
+
+
+def power_broad(arg, n: int):
+    """power_broad(arg, n)   src/pressure.jl:363-385 -- temp = 1; temp *= arg, n times (host scalar helper)."""
+    temp = 1.0 if isinstance(arg, float) else 1
+    for _ in range(n):
+        temp = temp * arg
+    return temp
+
+
+def power_2(arg):  # src/pressure.jl:392-394
+    return arg * arg
+
+
+def power_3(arg):  # src/pressure.jl:401-403
+    return arg * arg * arg
+
+
+def fast_93(arg):  # src/pressure.jl:410-413
+    temp = power_3(arg)
+    return power_3(temp) - temp
+
+
+def fast_32(arg):  # src/pressure.jl:420-422
+    return power_3(arg) - power_2(arg)
+
+
+# ------------------------------------------------------------------------------------------------
 # drivers  (src/simulate.jl)
 
 
@@ -572,5 +612,6 @@ JULIA_NAMES = {
     "run_rayleightaylor": run_rayleightaylor, "run_dropletrelax": run_dropletrelax,
     "run_dropletpatterned": run_dropletpatterned, "run_dropletforced": run_dropletforced, "Sys": Sys,
     "SysConst": SysConst, "Sys_const": Sys_const, "Taumucs": Taumucs, "CuState": CuState,
-    "CuState_thermal": CuState_thermal, "Swalbe_state": Swalbe_state,
+    "CuState_thermal": CuState_thermal, "Swalbe_state": Swalbe_state, "viewdists": viewdists,
+    "viewneighbors": viewneighbors, "power_broad": power_broad, "fast_93": fast_93, "fast_32": fast_32,
 }
