@@ -31,15 +31,39 @@ sys.path.insert(0, ROOT)
 B_ALG = 144.0  # algorithmic bytes per lattice update
 
 
-def initial_height(L, Ly=None, j0=0, Ly_global=None):
-    """flat film + perturbation, h = 1 + 1e-3 sin(2π i/Lx) sin(2π j/Ly) as a NumPy F-array."""
+def initial_height(L, Ly=None, j0=0, Ly_global=None, workload="film"):
+    """Synthetic initial conditions of SURVEY.md 8d as NumPy F-arrays (rows j0 .. j0+Ly of a L x Ly_global lattice).
+    film/thermal: h = 1 + 1e-3 sin(2π i/Lx) sin(2π j/Ly); droplet: spherical cap (singledroplet, radius L/4, θ0 = 1/6,
+    precursor 0.05); spinodal: h = 1 + 0.01 N(0,1), seed 20261017."""
     import numpy as np
 
     Ly = Ly or L
     Ly_global = Ly_global or Ly
     i = np.arange(L, dtype=np.float64)[:, None]
     j = (j0 + np.arange(Ly, dtype=np.float64))[None, :]
+    if workload == "droplet":
+        radius, c = L / 4.0, (L // 2, Ly_global // 2)
+        circ = np.sqrt((i + 1 - c[0]) ** 2 + (j + 1 - c[1]) ** 2)
+        inside = circ <= radius
+        cap = (np.cos(np.arcsin(np.where(inside, circ / radius, 0.0))) - math.cos(math.pi / 6)) * radius
+        h = np.where(inside, cap, 0.05)
+        return np.asfortranarray(np.where(h < 0, 0.05, h))
+    if workload == "spinodal":
+        rng = np.random.default_rng([20261017, j0])
+        return np.asfortranarray(1.0 + 0.01 * rng.standard_normal((L, Ly)))
     return np.asfortranarray(1.0 + 1e-3 * np.sin(2 * np.pi * i / L) * np.sin(2 * np.pi * j / Ly_global))
+
+
+def workload_params(args, K):
+    """Taumucs keyword arguments of the workload."""
+    kw = dict(Tmax=K, tdump=max(1, K // 2))
+    if args.workload == "thermal":
+        kw.update(kbt=1e-7)
+    elif args.workload == "droplet":
+        kw.update(n=3, m=2, hmin=0.07, δ=1.0)
+    elif args.workload == "spinodal":
+        kw.update(n=3, m=2, hmin=0.07, γ=0.01)
+    return kw
 
 
 class ClockSampler:
@@ -97,15 +121,17 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in inside), "samples": len(sm), "window": window}
 
 
-def cpu_baseline_run(L, steps, threads, warmup=1):
-    """The C oracle (faithful pass structure of the reference's CPU path) on an L x L sample; returns MLUPS."""
+def cpu_baseline_run(L, steps, threads, warmup=1, workload="film"):
+    """The C oracle (faithful pass structure of the reference's CPU path) on an L x L sample; returns MLUPS.
+    (thermal: the deterministic part only -- Julia's randn! is not restated.)"""
     from oracle import oracle_c as oc
     from oracle import oracle_np as onp
 
     oc.build()
     st = onp.State(L, L)
-    st.height[...] = initial_height(L)
-    p = onp.Params()
+    st.height[...] = initial_height(L, workload=workload)
+    okw = {"droplet": dict(n=3, m=2, hmin=0.07), "spinodal": dict(n=3, m=2, hmin=0.07, gamma=0.01)}.get(workload, {})
+    p = onp.Params(**okw)
     oc.time_loop(st, p, nsteps=warmup, threads=threads)
     t0 = time.perf_counter()
     oc.time_loop(st, p, nsteps=steps, threads=threads)
@@ -122,8 +148,8 @@ def run_reference(args, rank):
 
     threads = oc.max_threads()
     Ls = 2048
-    mlups, dt = cpu_baseline_run(Ls, args.steps, threads, warmup=max(1, min(args.warmup, 3)))
-    m1, _ = cpu_baseline_run(1024, 3, 1)
+    mlups, dt = cpu_baseline_run(Ls, args.steps, threads, warmup=max(1, min(args.warmup, 3)), workload=args.workload)
+    m1, _ = cpu_baseline_run(1024, 3, 1, workload=args.workload)
     line = {
         "impl": "reference", "metric": "MLUPS", "value": round(mlups, 3), "unit": "MLUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
@@ -139,9 +165,14 @@ def run_reference(args, rank):
 
 
 def workload_config(args):
-    return {"workload": f"thin-film D2Q9 LBM step, {args.L}x{args.L} per GPU, tau=1, Taumucs defaults (n=9,m=3,theta=1/9), "
-                        f"flat film + sine perturbation{', thermal noise kbt=1e-7 (Philox)' if args.workload == 'thermal' else ''}",
-            "grid": [args.L, args.L * args.gpus], "per_gpu_grid": [args.L, args.L], "bytes_per_update_alg": B_ALG,
+    what = {"film": "Taumucs defaults (n=9,m=3,theta=1/9), flat film + sine perturbation (SURVEY 8d C5)",
+            "thermal": "Taumucs defaults + thermal noise kbt=1e-7 generated in-kernel (Philox), flat film + sine (C4)",
+            "droplet": "n=3,m=2,hmin=0.07,theta=1/9, spherical-cap droplet radius L/4 on a 0.05 precursor (C2)",
+            "spinodal": "n=3,m=2,hmin=0.07,gamma=0.01, randomly perturbed film h=1+0.01 N(0,1) (C3)"}[args.workload]
+    weak = args.gpus == 1 or getattr(args, "scaling", "weak") == "weak"
+    rows = args.L if weak else args.L // args.gpus
+    return {"workload": f"thin-film D2Q9 LBM step, {args.L}x{rows} per GPU, tau=1, {what}",
+            "grid": [args.L, rows * args.gpus], "per_gpu_grid": [args.L, rows], "bytes_per_update_alg": B_ALG,
             "decomposition": "row slabs along y, NCCL send/recv halos" if args.gpus > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (>= 1.5 GB touched per step vs 126 MB L2)"}
 
@@ -153,7 +184,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--L", type=int, default=8192)
-    ap.add_argument("--workload", default="film", choices=["film", "thermal"])
+    ap.add_argument("--workload", default="film", choices=["film", "thermal", "droplet", "spinodal"],
+                    help="film: C5 flat film + sine (default); thermal: C4 (+Philox noise); droplet: C2 spherical cap, "
+                         "n=3,m=2,hmin=0.07 (use --L 1024); spinodal: C3 random film, n=3,m=2,hmin=0.07,gamma=0.01 (--L 4096)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = L x L per rank (default, the contract), strong = L x L in total (L/N rows per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -184,14 +219,16 @@ def main():
 
     lib = _lib.load()
     L, K, W = args.L, args.steps, args.warmup
-    prm = sw.Taumucs(kbt=1e-7 if args.workload == "thermal" else 0.0, Tmax=K, tdump=max(1, K // 2))
+    prm = sw.Taumucs(**workload_params(args, K))
     sysc = sw.SysConst(Lx=L, Ly=L, param=prm)
+    rows = L if (world == 1 or args.scaling == "weak") else L // world   # rows per rank
+    Ly_glob = rows * world
     thermal_seed = 1234 if args.workload == "thermal" else None
     e2e = None
 
     if world == 1:
         st = sw.Sys(sysc, "GPU", kind="thermal" if thermal_seed is not None else "simple")
-        h0 = initial_height(L)
+        h0 = initial_height(L, workload=args.workload)
         st.height.set(h0)
         run = lambda n, s0=0: sw.fused_steps(st, sysc, n, thermal_seed=thermal_seed, step0=s0,  # noqa: E731
                                              pressure_variant=_lib.PRESSURE_POWER_BROAD)
@@ -234,7 +271,9 @@ def main():
                 out_host.copy_(st.height.t, non_blocking=True)
                 torch.cuda.synchronize()
 
-            sysc_warm = sw.SysConst(Lx=L, Ly=L, param=sw.Taumucs(kbt=prm.kbt, Tmax=min(K, 4), tdump=2))
+            wkw = workload_params(args, K)
+            wkw.update(Tmax=min(K, 4), tdump=2)
+            sysc_warm = sw.SysConst(Lx=L, Ly=L, param=sw.Taumucs(**wkw))
             sysc, sysc_keep = sysc_warm, sysc
             job()  # untimed warm-up of the e2e path (first-use costs: module load of the operator kernels, async pool)
             sysc = sysc_keep
@@ -263,10 +302,10 @@ def main():
         raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
         q = sw._c_params(prm, thermal_seed=thermal_seed)
         handle = C.c_void_p()
-        _lib.call("swalbe_dist_create", C.byref(handle), raw, rank, world, L, L * world, C.byref(q))
-        h0 = initial_height(L, L, rank * L, L * world)
-        hd = sw.Field(L, L).set(h0)
-        zero = sw.Field(L, L)
+        _lib.call("swalbe_dist_create", C.byref(handle), raw, rank, world, L, Ly_glob, C.byref(q))
+        h0 = initial_height(L, rows, rank * rows, Ly_glob, workload=args.workload)
+        hd = sw.Field(L, rows).set(h0)
+        zero = sw.Field(L, rows)
         stream = sw._stream()
         _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
         sampler = ClockSampler(local_rank)
@@ -290,7 +329,7 @@ def main():
         msum = torch.tensor([hd.t.sum().item(), float(h0.sum())], device="cuda", dtype=torch.float64)
         dist.all_reduce(msum)
         mass_drift = abs(msum[0].item() - msum[1].item()) / msum[1].item()
-        lu = L * L * world * K
+        lu = L * Ly_glob * K
         lazy_mlups = None
         if not args.no_e2e:
             # e2e at N GPUs: per-rank pinned-host slab in, K steps with halo exchange, per-rank slab out
@@ -306,7 +345,7 @@ def main():
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            plane = L * L * 8
+            plane = L * rows * 8
             e2e = {"value": round(lu / dt.item() / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": plane * world // K,
                    "d2h_bytes_per_step": plane * world // K,
                    "what": f"per-rank pinned-host slab -> H2D -> {K} fused steps with NCCL halos -> D2H slab; max over ranks"}
@@ -326,7 +365,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     kernel_ms = ms / K  # one fused kernel per step (plus two thin edge-strip launches per step at N > 1)
-    achieved = B_ALG * L * L / (kernel_ms * 1e-3) / 1e9
+    achieved = B_ALG * L * rows / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}_{L}")
@@ -334,13 +373,14 @@ def main():
         pass
     line = {
         "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+        "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args), "impl": "b200",
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                      "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), "per_gpu": True,
-                     "alg_bytes_per_launch": B_ALG * L * L},
+                     "alg_bytes_per_launch": B_ALG * L * rows},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         "mass_drift_rel": mass_drift,
     }
@@ -350,10 +390,10 @@ def main():
         from oracle import oracle_c as oc
 
         threads = oc.max_threads()
-        m, dt = cpu_baseline_run(1024, 4, threads)
+        m, dt = cpu_baseline_run(1024, 4, threads, workload=args.workload)
         nst = max(4, min(400, int(12.0 / (dt / 4) / 4)))
-        mN, dtN = cpu_baseline_run(2048, nst, threads)
-        m1, dt1 = cpu_baseline_run(1024, max(2, min(40, int(8.0 * m / threads / 1.05 + 1))), 1)
+        mN, dtN = cpu_baseline_run(2048, nst, threads, workload=args.workload)
+        m1, dt1 = cpu_baseline_run(1024, max(2, min(40, int(8.0 * m / threads / 1.05 + 1))), 1, workload=args.workload)
         line["cpu_baseline"] = {"value": round(mN, 2), "unit": "MLUPS", "cores": threads, "kind": "port",
                                 "sample": f"2048x2048 sample of the workload, {nst} steps ({dtN:.1f} s), C restatement of the "
                                           f"reference CPU path with OpenMP x{threads}; single thread (as Julia runs it): "
