@@ -89,6 +89,7 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
     int cand[160], nc = 0;
     for (int c = 1; c <= nrows && nc < 40; c *= 2) cand[nc++] = c;
     cand[nc++] = nrows;
+    cand[nc++] = std::min(nrows, 65535);
     for (int w = 1; w <= 64 && nc < 150; ++w) {
       const long long c = (w * slots) / nstrips;
       if (c >= 1 && c <= nrows) cand[nc++] = (int)c;
@@ -99,6 +100,7 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
       int R = (nrows + cand[q] - 1) / cand[q];
       if (R > rmax && nrows > rmax) continue;
       const int nchunks = (nrows + R - 1) / R;
+      if (nchunks > 65535) continue;  // gridDim.y limit
       const long long ctas = (long long)nstrips * nchunks;
       double cost;
       if (ctas <= slots) {  // a single, possibly partial wave: c CTAs share an SM

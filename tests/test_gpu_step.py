@@ -56,6 +56,16 @@ def test_fused_loop_bitwise_default_params(sw, Lx, Ly, nsteps):
     _compare(st, ref)
 
 
+@pytest.mark.parametrize("Lx,Ly", [(1, 1), (2, 3), (3, 1), (1, 40), (9, 2)])
+def test_fused_loop_tiny_extents(sw, Lx, Ly):
+    """Degenerate periodic lattices: every neighbour is a wrapped copy of the few sites there are."""
+    for kw, pops in ((dict(g=-0.001), False), (dict(τ=0.9), True)):
+        st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx * 10 + Ly, prm_kw=kw, tau_pops=pops)
+        sw.fused_steps(st, sysc, 3)
+        oc.time_loop(ref, p, nsteps=3)
+        _compare(st, ref, what=f"{Lx}x{Ly}:")
+
+
 @pytest.mark.parametrize("prm_kw", [
     dict(n=3, m=2, hmin=0.07, γ=0.01),
     dict(n=4, m=2, δ=2.0),
