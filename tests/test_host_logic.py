@@ -1,0 +1,103 @@
+"""CPU tests of the host mirror's driver logic (no GPU, no kernels): the fused time loop must be chunked so that the
+mass print of the reference (`t % tdump == 0`, src/simulate.jl:8-14) happens at the same steps, the chunks add up to
+Tmax, and the four time_loop call shapes dispatch like the reference's methods (src/simulate.jl:6-96)."""
+import math
+
+import numpy as np
+import pytest
+
+import swalbe_b200 as sw
+
+
+class _FakeTensor:
+    def __init__(self, a):
+        self.a = np.asarray(a, dtype=np.float64)
+
+    def __sub__(self, o):
+        return _FakeTensor(self.a - o.a)
+
+    def cpu(self):
+        return self
+
+    def tolist(self):
+        return self.a.tolist()
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    calls = {"steps": [], "stats_at": [], "kw": []}
+    state = {"t": 1}
+
+    def fused_steps(st, sysc, n, **kw):
+        calls["steps"].append(n)
+        calls["kw"].append(kw)
+        state["t"] += n
+        mn = _FakeTensor(np.zeros(n)) if kw.get("log_minmax") else None
+        mx = _FakeTensor(np.arange(n) + 1.0) if kw.get("log_minmax") else None
+        wet = _FakeTensor(np.full(n, 7)) if kw.get("log_wetted") else None
+        return mn, mx, wet
+
+    def field_stats(f, thresh=0.055):
+        calls["stats_at"].append(state["t"])
+        return 0.0, 1.0, 625.0, 3
+
+    monkeypatch.setattr(sw, "fused_steps", fused_steps)
+    monkeypatch.setattr(sw, "field_stats", field_stats)
+    return calls
+
+
+class _State(sw.CuState):
+    def __init__(self):  # no device allocation
+        self.height = None
+
+
+@pytest.mark.parametrize("Tmax,tdump", [(1000, 100), (200, 100), (10, 3), (7, 10), (5, 1), (1000, None)])
+def test_time_loop_chunks_and_mass_prints(fake, capsys, Tmax, tdump):
+    sysc = sw.SysConst(Lx=5, Ly=5, param=sw.Taumucs(Tmax=Tmax, tdump=tdump))
+    td = sysc.param.tdump
+    sw.time_loop(sysc, _State(), verbose=True)
+    assert sum(fake["steps"]) == Tmax
+    expected = [t for t in range(1, Tmax + 1) if t % td == 0]  # the reference prints BEFORE the update of step t
+    assert fake["stats_at"] == expected
+    out = capsys.readouterr().out.strip().splitlines()
+    assert out == [f"Time step {t} mass is 625.0" for t in expected]
+
+
+def test_time_loop_method_shapes(fake):
+    sysc = sw.SysConst(Lx=5, Ly=5, param=sw.Taumucs(Tmax=12, tdump=5))
+    st = _State()
+    assert sw.time_loop(sysc, st) is st                                   # src/simulate.jl:6-25
+    assert all(k.get("θ") is None for k in fake["kw"])
+    fake["kw"].clear()
+    sw.time_loop(sysc, st, 1 / 9)                                          # :26-45 (θ scalar)
+    assert all(k["θ"] == 1 / 9 for k in fake["kw"])
+    dh = []
+    sw.time_loop(sysc, st, dh)                                             # :47-67 (Δh log, one entry per step)
+    assert len(dh) == 12
+    area = []
+    ret = sw.time_loop(sysc, st, sw.wetted, area)                          # :69-96 (callback slot)
+    assert ret == (st, area) and area == [7] * 12
+    force = [1e-4, 0.0]
+    fake["kw"].clear()
+    sw.time_loop(sysc, st, sw.inclination, force)
+    alpha, factor = fake["kw"][0]["incl"]
+    assert alpha is force and factor == 0.5 + 0.5 * math.tanh(1000.0)     # defaults t=1000, tstart=0, tsmooth=1 (forcing.jl:363)
+    with pytest.raises(sw.SwalbeError):
+        sw.time_loop(sysc, st, lambda m, s: None, [])
+    with pytest.raises(TypeError):
+        sw.time_loop(sysc, st, 1, 2, 3)
+
+
+def test_julia_name_table_and_aliases():
+    for name in ("equilibrium!", "BGKandStream!", "moments!", "filmpressure!", "h∇p!", "slippage!", "update!", "time_loop",
+                 "run_flat", "run_random", "run_rayleightaylor", "run_dropletrelax", "run_dropletpatterned",
+                 "run_dropletforced", "∇f!", "∇²f!", "thermal!", "inclination!", "slippage2!", "slippage_ring_riv!"):
+        assert callable(sw.JULIA_NAMES[name]), name
+    assert sw.Sys_const is sw.SysConst and sw.Swalbe_state is sw.CuState
+    assert issubclass(sw.CuState_thermal, sw.CuState)
+
+
+def test_cospi_matches_reference_points():
+    assert sw.cospi(0) == 1.0 and sw.cospi(0.5) == 0.0 and sw.cospi(1) == -1.0 and sw.cospi(1.5) == 0.0
+    assert sw.cospi(-1 / 9) == sw.cospi(1 / 9) and sw.cospi(2.25) == sw.cospi(0.25) == sw.cospi(-1.75)
+    assert abs(sw.cospi(1 / 6) - math.sqrt(3) / 2) < 2e-16
