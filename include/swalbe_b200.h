@@ -150,6 +150,10 @@ typedef struct swalbe_params {
 /* tau == 1 only: populations are written on the LAST step of the call only ("moments-only" steps, reported
  * separately from the 144-B/LU accounting).  Field values on return are identical to the default mode. */
 #define SWALBE_LOOP_LAZY_POPULATIONS 1
+/* Do not materialise feq/vsq/pressure/h∇p/slip/F[/kbt] on the last step of the call (they keep whatever they held).
+ * height/velx/vely and fout == ftemp are always current on return.  For drivers that call the loop in chunks (mass
+ * print every tdump steps, moving substrates) and only need the intermediate fields at the very end. */
+#define SWALBE_LOOP_SKIP_AUX 2
 /* per-step device logs (see swalbe_time_loop) */
 typedef struct swalbe_loop_logs {
   double *hmin, *hmax;        /* device, nsteps each: min/max of height BEFORE each step (src/simulate.jl:56); NULL = off */

@@ -241,6 +241,7 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
   const bool thermal = prm->use_thermal != 0;
   if (thermal && (!st->kbtx || !st->kbty)) return set_error(SWALBE_ERR_ARG, "thermal loop needs state.kbtx/kbty");
   const bool lazy = (flags & SWALBE_LOOP_LAZY_POPULATIONS) != 0;
+  const bool skip_aux = (flags & SWALBE_LOOP_SKIP_AUX) != 0;
   if (lazy && !tau1) return set_error(SWALBE_ERR_ARG, "SWALBE_LOOP_LAZY_POPULATIONS requires tau == 1");
 
   FusedArgs a = {};
@@ -292,7 +293,7 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
       a.f_out = fsrc_is_ftemp ? st->fout : st->ftemp;
       a.f_out2 = nullptr;
     }
-    if (last) {  // materialise every intermediate field the reference's state would hold
+    if (last && !skip_aux) {  // materialise every intermediate field the reference's state would hold
       a.pressure = st->pressure; a.hgx = st->hgradpx; a.hgy = st->hgradpy; a.slipx = st->slipx; a.slipy = st->slipy;
       a.Fx = st->Fx; a.Fy = st->Fy; a.feq = st->feq; a.vsq = st->vsq;
       a.kbtx = thermal ? st->kbtx : nullptr; a.kbty = thermal ? st->kbty : nullptr;
@@ -301,9 +302,10 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
     a.log_min = log_mm ? logs->hmin + s : nullptr;
     a.log_max = log_mm ? logs->hmax + s : nullptr;
     a.log_wet = log_wet ? logs->wetted + s : nullptr;
-    const LaunchGeom &g = last ? *g_full : *g_mid;
+    const bool use_full = last && !skip_aux;
+    const LaunchGeom &g = use_full ? *g_full : *g_mid;
     a.rows_per_cta = g.rows_per_cta; a.W = g.W;
-    if (int e = launch_fused(g, a, last ? key_full : key_mid, stream)) return e;
+    if (int e = launch_fused(g, a, use_full ? key_full : key_mid, stream)) return e;
     src_is_A = !src_is_A;
     fsrc_is_ftemp = !fsrc_is_ftemp;
   }

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
           if (a.f_out != nullptr) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) *at(a.f_out, cO.off + k * fs_out8) = fn[k];
-            if (!LEAN && a.f_out2 != nullptr) {
+            if (a.f_out2 != nullptr) {
 #pragma unroll
               for (int k = 0; k < 9; ++k) *at(a.f_out2, cO.off + k * fs_out2_8) = fn[k];
             }

@@ -275,3 +275,31 @@ def test_large_grid_properties(sw, L):
     assert torch.all(st.height.t == 1.0)
     del st
     torch.cuda.empty_cache()
+
+
+def test_skip_aux_keeps_moments_and_populations_current(sw):
+    """SWALBE_LOOP_SKIP_AUX: intermediate chunks of a driver skip the materialisation of feq/pressure/h∇p/slip/F; the
+    moments and fout == ftemp are still exactly the reference's, and a later default call materialises everything."""
+    for kw, pops in ((dict(g=-0.001), False), (dict(τ=0.8), True)):
+        st, sysc, ref, p = _mk(sw, 96, 70, seed=31, prm_kw=kw, tau_pops=pops)
+        sw.fused_steps(st, sysc, 5, skip_aux=True)
+        oc.time_loop(ref, p, nsteps=5)
+        _compare(st, ref, fields=("height", "velx", "vely", "fout", "ftemp"))
+        assert np.all(st.pressure.numpy() == 0.0) and np.all(st.feq.numpy() == 0.0)  # untouched since Sys()
+        sw.fused_steps(st, sysc, 4)
+        oc.time_loop(ref, p, nsteps=4)
+        _compare(st, ref)
+
+
+def test_time_loop_driver_matches_oracle_with_chunking(sw):
+    """time_loop(sys, state) with tdump chunking (mass read-back between fused chunks) == oracle, all fields."""
+    sysc = sw.SysConst(Lx=60, Ly=44, param=sw.Taumucs(Tmax=23, tdump=5, g=-0.001))
+    st = sw.Sys(sysc, "GPU")
+    rng = np.random.default_rng(9)
+    h0 = np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((60, 44))) + 0.06)
+    st.height.set(h0)
+    sw.time_loop(sysc, st)
+    ref = onp.State(60, 44)
+    ref.height[...] = h0
+    oc.time_loop(ref, onp.Params(Tmax=23, tdump=5, g=-0.001))
+    _compare(st, ref)
