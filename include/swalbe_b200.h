@@ -192,6 +192,12 @@ int swalbe_dist_local_rows(const swalbe_dist *dist, int *j_begin, int *j_count);
  * from DEVICE arrays holding only the local slab (Lx * j_count each), then exchange halos */
 int swalbe_dist_set_state(swalbe_dist *dist, const double *height, const double *velx, const double *vely,
                           const double *ftemp, void *stream);
+/* contact-angle field: this rank's rows of cospi.(theta) (Lx * j_count, device); NULL switches back to the scalar of
+ * `params`.  Ghost rows are exchanged once here; call again after moving the substrate. */
+int swalbe_dist_set_theta(swalbe_dist *dist, const double *cospi_theta_slab, void *stream);
+/* min / max / sum / count(h > thresh) of this rank's rows of the height field -> out4[4] (device); combine across
+ * ranks on the host (min, max, +, +).  sum(state.height) src/simulate.jl:8-14, wetted! src/measures.jl:13-17 */
+int swalbe_dist_height_stats(swalbe_dist *dist, double *out4, double thresh, void *stream);
 /* nsteps fused steps with halo exchange overlapped with the interior update */
 int swalbe_dist_time_loop(swalbe_dist *dist, int nsteps, unsigned long long step0, void *stream);
 /* copy this rank's slab rows of height/velx/vely and (optional, may be NULL) the nine population planes out */

@@ -76,6 +76,7 @@ struct swalbe_dist {
   int gh_f;
   double *m[2][3];        // ping-pong sets of (h, ux, uy)
   double *f[2];           // population sets (tau == 1: only f[0], no ghosts)
+  double *ct;             // cospi(theta) slab with GH ghost rows (NULL: scalar theta)
   int cur;                // index of the set holding the current moments
   int fcur;               // index of the set holding the current populations (tau != 1)
   ncclComm_t comm;
@@ -147,7 +148,7 @@ int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nrank
   d->rank = rank; d->nranks = nranks; d->Lx = Lx; d->Ly_global = Ly_global; d->Ly_loc = Ly_loc; d->j_begin = rank * Ly_loc;
   d->prm = *prm;
   d->tau1 = prm->tau == 1.0; d->thermal = prm->use_thermal != 0;
-  if (prm->cospi_theta_field) { delete d; return set_error(SWALBE_ERR_ARG, "theta fields are not supported by the slab runtime yet"); }
+  if (prm->cospi_theta_field) { delete d; return set_error(SWALBE_ERR_ARG, "pass theta fields to the slab runtime with swalbe_dist_set_theta"); }
   d->base = FusedArgs{};
   if (int e = fill_consts(d->base, *prm)) { delete d; return e; }
   d->mplane = (size_t)(Ly_loc + 2 * GH) * Lx;
@@ -195,6 +196,7 @@ int swalbe_dist_destroy(swalbe_dist *d) {
     for (int q = 0; q < 3; ++q) cudaFree(d->m[s][q]);
     cudaFree(d->f[s]);
   }
+  cudaFree(d->ct);
   cudaStreamDestroy(d->s_comp); cudaStreamDestroy(d->s_comm); cudaStreamDestroy(d->s_edge);
   cudaEventDestroy(d->ev_int);
   cudaEventDestroy(d->ev_edges); cudaEventDestroy(d->ev_halo); cudaEventDestroy(d->ev_user);
@@ -258,6 +260,7 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     if (d->tau1) { a.f_in = nullptr; a.f_out = d->f[0]; }
     else { fdst = d->fcur ^ 1; a.f_in = d->f[d->fcur] + fo; a.f_out = d->f[fdst] + fo; }
     a.fstride_in = a.fstride_out = a.fstride_out2 = d->fplane;
+    a.ct_field = d->ct ? d->ct + mo : nullptr;
     a.step = step0 + (unsigned long long)s;
     // edge strips: need the ghost rows of `src` (previous exchange) and the rows the previous interior kernel wrote
     SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_halo, 0));
@@ -305,6 +308,44 @@ int swalbe_dist_get_state(swalbe_dist *d, double *height, double *velx, double *
                               cudaMemcpyDeviceToDevice, user));
   }
   return 0;
+}
+
+int swalbe_dist_set_theta(swalbe_dist *d, const double *ct_slab, void *stream_) {
+  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
+  cudaStream_t user = (cudaStream_t)stream_;
+  SW_CUDA(cudaStreamSynchronize(d->s_comp));  // geometry / kernel flavour may change: drain our own streams first
+  SW_CUDA(cudaStreamSynchronize(d->s_edge));
+  SW_CUDA(cudaStreamSynchronize(d->s_comm));
+  if (!ct_slab) {
+    cudaFree(d->ct);
+    d->ct = nullptr;
+    d->prm.cospi_theta_field = nullptr;
+  } else {
+    if (!d->ct) SW_CUDA(cudaMalloc((void **)&d->ct, d->mplane * sizeof(double)));
+    const size_t n = (size_t)d->Ly_loc * d->Lx;
+    SW_CUDA(cudaMemcpyAsync(d->ct + (size_t)GH * d->Lx, ct_slab, n * sizeof(double), cudaMemcpyDeviceToDevice, user));
+    SW_CUDA(cudaEventRecord(d->ev_user, user));
+    SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_user, 0));
+    if (d->nranks > 1) SW_NCCL(g_nccl.GroupStart());
+    if (int e = exchange_rows(d, d->ct, GH, d->Ly_loc + 2 * GH)) return e;
+    if (d->nranks > 1) SW_NCCL(g_nccl.GroupEnd());
+    SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
+    SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+    SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_halo, 0));
+    SW_CUDA(cudaStreamWaitEvent(user, d->ev_halo, 0));
+    d->prm.cospi_theta_field = d->ct;  // only its NULL-ness matters for the kernel flavour
+  }
+  d->key = make_key(d->prm, d->base.pc.pmode, true);
+  const int Ly_loc = d->Ly_loc;
+  if (int e = choose_geometry(d->Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
+  if (int e = choose_geometry(d->Lx, GH, d->key, &d->g_edge)) return e;
+  return 0;
+}
+
+int swalbe_dist_height_stats(swalbe_dist *d, double *out4, double thresh, void *stream_) {
+  if (!d || !out4) return set_error(SWALBE_ERR_ARG, "NULL argument");
+  // the owned rows of a ghosted plane are one contiguous Lx * Ly_loc block
+  return swalbe_field_stats(out4, d->m[d->cur][0] + (size_t)GH * d->Lx, thresh, d->Lx, d->Ly_loc, stream_);
 }
 
 int swalbe_dist_last_loop_ms(swalbe_dist *d, float *ms) {

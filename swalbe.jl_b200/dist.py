@@ -103,6 +103,20 @@ class DistSim:
         _lib.call("swalbe_dist_set_state", self.handle, height.ptr, velx.ptr, vely.ptr,
                   ftemp.ptr if ftemp is not None else None, self._stream())
 
+    def set_theta(self, cospi_theta_slab):
+        """cospi.(θ) of this rank's rows as a Field of shape (Lx, j_count), or None for the scalar θ of the params."""
+        _lib.call("swalbe_dist_set_theta", self.handle, cospi_theta_slab.ptr if cospi_theta_slab is not None else None,
+                  self._stream())
+
+    def height_stats(self, thresh=0.055):
+        """(min, max, sum, count(h > thresh)) of this rank's rows; combine across ranks with min/max/+/+."""
+        import torch
+
+        out = torch.empty(4, dtype=torch.float64, device="cuda")
+        _lib.call("swalbe_dist_height_stats", self.handle, C.c_void_p(out.data_ptr()), float(thresh), self._stream())
+        mn, mx, sm, cnt = out.cpu().tolist()
+        return mn, mx, sm, int(cnt)
+
     def time_loop(self, nsteps: int, step0: int = 0):
         _lib.call("swalbe_dist_time_loop", self.handle, int(nsteps), int(step0), self._stream())
 

@@ -15,7 +15,8 @@ def main():
     import swalbe_b200 as sw
     from swalbe_b200.dist import DistSim, broadcast_unique_id_torch, slab_of
 
-    out, thermal = sys.argv[1], sys.argv[2] == "1"
+    out, mode = sys.argv[1], sys.argv[2]
+    thermal = mode == "thermal"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl")
@@ -27,6 +28,10 @@ def main():
     n = sim.j_count
     h, z1, z2 = sw.Field(Lx, n).set(slab_of(hg, sim.decomp, rank)), sw.Field(Lx, n), sw.Field(Lx, n)
     sim.set_state(h, z1, z2)
+    theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))  # same draw order as the single-GPU reference run
+    if mode == "theta_field":
+        ct = np.asfortranarray(np.vectorize(sw.cospi)(theta))
+        sim.set_theta(sw.Field(Lx, n).set(slab_of(ct, sim.decomp, rank)))
     sim.time_loop(5)
     sim.time_loop(4, step0=5)
     sim.get_state(h)

@@ -43,6 +43,38 @@ def test_single_rank_slab_matches_oracle(Lx, Ly, tau):
     sim.close()
 
 
+def test_single_rank_slab_theta_field_and_stats():
+    import swalbe_b200 as sw
+    from swalbe_b200.dist import DistSim
+
+    Lx, Ly = 96, 30
+    rng = np.random.default_rng(4)
+    h0 = np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06)
+    theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))
+    ct = np.asfortranarray(np.vectorize(sw.cospi)(theta))
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(n=3, m=2, hmin=0.07))
+    sim = DistSim(sysc, 0, 1, None)
+    h, z1, z2 = sw.Field(Lx, Ly).set(h0), sw.Field(Lx, Ly), sw.Field(Lx, Ly)
+    sim.set_state(h, z1, z2)
+    sim.set_theta(sw.Field(Lx, Ly).set(ct))
+    sim.time_loop(5)
+    mn, mx, sm, cnt = sim.height_stats(1.0)
+    sim.get_state(h)
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = h0
+    p = onp.Params(n=3, m=2, hmin=0.07)
+    oc.time_loop(ref, p, nsteps=5, cospi_theta=ct)
+    assert np.array_equal(h.numpy(), ref.height)
+    assert mn == ref.height.min() and mx == ref.height.max() and cnt == int((ref.height > 1.0).sum())
+    assert abs(sm - ref.height.sum()) < 1e-10 * ref.height.sum()
+    sim.set_theta(None)  # back to the scalar theta of the params
+    sim.time_loop(3)
+    sim.get_state(h)
+    oc.time_loop(ref, p, nsteps=3)
+    assert np.array_equal(h.numpy(), ref.height)
+    sim.close()
+
+
 def test_slab_too_thin_is_rejected():
     import swalbe_b200 as sw
     from swalbe_b200.dist import DistSim
@@ -57,24 +89,28 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("thermal", [False, True])
-def test_two_rank_nccl_matches_single_gpu(tmp_path, thermal):
-    """2 ranks over NCCL == 1 GPU, bit for bit -- including the thermal noise (counter-based on the global cell)."""
+@pytest.mark.parametrize("mode", ["plain", "thermal", "theta_field"])
+def test_two_rank_nccl_matches_single_gpu(tmp_path, mode):
+    """2 ranks over NCCL == 1 GPU, bit for bit -- including the thermal noise (counter-based on the global cell) and a
+    contact-angle field whose ghost rows travel through the same exchange."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     out = tmp_path / "res.npy"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29631", os.path.join(ROOT, "tests", "dist_worker.py"), str(out), "1" if thermal else "0"]
+           "--master-port", "29631", os.path.join(ROOT, "tests", "dist_worker.py"), str(out), mode]
     subprocess.run(cmd, check=True, cwd=ROOT, timeout=600)
     got = np.load(out)
     import swalbe_b200 as sw
 
     Lx, Ly = 520, 96
+    thermal = mode == "thermal"
     sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(kbt=1e-6 if thermal else 0.0, g=-0.001))
     st = sw.Sys(sysc, "GPU", kind="thermal" if thermal else "simple")
     rng = np.random.default_rng(5)
     st.height.set(np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06))
+    theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))
     from swalbe_b200 import _lib
 
-    sw.fused_steps(st, sysc, 9, thermal_seed=77 if thermal else None, pressure_variant=_lib.PRESSURE_POWER_BROAD)
+    sw.fused_steps(st, sysc, 9, thermal_seed=77 if thermal else None, pressure_variant=_lib.PRESSURE_POWER_BROAD,
+                   θ=sw.Field(Lx, Ly).set(theta) if mode == "theta_field" else None)
     assert np.array_equal(got, st.height.numpy())
