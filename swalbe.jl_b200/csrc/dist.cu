@@ -134,6 +134,11 @@ int swalbe_dist_unique_id(void *id128) {
   return 0;
 }
 
+int swalbe_dist_destroy(swalbe_dist *d);
+
+static int dist_allocate(swalbe_dist *d, const void *id128, int rank, int nranks, int Lx, int Ly_loc,
+                         const swalbe_params *prm);
+
 int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nranks, int Lx, int Ly_global,
                        const swalbe_params *prm) {
   if (!out || !prm) return set_error(SWALBE_ERR_ARG, "swalbe_dist_create: NULL argument");
@@ -151,6 +156,17 @@ int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nrank
   if (prm->cospi_theta_field) { delete d; return set_error(SWALBE_ERR_ARG, "pass theta fields to the slab runtime with swalbe_dist_set_theta"); }
   d->base = FusedArgs{};
   if (int e = fill_consts(d->base, *prm)) { delete d; return e; }
+  if (int e = dist_allocate(d, id128, rank, nranks, Lx, Ly_loc, prm)) {
+    swalbe_dist_destroy(d);  // releases whatever was created before the failure
+    return e;
+  }
+  d->cur = 0; d->fcur = 0;
+  *out = d;
+  return 0;
+}
+
+static int dist_allocate(swalbe_dist *d, const void *id128, int rank, int nranks, int Lx, int Ly_loc,
+                         const swalbe_params *prm) {
   d->mplane = (size_t)(Ly_loc + 2 * GH) * Lx;
   d->gh_f = d->tau1 ? 0 : 1;
   d->fplane = (size_t)(Ly_loc + 2 * d->gh_f) * Lx;
@@ -183,8 +199,6 @@ int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nrank
   d->key = make_key(*prm, d->base.pc.pmode, true);
   if (int e = choose_geometry(Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
   if (int e = choose_geometry(Lx, GH, d->key, &d->g_edge)) return e;
-  d->cur = 0; d->fcur = 0;
-  *out = d;
   return 0;
 }
 
@@ -197,10 +211,12 @@ int swalbe_dist_destroy(swalbe_dist *d) {
     cudaFree(d->f[s]);
   }
   cudaFree(d->ct);
-  cudaStreamDestroy(d->s_comp); cudaStreamDestroy(d->s_comm); cudaStreamDestroy(d->s_edge);
-  cudaEventDestroy(d->ev_int);
-  cudaEventDestroy(d->ev_edges); cudaEventDestroy(d->ev_halo); cudaEventDestroy(d->ev_user);
-  cudaEventDestroy(d->ev_t0); cudaEventDestroy(d->ev_t1);
+  if (d->s_comp) cudaStreamDestroy(d->s_comp);
+  if (d->s_comm) cudaStreamDestroy(d->s_comm);
+  if (d->s_edge) cudaStreamDestroy(d->s_edge);
+  cudaEvent_t evs[] = {d->ev_int, d->ev_edges, d->ev_halo, d->ev_user, d->ev_t0, d->ev_t1};
+  for (cudaEvent_t ev : evs)
+    if (ev) cudaEventDestroy(ev);
   delete d;
   return 0;
 }
