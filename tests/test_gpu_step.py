@@ -303,3 +303,50 @@ def test_time_loop_driver_matches_oracle_with_chunking(sw):
     ref.height[...] = h0
     oc.time_loop(ref, onp.Params(Tmax=23, tdump=5, g=-0.001))
     _compare(st, ref)
+
+
+def test_special_values_propagate_like_the_reference(sw):
+    """Zeros, negatives, denormals, huge values, Inf and NaN in the input fields: every IEEE corner (division by zero,
+    0*Inf, overflow in the power chain, the division slow paths) must come out exactly as in the oracle (NaN == NaN)."""
+    Lx, Ly = 48, 20
+    rng = np.random.default_rng(77)
+    h0 = np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06)
+    specials = [0.0, -0.0, -0.05, -1.0, 1e-310, 5e-324, 1e-160, 1e160, 1e300, np.inf, -np.inf, np.nan, 0.05, -0.0500000001]
+    for k, v in enumerate(specials):
+        h0[3 * k % Lx, (5 * k + 2) % Ly] = v
+    u0 = np.asfortranarray(0.01 * rng.standard_normal((Lx, Ly)))
+    u0[7, 3], u0[9, 9], u0[11, 1] = np.nan, np.inf, 1e308
+    for kw, pops in ((dict(g=0.01), False), (dict(τ=0.75, n=3, m=2), True)):
+        okw = {{"τ": "tau"}.get(k, k): v for k, v in kw.items()}
+        sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(**kw))
+        st = sw.Sys(sysc, "GPU")
+        ref = onp.State(Lx, Ly)
+        st.height.set(h0); st.velx.set(u0)
+        ref.height[...] = h0; ref.velx[...] = u0
+        if pops:
+            f0 = np.asfortranarray(0.1 + 0.01 * rng.random((Lx, Ly, 9)))
+            st.ftemp.set(f0); ref.ftemp[...] = f0
+        with np.errstate(all="ignore"):
+            sw.fused_steps(st, sysc, 2)
+            oc.time_loop(ref, onp.Params(**okw), nsteps=2)
+        _compare(st, ref, what=f"{kw}:")
+
+
+def test_spinodal_dewetting_long_run_bitwise(sw):
+    """A physically UNSTABLE configuration (thin random film, disjoining pressure n=3, m=2: spinodal dewetting, C3-style)
+    amplifies any rounding difference exponentially: the perturbation first decays, then grows 6x within 3000 steps.
+    The whole max-min history and the final fields must still equal the oracle bit for bit."""
+    Lx, Ly, nsteps = 192, 160, 3000
+    rng = np.random.default_rng(20261017)
+    h0 = np.asfortranarray(0.2 * (1.0 + 0.01 * rng.standard_normal((Lx, Ly))))
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(n=3, m=2, hmin=0.07, γ=0.02))
+    st = sw.Sys(sysc, "GPU")
+    st.height.set(h0)
+    mn, mx, _ = sw.fused_steps(st, sysc, nsteps, θ=1 / 9, log_minmax=True)
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = h0
+    p = onp.Params(n=3, m=2, hmin=0.07, gamma=0.02)
+    dh, _ = oc.time_loop(ref, p, nsteps=nsteps, cospi_theta=onp.cospi(1 / 9), threads=oc.max_threads(), log_dh=True)
+    assert dh[-1] > 3 * dh.min() and dh.argmin() > 100  # decayed first, then the instability took over
+    assert np.array_equal((mx - mn).cpu().numpy(), dh)
+    _compare(st, ref, fields=("height", "velx", "vely", "pressure", "fout"))
