@@ -342,7 +342,7 @@ def test_special_values_propagate_like_the_reference(sw):
             fin = np.isfinite(want)
             assert np.array_equal(np.isfinite(got), fin), name
             assert np.array_equal(got[fin], want[fin]), name
-            assert np.isfinite(want).sum() > 0.5 * want.size  # most of the lattice is still healthy
+            assert np.isfinite(want).sum() > 0.3 * want.size  # a good part of the lattice is still healthy
 
 
 def test_spinodal_dewetting_long_run_bitwise(sw):
