@@ -83,7 +83,7 @@ struct swalbe_dist {
   cudaStream_t s_comp, s_comm, s_edge;
   cudaEvent_t ev_edges, ev_halo, ev_int, ev_t0, ev_t1, ev_user;
   LaunchGeom g_int, g_edge;
-  KernelKey key;
+  KernelKey key, key_edge;  // interior / edge-strip kernel flavours
   FusedArgs base;
   float last_ms;
 };
@@ -197,8 +197,11 @@ static int dist_allocate(swalbe_dist *d, const void *id128, int rank, int nranks
     SW_NCCL(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
   }
   d->key = make_key(*prm, d->base.pc.pmode, true);
+  d->key_edge = d->key;
+  // interior kernel: bulk-copy row prefetch where it pays (slab planes are cudaMalloc'ed, ghost offset = GH*Lx*8 bytes)
+  d->key.bulk = d->key.lean_pm > 0 && !d->key.thermal && bulk_eligible(Lx, (size_t)Lx * Ly_loc);
   if (int e = choose_geometry(Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
-  if (int e = choose_geometry(Lx, GH, d->key, &d->g_edge)) return e;
+  if (int e = choose_geometry(Lx, GH, d->key_edge, &d->g_edge)) return e;
   return 0;
 }
 
@@ -285,9 +288,9 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_edges, 0));
     a.W = d->g_edge.W; a.rows_per_cta = d->g_edge.rows_per_cta;
     a.jbeg = 0; a.jend = GH;
-    if (int e = launch_fused(d->g_edge, a, d->key, d->s_edge)) return e;
+    if (int e = launch_fused(d->g_edge, a, d->key_edge, d->s_edge)) return e;
     a.jbeg = Ly - GH; a.jend = Ly;
-    if (int e = launch_fused(d->g_edge, a, d->key, d->s_edge)) return e;
+    if (int e = launch_fused(d->g_edge, a, d->key_edge, d->s_edge)) return e;
     SW_CUDA(cudaEventRecord(d->ev_edges, d->s_edge));
     // halo exchange of the freshly written edge rows of `dst`
     SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_edges, 0));
@@ -352,9 +355,11 @@ int swalbe_dist_set_theta(swalbe_dist *d, const double *ct_slab, void *stream_) 
     d->prm.cospi_theta_field = d->ct;  // only its NULL-ness matters for the kernel flavour
   }
   d->key = make_key(d->prm, d->base.pc.pmode, true);
+  d->key_edge = d->key;
   const int Ly_loc = d->Ly_loc;
+  d->key.bulk = d->key.lean_pm > 0 && !d->key.thermal && bulk_eligible(d->Lx, (size_t)d->Lx * Ly_loc);
   if (int e = choose_geometry(d->Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
-  if (int e = choose_geometry(d->Lx, GH, d->key, &d->g_edge)) return e;
+  if (int e = choose_geometry(d->Lx, GH, d->key_edge, &d->g_edge)) return e;
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // Host side of the fused time loop: plan (scratch + launch geometry) and swalbe_time_loop.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cmath>
@@ -24,19 +25,24 @@ struct Variant {
   int nt;
   fused_fn full[2][2];     // [tau1][thermal]           PM = -1: every option at run time
   fused_fn lean[2][5];     // [thermal][pmode]          tau == 1 only, pmode in PM_BROAD_93..PM_FAST_32 (index 0 unused)
+  fused_fn bulk[5];        // [pmode]                   lean, non-thermal, rows prefetched with cp.async.bulk (TMA unit)
 };
 
 // MB1: minimum CTAs/SM requested for the tau == 1 kernels, MB0: for the general-tau kernels (18 more registers)
 #define SW_VARIANT(NT, MB1, MB0)                                                                              \
   {                                                                                                           \
     NT,                                                                                                       \
-        {{k_fused_step<NT, MB0, false, false, -1>, k_fused_step<NT, MB0, false, true, -1>},                    \
-         {k_fused_step<NT, MB1, true, false, -1>, k_fused_step<NT, MB1, true, true, -1>}},                     \
+        {{k_fused_step<NT, MB0, false, false, -1, false>, k_fused_step<NT, MB0, false, true, -1, false>},      \
+         {k_fused_step<NT, MB1, true, false, -1, false>, k_fused_step<NT, MB1, true, true, -1, false>}},       \
+        {{nullptr, k_fused_step<NT, MB1, true, false, PM_BROAD_93, false>,                                     \
+          k_fused_step<NT, MB1, true, false, PM_BROAD_32, false>, k_fused_step<NT, MB1, true, false, PM_FAST_93, false>, \
+          k_fused_step<NT, MB1, true, false, PM_FAST_32, false>},                                              \
+         {nullptr, k_fused_step<NT, MB1, true, true, PM_BROAD_93, false>,                                      \
+          k_fused_step<NT, MB1, true, true, PM_BROAD_32, false>, k_fused_step<NT, MB1, true, true, PM_FAST_93, false>, \
+          k_fused_step<NT, MB1, true, true, PM_FAST_32, false>}},                                              \
     {                                                                                                         \
-      {nullptr, k_fused_step<NT, MB1, true, false, PM_BROAD_93>, k_fused_step<NT, MB1, true, false, PM_BROAD_32>, \
-       k_fused_step<NT, MB1, true, false, PM_FAST_93>, k_fused_step<NT, MB1, true, false, PM_FAST_32>},        \
-      {nullptr, k_fused_step<NT, MB1, true, true, PM_BROAD_93>, k_fused_step<NT, MB1, true, true, PM_BROAD_32>, \
-       k_fused_step<NT, MB1, true, true, PM_FAST_93>, k_fused_step<NT, MB1, true, true, PM_FAST_32>}           \
+      nullptr, k_fused_step<NT, MB1, true, false, PM_BROAD_93, true>, k_fused_step<NT, MB1, true, false, PM_BROAD_32, true>, \
+          k_fused_step<NT, MB1, true, false, PM_FAST_93, true>, k_fused_step<NT, MB1, true, false, PM_FAST_32, true>          \
     }                                                                                                         \
   }
 
@@ -45,6 +51,7 @@ static const Variant g_variants[] = {SW_VARIANT(128, 5, 3), SW_VARIANT(160, 4, 3
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
+  if (k.lean_pm > 0 && k.bulk) return var.bulk[k.lean_pm];
   if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm];
   return var.full[k.tau1 ? 1 : 0][k.thermal ? 1 : 0];
 }
@@ -74,6 +81,7 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   for (int v = 0; v < g_nvariants; ++v) {
     const Variant &var = g_variants[v];
     if (force_nt && var.nt != force_nt) continue;
+    if (key.bulk && Lx < var.nt) continue;  // a strip may cross the periodic x boundary at most once
     fused_fn fn = pick_kernel(var, key);
     int bps = 0;
     const size_t smem = fused_smem_doubles(var.nt) * sizeof(double);
@@ -149,12 +157,18 @@ int launch_fused(const LaunchGeom &g, const FusedArgs &a, const KernelKey &key, 
   return 0;
 }
 
+// cp.async.bulk row prefetch: even Lx (16-byte aligned row segments), at most one periodic wrap per strip, HBM-bound size
+bool bulk_eligible(int Lx, size_t ncells) {
+  return (Lx % 2 == 0) && Lx >= 256 && ncells >= ((size_t)1 << 22) && env_int("SWALBE_BULK", 1) != 0;
+}
+
 // the lean kernels cover: tau == 1, scalar theta, standard slip, no inclination, a known (n, m) pressure mode
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   KernelKey k;
   k.tau1 = p.tau == 1.0;
   k.thermal = p.use_thermal != 0;
   k.lean_pm = 0;
+  k.bulk = false;
   if (want_lean && k.tau1 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
       pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
@@ -187,15 +201,15 @@ using namespace swalbe;
 struct swalbe_plan {
   int Lx, Ly;
   double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
-  LaunchGeom geom[2][2][5];  // [tau1][thermal][lean_pm]
-  bool geom_ok[2][2][5];
+  LaunchGeom geom[2][2][5][2];  // [tau1][thermal][lean_pm][bulk]
+  bool geom_ok[2][2][5][2];
 };
 
 static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
-  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm];
-  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm]) {
+  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk];
+  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk]) {
     if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
-    plan->geom_ok[k.tau1][k.thermal][k.lean_pm] = true;
+    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk] = true;
   }
   *g = &gg;
   return 0;
@@ -208,7 +222,7 @@ int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly) {
   if (int e = check_extent(Lx, Ly)) return e;
   swalbe_plan *p = new swalbe_plan();
   p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr;
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 5; ++k) p->geom_ok[i][j][k] = false;
+  memset(p->geom_ok, 0, sizeof(p->geom_ok));
   cudaError_t e = cudaMalloc((void **)&p->scratch, sizeof(double) * 3 * (size_t)Lx * Ly);
   if (e != cudaSuccess) {
     delete p;
@@ -248,7 +262,13 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
   if (int e = fill_consts(a, *prm)) return e;
   const KernelKey key_full = make_key(*prm, a.pc.pmode, false);
   const bool logs_on = logs && (logs->hmin || logs->wetted);
-  const KernelKey key_mid = make_key(*prm, a.pc.pmode, !logs_on);  // lean kernel for the steps before the last
+  KernelKey key_mid = make_key(*prm, a.pc.pmode, !logs_on);  // lean kernel for the steps before the last
+  // bulk-copy (TMA unit) row prefetch: needs 16-byte aligned row segments, i.e. even Lx and 16-B aligned planes
+  auto aligned16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
+  // Measured on B200: +3 % where the step is HBM-bound (8192^2: 43.2 vs 41.9 GLUPS), -2..3 % where it is latency- or
+  // compute-bound (1024^2, moments-only steps) -> used for large lattices whose populations are written every step.
+  key_mid.bulk = key_mid.lean_pm > 0 && !key_mid.thermal && !lazy && bulk_eligible(Lx, N) && aligned16(st->height) &&
+                 aligned16(st->velx) && aligned16(st->vely) && aligned16(plan->scratch);
   LaunchGeom *g_full = nullptr, *g_mid = nullptr;
   if (int e = plan_geometry(plan, key_full, &g_full)) return e;
   if (int e = plan_geometry(plan, key_mid, &g_mid)) return e;

@@ -99,6 +99,36 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// TMA-style bulk asynchronous copy (cp.async.bulk, SASS UBLKCP): ONE thread moves a whole contiguous row segment
+// global -> shared; completion is signalled on an mbarrier by byte count (complete_tx), not on any scoreboard.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; ++spin) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(b), "r"(parity)
+                 : "memory");
+    if (spin > (1u << 24)) __trap();  // a lost copy must fail loudly instead of hanging the device
+  }
+}
+
 // A row cursor: BYTE offset of (row, own column) inside a plane, advanced one row per iteration with the periodic
 // wrap folded in (no integer division and no index->byte scaling inside the loop).
 struct RowCursor {
@@ -119,7 +149,8 @@ __device__ __forceinline__ const double *at(const double *base, long long byte_o
 }
 __device__ __forceinline__ double *at(double *base, long long byte_off) { return (double *)((char *)base + byte_off); }
 
-// shared-memory layout (in lines of LW = NT+2 doubles; every line has one pad cell on either side)
+// shared-memory layout (in lines of LW = NT+4 doubles; every line has two pad cells on either side, so that column 0 of a
+// line is 16-byte aligned for bulk copies; only the inner pad cell is ever read)
 //   h ring   : 8 slots x 1 line               row N(t) <-> slot t & 7   (rows N(t-3) .. N(t+D) are live)
 //   ring-4   : 4 slots x 5 lines  P F1 F3 F5 F6   row P(t) / F(t) <-> slot t & 3
 //   ring-2   : 2 slots x 2 lines  F7 F8           row F(t) <-> slot t & 1
@@ -131,13 +162,14 @@ constexpr int R2_F7 = 0, R2_F8 = 1, R2_LINES = 2;
 constexpr int RU_UX = 0, RU_UY = 1, RU_LINES = 2;
 constexpr int FUSED_H_SLOTS = 8;
 constexpr int FUSED_LINES = FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES + 4 * RU_LINES;
-constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2); }
+constexpr int FUSED_PAD = 2;
+constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2 * FUSED_PAD); }
 
-template <int NT, int MINB, bool TAU1, bool THERMAL, int PM>
+template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(16) double smem[];
   constexpr bool LEAN = PM >= 0;
-  constexpr int LW = NT + 2;
+  constexpr int LW = NT + 2 * FUSED_PAD;
   constexpr int D = FUSED_D;
   constexpr int R4S = R4_LINES * LW, R2S = R2_LINES * LW, RUS = RU_LINES * LW;  // slot strides in doubles
 
@@ -151,16 +183,29 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   const int wrapLy = a.wrap_y ? a.Ly : INT_MAX;
   const long long row_bytes = (long long)Lx * 8, col_bytes = (long long)ci * 8;
 
-  double *const sh = smem + tid + 1;               // own column, h ring slot 0
+  double *const sh = smem + tid + FUSED_PAD;       // own column, h ring slot 0
   double *const s4 = sh + FUSED_H_SLOTS * LW;      // own column, ring-4 slot 0, line 0
   double *const s2 = s4 + 4 * R4S;                 // own column, ring-2 slot 0, line 0
   double *const su = s2 + 2 * R2S;                 // own column, u ring slot 0, line 0
 
   // Programmatic dependent launch: let the next step's grid start filling SMs as ours drains ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (tid < 2) {  // the two pad cells of every line are never written by the pipeline; keep them finite
-    const int e = tid ? NT + 1 : 0;
+  if (tid < 2 * FUSED_PAD) {  // the pad cells of every line are never written by the pipeline; keep them finite
+    const int e = tid < FUSED_PAD ? tid : NT + tid;
     for (int q = 0; q < FUSED_LINES; ++q) smem[q * LW + e] = 0.0;
+  }
+  // bulk-copy variant: one mbarrier per in-flight prefetch group (4 >= D+1), armed and fed by thread 0 only.
+  // The strip's NT columns are one contiguous run of the row, or two when the strip crosses the periodic x boundary.
+  __shared__ unsigned long long s_bar[4];
+  int seg_a = 0;  // columns [c_start, c_start + seg_a) then [0, NT - seg_a)
+  if (BULK) {
+    seg_a = min(NT, Lx - ci);  // (thread 0: ci == c_start; only thread 0 uses it)
+    if (tid == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mbar_init(&s_bar[q], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
   }
 
   RowCursor cN, cU, cO, cC, cT;
@@ -192,15 +237,39 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     // ---- asynchronous prefetch of the next row ----------------------------------------------------------
     {
       const int tn = t + D;  // h row N(tn) = j0-4+tn is needed for tn in [1, R+6]; u rows F(tn) for tn in [6, R+7]
-      if (S || (tn >= 1 && tn <= R + 6)) cp_async8(sh + (tn & 7) * LW, at(a.h_in, cN.off));
-      cN.advance(row_bytes, wrapLy, col_bytes);
-      if (S || (tn >= 6 && tn <= R + 7)) {
-        double *dst = su + (tn & 3) * RUS;
-        cp_async8(dst + RU_UX * LW, at(a.ux_in, cU.off));
-        cp_async8(dst + RU_UY * LW, at(a.uy_in, cU.off));
+      const bool need_h = S || (tn >= 1 && tn <= R + 6), need_u = S || (tn >= 6 && tn <= R + 7);
+      if (BULK) {
+        if (tid == 0) {
+          unsigned long long *bar = &s_bar[tn & 3];
+          const unsigned nb = (unsigned)NT * 8u;
+          mbar_arrive_expect_tx(bar, (need_h ? nb : 0u) + (need_u ? 2u * nb : 0u));  // 0 bytes: completes at once
+          const unsigned ba = (unsigned)seg_a * 8u, bb = nb - ba;
+          if (need_h) {
+            double *dst = sh + (tn & 7) * LW;
+            bulk_g2s(dst, at(a.h_in, cN.off), ba, bar);
+            if (bb) bulk_g2s(dst + seg_a, at(a.h_in, cN.off - col_bytes), bb, bar);
+          }
+          if (need_u) {
+            double *dst = su + (tn & 3) * RUS;
+            bulk_g2s(dst + RU_UX * LW, at(a.ux_in, cU.off), ba, bar);
+            bulk_g2s(dst + RU_UY * LW, at(a.uy_in, cU.off), ba, bar);
+            if (bb) {
+              bulk_g2s(dst + RU_UX * LW + seg_a, at(a.ux_in, cU.off - col_bytes), bb, bar);
+              bulk_g2s(dst + RU_UY * LW + seg_a, at(a.uy_in, cU.off - col_bytes), bb, bar);
+            }
+          }
+        }
+      } else {
+        if (need_h) cp_async8(sh + (tn & 7) * LW, at(a.h_in, cN.off));
+        if (need_u) {
+          double *dst = su + (tn & 3) * RUS;
+          cp_async8(dst + RU_UX * LW, at(a.ux_in, cU.off));
+          cp_async8(dst + RU_UY * LW, at(a.uy_in, cU.off));
+        }
       }
+      cN.advance(row_bytes, wrapLy, col_bytes);
       cU.advance(row_bytes, wrapLy, col_bytes);
-      cp_async_commit();
+      if (!BULK) cp_async_commit();
     }
     if (S || t >= 0) {
       // ring slots of this iteration
@@ -334,7 +403,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         for (int k = 0; k < 9; ++k) ft_c[k] = ft_n[k];
       }
     }
-    cp_async_wait<D - 1>();  // the group issued D-1 iterations ago (h row N(t+1), u rows F(t+1)) has landed
+    // the prefetch issued D-1 iterations ago (h row N(t+1), u rows F(t+1)) must have landed before the next iteration
+    if (BULK) mbar_wait(&s_bar[(t + 1) & 3], (unsigned)((t + 1) >> 2) & 1u);
+    else cp_async_wait<D - 1>();
     __syncthreads();
   };
 

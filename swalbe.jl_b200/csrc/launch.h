@@ -1,6 +1,7 @@
 // Launch geometry of the fused step kernel, shared by fused.cu (single GPU) and dist.cu (slabs).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 
 namespace swalbe {
 
@@ -20,6 +21,7 @@ struct LaunchGeom {
 struct KernelKey {
   bool tau1, thermal;
   int lean_pm;
+  bool bulk;  // lean non-thermal kernel whose row prefetch uses cp.async.bulk (needs even Lx >= NT and 16-B aligned planes)
 };
 
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);
@@ -31,4 +33,5 @@ struct swalbe_params;
 namespace swalbe {
 int fill_consts(FusedArgs &a, const swalbe_params &p);
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean);
+bool bulk_eligible(int Lx, size_t ncells);
 }
