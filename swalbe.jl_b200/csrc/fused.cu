@@ -158,8 +158,11 @@ int launch_fused(const LaunchGeom &g, const FusedArgs &a, const KernelKey &key, 
 }
 
 // cp.async.bulk row prefetch: even Lx (16-byte aligned row segments), at most one periodic wrap per strip, HBM-bound size
+// SWALBE_BULK: 0 = never, 1 (default) = large lattices only, 2 = whenever the alignment rules allow (tests)
 bool bulk_eligible(int Lx, size_t ncells) {
-  return (Lx % 2 == 0) && Lx >= 256 && ncells >= ((size_t)1 << 22) && env_int("SWALBE_BULK", 1) != 0;
+  const int mode = env_int("SWALBE_BULK", 1);
+  if (mode == 0 || (Lx % 2) != 0 || Lx < 256) return false;
+  return mode >= 2 || ncells >= ((size_t)1 << 22);
 }
 
 // the lean kernels cover: tau == 1, scalar theta, standard slip, no inclination, a known (n, m) pressure mode

@@ -75,6 +75,28 @@ def test_single_rank_slab_theta_field_and_stats():
     sim.close()
 
 
+def test_single_rank_slab_bulk_copy_variant(monkeypatch):
+    """Ghost-row layout + cp.async.bulk row prefetch (what the interior kernel of a large slab uses), forced on."""
+    import swalbe_b200 as sw
+    from swalbe_b200.dist import DistSim
+
+    monkeypatch.setenv("SWALBE_BULK", "2")
+    Lx, Ly = 512, 40
+    rng = np.random.default_rng(12)
+    h0 = np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06)
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(g=-0.001))
+    sim = DistSim(sysc, 0, 1, None)
+    h, z1, z2 = sw.Field(Lx, Ly).set(h0), sw.Field(Lx, Ly), sw.Field(Lx, Ly)
+    sim.set_state(h, z1, z2)
+    sim.time_loop(6)
+    sim.get_state(h)
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = h0
+    oc.time_loop(ref, onp.Params(g=-0.001), nsteps=6)
+    assert np.array_equal(h.numpy(), ref.height)
+    sim.close()
+
+
 def test_slab_too_thin_is_rejected():
     import swalbe_b200 as sw
     from swalbe_b200.dist import DistSim

@@ -363,3 +363,17 @@ def test_spinodal_dewetting_long_run_bitwise(sw):
     assert dh[-1] > 3 * dh.min() and dh.argmin() > 100  # decayed first, then the instability took over
     assert np.array_equal((mx - mn).cpu().numpy(), dh)
     _compare(st, ref, fields=("height", "velx", "vely", "pressure", "fout"))
+
+
+@pytest.mark.parametrize("Lx,Ly", [(256, 40), (600, 50), (1030, 33), (2048, 16)])
+def test_bulk_copy_prefetch_variant_bitwise(sw, monkeypatch, Lx, Ly):
+    """The cp.async.bulk (TMA unit) row-prefetch flavour of the lean kernel, forced on for small lattices: strips that
+    cross the periodic x boundary are fed by two bulk copies; results must not move by a bit."""
+    monkeypatch.setenv("SWALBE_BULK", "2")
+    for nt in (0, 192, 256):
+        if nt:
+            monkeypatch.setenv("SWALBE_NT", str(nt))
+        st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx + Ly, prm_kw=dict(g=-0.001, n=3, m=2, hmin=0.07))
+        sw.fused_steps(st, sysc, 6)
+        oc.time_loop(ref, p, nsteps=6)
+        _compare(st, ref, what=f"NT={nt}:")
