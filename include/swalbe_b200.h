@@ -118,6 +118,12 @@ int swalbe_inclination(double *Fx, double *Fy, const double *height, double alph
  * sum(state.height) src/simulate.jl:8-14; maximum-minimum :56; wetted! src/measures.jl:13-17. */
 int swalbe_field_stats(double *out4, const double *f, double thresh, int Lx, int Ly, void *stream);
 
+/* self-test (diagnostics, not part of the reference's API): runs the library's exact-division helper (shared
+ * reciprocal, zero-numerator fast path) against the compiler's IEEE `/` on n pseudo-random operand triples of every
+ * class (all exponents, +-0, Inf, NaN, denormals, near-equal operands) and writes the number of bitwise mismatches to
+ * *mismatches (device). Must be 0. */
+int swalbe_selftest_division(unsigned long long n, unsigned long long seed, unsigned long long *mismatches, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused time loop (what time_loop / run_* call when the device string is "GPU").
  * ------------------------------------------------------------------------------------------- */

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         const double hc = r1[0];
         const double lap = lap9_bracket(hc, r1[-1], r0[0], r1[1], r2[0], r0[-1], r0[1], r2[1], r2[-1]);
         const double kappa = theta_field ? kappa_from_field(ct_c, a.pc) : a.pc.kappa;
-        const double x = a.pc.hmin / (hc + a.pc.hcrit);
+        const double x = div_exact(a.pc.hmin, hc + a.pc.hcrit);
         const double pw = disjoining_powers(x, pmode, a.pc.n, a.pc.m);
         w4[R4_P * LW] = (-a.pc.gamma * (kappa * pw)) - a.pc.gamma * lap;  // == film_pressure()
       }

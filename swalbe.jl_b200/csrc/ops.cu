@@ -234,6 +234,42 @@ __global__ void __launch_bounds__(ST_THREADS) k_stats_final(double *__restrict__
   if (threadIdx.x == 0) { out4[0] = v.mn; out4[1] = v.mx; out4[2] = v.sm; out4[3] = (double)v.cnt; }
 }
 
+// ---- self-test: div_exact / div2_exact against the compiler's IEEE division ------------------------------------
+__device__ __forceinline__ bool same_double(double x, double y) {
+  if (x != x && y != y) return true;  // NaN == NaN for this purpose
+  return __double_as_longlong(x) == __double_as_longlong(y);
+}
+__global__ void k_selftest_division(unsigned long long n, unsigned long long seed, unsigned long long *mismatch) {
+  unsigned long long bad = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    uint32_t r[4], q[4];
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 2u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), q);
+    unsigned long long ba = ((unsigned long long)r[0] << 32) | r[1], bb = ((unsigned long long)r[2] << 32) | r[3];
+    unsigned long long bc = ((unsigned long long)q[0] << 32) | q[1];
+    const unsigned mode = q[2] & 7u;
+    auto squeeze = [](unsigned long long bits, int lo, int span, uint32_t rnd) {  // exponent into [lo, lo+span)
+      const unsigned long long e = (unsigned long long)(lo + (int)(rnd % (unsigned)span));
+      return (bits & 0x800fffffffffffffull) | (e << 52);
+    };
+    if (mode == 0) { /* raw bit patterns: every exponent, Inf, NaN, denormals */ }
+    else if (mode <= 3) { ba = squeeze(ba, 1023 - 60, 120, q[3]); bb = squeeze(bb, 1023 - 60, 120, q[3] >> 8); bc = squeeze(bc, 1023 - 60, 120, q[3] >> 16); }
+    else if (mode == 4) { ba = squeeze(ba, 600, 850, q[3]); bb = squeeze(bb, 600, 850, q[3] >> 7); bc = squeeze(bc, 600, 850, q[3] >> 14); }
+    else if (mode == 5) { ba &= 0x8000000000000000ull; bb = squeeze(bb, 900, 250, q[3]); }                    // +-0 numerator
+    else if (mode == 6) { ba = squeeze(ba | 0x000fffffffffff00ull, 1000, 50, q[3]); bb = squeeze(bb & 0xfff00000000000ffull, 1000, 50, q[3] >> 9); }
+    else { bb = squeeze(bb | 0x000fffffffffffffull, 1010, 30, q[3]); bc &= 0x8000000000000000ull; ba = squeeze(ba, 1010, 30, q[3] >> 5); }
+    const double a = __longlong_as_double((long long)ba), b = __longlong_as_double((long long)bb),
+                 c = __longlong_as_double((long long)bc);
+    double q1, q2;
+    div2_exact(a, c, b, q1, q2);
+    bad += !same_double(div_exact(a, b), a / b);
+    bad += !same_double(q1, a / b);
+    bad += !same_double(q2, c / b);
+  }
+  if (bad) atomicAdd(mismatch, bad);
+}
+
 }  // namespace swalbe
 
 using namespace swalbe;
@@ -357,6 +393,14 @@ int swalbe_inclination(double *Fx, double *Fy, const double *height, double alph
   if (int e = check_extent(Lx, Ly)) return e;
   REQUIRE(Fx); REQUIRE(Fy); REQUIRE(height);
   k_inclination<<<grid2(Lx, Ly), block2(), 0, (cudaStream_t)stream>>>(Fx, Fy, height, alpha_x, alpha_y, factor, Lx, Ly);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_selftest_division(unsigned long long n, unsigned long long seed, unsigned long long *mismatches, void *stream) {
+  REQUIRE(mismatches);
+  SW_CUDA(cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  k_selftest_division<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(n, seed, mismatches);
   SW_LAUNCH_CHECK();
   return 0;
 }

@@ -195,3 +195,19 @@ def test_thermal_moments_at_scale(G):
     k2x, k2y = sw.Field(256, 192), sw.Field(256, 192)
     sw.thermal(k2x, k2y, h0, kbt, mu, delta, seed=99, step=5)
     assert np.array_equal(st.kbtx.numpy(), k2x.numpy()) and np.array_equal(st.kbty.numpy(), k2y.numpy())
+
+
+def test_exact_division_helper_matches_ieee_division(G):
+    """div_exact/div2_exact (shared reciprocal, +-0 numerators on the fast path) must be bit-identical to `/` for every
+    operand class; 2^28 random triples x 3 quotients each."""
+    import ctypes as C
+
+    import torch
+
+    import swalbe_b200 as sw
+    from swalbe_b200 import _lib
+
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed in (1, 20261017):
+        _lib.call("swalbe_selftest_division", 1 << 27, seed, C.c_void_p(out.data_ptr()), sw._stream())
+        assert out.item() == 0, f"{out.item()} mismatching quotients (seed {seed})"
