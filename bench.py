@@ -33,7 +33,7 @@ B_ALG = 144.0  # algorithmic bytes per lattice update
 
 def initial_height(L, Ly=None, j0=0, Ly_global=None, workload="film"):
     """Synthetic initial conditions of SURVEY.md 8d as NumPy F-arrays (rows j0 .. j0+Ly of a L x Ly_global lattice).
-    film/thermal: h = 1 + 1e-3 sin(2π i/Lx) sin(2π j/Ly); droplet: spherical cap (singledroplet, radius L/4, θ0 = 1/6,
+    film/thermal: h = 1 + 1e-3 sin(2π i/Lx) sin(2π j/Ly); droplet: spherical cap (singledroplet, radius min(L/4, 256), θ0 = 1/6,
     precursor 0.05); spinodal: h = 1 + 0.01 N(0,1), seed 20261017."""
     import numpy as np
 
@@ -42,7 +42,7 @@ def initial_height(L, Ly=None, j0=0, Ly_global=None, workload="film"):
     i = np.arange(L, dtype=np.float64)[:, None]
     j = (j0 + np.arange(Ly, dtype=np.float64))[None, :]
     if workload == "droplet":
-        radius, c = L / 4.0, (L // 2, Ly_global // 2)
+        radius, c = min(L / 4.0, 256.0), (L // 2, Ly_global // 2)  # C2: radius 256 at 1024^2 (larger caps are unstable)
         circ = np.sqrt((i + 1 - c[0]) ** 2 + (j + 1 - c[1]) ** 2)
         inside = circ <= radius
         cap = (np.cos(np.arcsin(np.where(inside, circ / radius, 0.0))) - math.cos(math.pi / 6)) * radius
@@ -167,7 +167,7 @@ def run_reference(args, rank):
 def workload_config(args):
     what = {"film": "Taumucs defaults (n=9,m=3,theta=1/9), flat film + sine perturbation (SURVEY 8d C5)",
             "thermal": "Taumucs defaults + thermal noise kbt=1e-7 generated in-kernel (Philox), flat film + sine (C4)",
-            "droplet": "n=3,m=2,hmin=0.07,theta=1/9, spherical-cap droplet radius L/4 on a 0.05 precursor (C2)",
+            "droplet": "n=3,m=2,hmin=0.07,theta=1/9, spherical-cap droplet radius min(L/4,256) on a 0.05 precursor (C2)",
             "spinodal": "n=3,m=2,hmin=0.07,gamma=0.01, randomly perturbed film h=1+0.01 N(0,1) (C3)"}[args.workload]
     weak = args.gpus == 1 or getattr(args, "scaling", "weak") == "weak"
     rows = args.L if weak else args.L // args.gpus
