@@ -165,14 +165,14 @@ bool bulk_eligible(int Lx, size_t ncells) {
   return mode >= 2 || ncells >= ((size_t)1 << 22);
 }
 
-// the lean kernels cover: tau == 1, scalar theta, standard slip, no inclination, a known (n, m) pressure mode
+// the lean kernels cover: tau == 1, g == 0, scalar theta, standard slip, no inclination, a known (n, m) pressure mode
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   KernelKey k;
   k.tau1 = p.tau == 1.0;
   k.thermal = p.use_thermal != 0;
   k.lean_pm = 0;
   k.bulk = false;
-  if (want_lean && k.tau1 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
+  if (want_lean && k.tau1 && p.g == 0.0 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
       pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
   return k;

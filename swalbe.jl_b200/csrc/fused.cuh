@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
           Fy = Fy + (hc * a.incl_ay) * a.incl_factor;
         }
         double fe[9], vsq, fs[9];
-        equilibrium_site(hc, ux_c, uy_c, a.ec, fe, vsq);
+        equilibrium_site<LEAN>(hc, ux_c, uy_c, a.ec, fe, vsq);  // the lean flavour is only chosen for g == 0
         if (TAU1) collide_site_tau1(fe, Fx, Fy, fs);
         else collide_site(ft_c, fe, Fx, Fy, a.omega, a.invtau, fs);
         w4[R4_F1 * LW] = fs[1]; w4[R4_F3 * LW] = fs[3]; w4[R4_F5 * LW] = fs[5]; w4[R4_F6 * LW] = fs[6];
