@@ -330,11 +330,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         if (THERMAL) {
           long long jg = (a.jglobal0 + rF) % a.Ly_global;
           if (jg < 0) jg += a.Ly_global;
-          double n1, n2;
-          normal_pair(a.seed, a.step, (unsigned long long)ci + (unsigned long long)Lx * (unsigned long long)jg, n1, n2);
-          const double amp = thermal_amplitude(hc, a.tc);
-          kx = n1 * amp;
-          ky = n2 * amp;
+          thermal_pair(hc, a.tc, a.seed, a.step, (unsigned long long)ci + (unsigned long long)Lx * (unsigned long long)jg, kx, ky);
           Fx = Fx - kx;
           Fy = Fy - ky;
         }

@@ -167,11 +167,10 @@ __global__ void __launch_bounds__(BX *BY) k_thermal(double *__restrict__ kx, dou
                                                      const double *__restrict__ h, ThermalConsts tc,
                                                      unsigned long long seed, unsigned long long step, int Lx, int Ly) {
   SITE_GUARD();
-  double n1, n2;
-  normal_pair(seed, step, (unsigned long long)c, n1, n2);
-  const double amp = thermal_amplitude(h[c], tc);
-  kx[c] = n1 * amp;
-  ky[c] = n2 * amp;
+  double a, b;
+  thermal_pair(h[c], tc, seed, step, (unsigned long long)c, a, b);
+  kx[c] = a;
+  ky[c] = b;
 }
 
 __global__ void __launch_bounds__(BX *BY) k_inclination(double *__restrict__ Fx, double *__restrict__ Fy,
