@@ -207,6 +207,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback on the b200 arm)")
     torch.cuda.set_device(local_rank)
+    # nvidia-smi needs seconds to come up on a busy 8-GPU box: start the clock sampler now, on rank 0 only
+    early_sampler = ClockSampler(local_rank) if rank == 0 else None
     if rank == 0:
         ge.build()
     if world > 1:
@@ -232,7 +234,7 @@ def main():
         st.height.set(h0)
         run = lambda n, s0=0: sw.fused_steps(st, sysc, n, thermal_seed=thermal_seed, step0=s0,  # noqa: E731
                                              pressure_variant=_lib.PRESSURE_POWER_BROAD)
-        sampler = ClockSampler(local_rank)
+        sampler = early_sampler
         run(W)
         torch.cuda.synchronize()
         l0 = lib.swalbe_launch_count()
@@ -308,7 +310,9 @@ def main():
         zero = sw.Field(L, rows)
         stream = sw._stream()
         _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
-        sampler = ClockSampler(local_rank)
+        sampler = early_sampler if early_sampler is not None else ClockSampler.__new__(ClockSampler)
+        if early_sampler is None:  # ranks > 0 do not sample; the context manager below is a no-op for them
+            sampler.rows, sampler.proc, sampler.t0, sampler.t1 = [], None, None, None
         _lib.call("swalbe_dist_time_loop", handle, W, 0, stream)
         torch.cuda.synchronize()
         dist.barrier()
