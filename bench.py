@@ -73,8 +73,10 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, enabled=True):
         self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
+        if not enabled:  # ranks > 0: same interface, no nvidia-smi process
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -208,7 +210,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback on the b200 arm)")
     torch.cuda.set_device(local_rank)
     # nvidia-smi needs seconds to come up on a busy 8-GPU box: start the clock sampler now, on rank 0 only
-    early_sampler = ClockSampler(local_rank) if rank == 0 else None
+    early_sampler = ClockSampler(local_rank, enabled=rank == 0)
     if rank == 0:
         ge.build()
     if world > 1:
@@ -310,9 +312,7 @@ def main():
         zero = sw.Field(L, rows)
         stream = sw._stream()
         _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
-        sampler = early_sampler if early_sampler is not None else ClockSampler.__new__(ClockSampler)
-        if early_sampler is None:  # ranks > 0 do not sample; the context manager below is a no-op for them
-            sampler.rows, sampler.proc, sampler.t0, sampler.t1 = [], None, None, None
+        sampler = early_sampler
         _lib.call("swalbe_dist_time_loop", handle, W, 0, stream)
         torch.cuda.synchronize()
         dist.barrier()
