@@ -6,8 +6,8 @@
 #include <algorithm>
 #include <cmath>
 
-#include "fused.cuh"
 #include "launch.h"
+#include "variants.h"
 
 namespace swalbe {
 
@@ -18,41 +18,13 @@ __global__ void k_init_logs(double *mn, double *mx, unsigned long long *wet, int
   if (wet) wet[i] = 0ull;
 }
 
-// ---- kernel variant table ------------------------------------------------------------------------
-typedef void (*fused_fn)(const FusedArgs);
-
-struct Variant {
-  int nt;
-  fused_fn full[2][2];     // [tau1][thermal]           PM = -1: every option at run time
-  fused_fn lean[2][5];     // [thermal][pmode]          tau == 1 only, pmode in PM_BROAD_93..PM_FAST_32 (index 0 unused)
-  fused_fn bulk[5];        // [pmode]                   lean, non-thermal, rows prefetched with cp.async.bulk (TMA unit)
-};
-
-// MB1: minimum CTAs/SM requested for the tau == 1 kernels, MB0: for the general-tau kernels (18 more registers)
-#define SW_VARIANT(NT, MB1, MB0)                                                                              \
-  {                                                                                                           \
-    NT,                                                                                                       \
-        {{k_fused_step<NT, MB0, false, false, -1, false>, k_fused_step<NT, MB0, false, true, -1, false>},      \
-         {k_fused_step<NT, MB1, true, false, -1, false>, k_fused_step<NT, MB1, true, true, -1, false>}},       \
-        {{nullptr, k_fused_step<NT, MB1, true, false, PM_BROAD_93, false>,                                     \
-          k_fused_step<NT, MB1, true, false, PM_BROAD_32, false>, k_fused_step<NT, MB1, true, false, PM_FAST_93, false>, \
-          k_fused_step<NT, MB1, true, false, PM_FAST_32, false>},                                              \
-         {nullptr, k_fused_step<NT, MB1, true, true, PM_BROAD_93, false>,                                      \
-          k_fused_step<NT, MB1, true, true, PM_BROAD_32, false>, k_fused_step<NT, MB1, true, true, PM_FAST_93, false>, \
-          k_fused_step<NT, MB1, true, true, PM_FAST_32, false>}},                                              \
-    {                                                                                                         \
-      nullptr, k_fused_step<NT, MB1, true, false, PM_BROAD_93, true>, k_fused_step<NT, MB1, true, false, PM_BROAD_32, true>, \
-          k_fused_step<NT, MB1, true, false, PM_FAST_93, true>, k_fused_step<NT, MB1, true, false, PM_FAST_32, true>          \
-    }                                                                                                         \
-  }
-
-static const Variant g_variants[] = {SW_VARIANT(128, 5, 3), SW_VARIANT(160, 4, 3), SW_VARIANT(192, 3, 2),
-                                     SW_VARIANT(224, 3, 2), SW_VARIANT(256, 2, 2)};
+// ---- kernel variant table (instantiated in fused_v*.cu) ---------------------------------------------
+static const Variant *const g_variants[] = {&g_variant_128, &g_variant_160, &g_variant_192, &g_variant_224, &g_variant_256};
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
-  if (k.lean_pm > 0 && k.bulk) return var.bulk[k.lean_pm];
-  if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm];
+  if (k.lean_pm > 0 && k.bulk) return var.bulk[k.lean_pm][k.gz ? 1 : 0];
+  if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm][k.gz ? 1 : 0];
   return var.full[k.tau1 ? 1 : 0][k.thermal ? 1 : 0];
 }
 
@@ -79,7 +51,7 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   const int fill = 8 + FUSED_D;
   double best_cost = 1e300;
   for (int v = 0; v < g_nvariants; ++v) {
-    const Variant &var = g_variants[v];
+    const Variant &var = *g_variants[v];
     if (force_nt && var.nt != force_nt) continue;
     if (key.bulk && Lx < var.nt) continue;  // a strip may cross the periodic x boundary at most once
     fused_fn fn = pick_kernel(var, key);
@@ -136,7 +108,7 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
 }
 
 int launch_fused(const LaunchGeom &g, const FusedArgs &a, const KernelKey &key, cudaStream_t stream) {
-  fused_fn fn = pick_kernel(g_variants[g.variant], key);
+  fused_fn fn = pick_kernel(*g_variants[g.variant], key);
   const int nrows = a.jend - a.jbeg;
   if (nrows <= 0) return 0;
   dim3 grid(g.nstrips, (nrows + a.rows_per_cta - 1) / a.rows_per_cta);
@@ -165,14 +137,16 @@ bool bulk_eligible(int Lx, size_t ncells) {
   return mode >= 2 || ncells >= ((size_t)1 << 22);
 }
 
-// the lean kernels cover: tau == 1, g == 0, scalar theta, standard slip, no inclination, a known (n, m) pressure mode
+// the lean kernels cover: tau == 1, scalar theta, standard slip, no inclination, a known (n, m) pressure mode
+// (with a further specialisation for gravity == 0)
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   KernelKey k;
   k.tau1 = p.tau == 1.0;
   k.thermal = p.use_thermal != 0;
   k.lean_pm = 0;
   k.bulk = false;
-  if (want_lean && k.tau1 && p.g == 0.0 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
+  k.gz = p.g == 0.0;
+  if (want_lean && k.tau1 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
       pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
   return k;
@@ -204,15 +178,15 @@ using namespace swalbe;
 struct swalbe_plan {
   int Lx, Ly;
   double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
-  LaunchGeom geom[2][2][5][2];  // [tau1][thermal][lean_pm][bulk]
-  bool geom_ok[2][2][5][2];
+  LaunchGeom geom[2][2][5][2][2];  // [tau1][thermal][lean_pm][bulk][gz]
+  bool geom_ok[2][2][5][2][2];
 };
 
 static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
-  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk];
-  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk]) {
+  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz];
+  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz]) {
     if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
-    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk] = true;
+    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz] = true;
   }
   *g = &gg;
   return 0;

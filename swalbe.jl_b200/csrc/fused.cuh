@@ -23,7 +23,7 @@
 //
 // Two flavours per (NT, tau==1, thermal): PM >= 0 is the LEAN kernel for the steps in the middle of a
 // swalbe_time_loop call (scalar theta, standard slip, no inclination, no logs, no materialisation, pressure mode
-// PM fixed at compile time); PM == -1 is the FULL kernel with every option decided at run time (used for the
+// PM fixed at compile time, optionally GZ: gravity == 0 folded in); PM == -1 is the FULL kernel with every option decided at run time (used for the
 // last step of a call, which materialises the reference's intermediate fields, and for all uncommon options).
 //
 // All arithmetic comes from common.cuh (reference evaluation order, no FMA contraction).
@@ -165,7 +165,7 @@ constexpr int FUSED_LINES = FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES + 4 * RU
 constexpr int FUSED_PAD = 2;
 constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2 * FUSED_PAD); }
 
-template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK>
+template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(16) double smem[];
   constexpr bool LEAN = PM >= 0;
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
           Fy = Fy + (hc * a.incl_ay) * a.incl_factor;
         }
         double fe[9], vsq, fs[9];
-        equilibrium_site<LEAN>(hc, ux_c, uy_c, a.ec, fe, vsq);  // the lean flavour is only chosen for g == 0
+        equilibrium_site<GZ>(hc, ux_c, uy_c, a.ec, fe, vsq);  // GZ instantiations are only chosen for g == 0
         if (TAU1) collide_site_tau1(fe, Fx, Fy, fs);
         else collide_site(ft_c, fe, Fx, Fy, a.omega, a.invtau, fs);
         w4[R4_F1 * LW] = fs[1]; w4[R4_F3 * LW] = fs[3]; w4[R4_F5 * LW] = fs[5]; w4[R4_F6 * LW] = fs[6];

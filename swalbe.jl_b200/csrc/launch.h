@@ -22,6 +22,7 @@ struct KernelKey {
   bool tau1, thermal;
   int lean_pm;
   bool bulk;  // lean non-thermal kernel whose row prefetch uses cp.async.bulk (needs even Lx >= NT and 16-B aligned planes)
+  bool gz;    // gravity == 0: lean kernels with the (+-0)*h terms of the equilibrium folded away
 };
 
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);
