@@ -214,7 +214,8 @@ function _loop(sys, state, θ, verbose)
             verbose && println("Time step $t mass is $(round(mass, digits=3))")
         end
         nxt = min(Tmax + 1, (t ÷ tdump + 1) * tdump)
-        fused_steps!(state, sys, nxt - t; θ = θ)
+        # SWALBE_LOOP_SKIP_AUX (= 2) on all but the final chunk: feq/pressure/h∇p/slip/F are materialised once, at the end
+        fused_steps!(state, sys, nxt - t; θ = θ, flags = nxt <= Tmax ? 2 : 0)
         t = nxt
     end
     return state
