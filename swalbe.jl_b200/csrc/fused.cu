@@ -33,21 +33,28 @@ static int env_int(const char *name, int dflt) {
   return s && *s ? atoi(s) : dflt;
 }
 
-// Launch geometry.  Time model calibrated on B200: a CTA marching R rows runs R + 8 + D pipeline
-// iterations; one iteration (one row of every CTA resident on an SM) costs
-//   t_iter(n) = max(0.87 us, 0.56 us + 1.86 ns * n),   n = resident threads on the SM
-// (0.87 us: dependent-chain latency of a lone CTA, 100^2 grid; 1.09 us at n = 320, 2048^2; 1.63 us at n = 576, the
-// compute-bound moments-only rate at 8192^2), and the whole launch cannot beat the HBM floor of 120 B per lattice
-// update at 5.5 TB/s (tools/membench.cu).  Large grids therefore want whole waves of long chunks, small grids many
-// short chunks (latency bound).
+// Launch geometry.  Time model calibrated on B200.  A CTA marching R rows runs R + 8 + D pipeline
+// iterations; one iteration of every CTA resident on an SM costs
+//   t_iter = max(0.87 us, (CTAs on the SM) * NT * c(NT)),   c(NT) = (1.80 + 0.0018 NT) ns per thread-row
+// for launches of several waves, and max(0.87 us, 0.56 us + 1.86 ns * resident threads) for a single partial wave
+// (0.87 us: dependent-chain latency of a lone CTA, measured on the 100^2 grid; c(NT) fitted to the compute-bound
+// moments-only rates at 8192^2: 2.02 / 2.10 / 2.14 / 2.23 ns for NT = 128 / 160 / 192 / 224 -- more, smaller CTAs hide the
+// per-row barrier better), x1.75 for the thermal kernels, x1.3 for the run-time-option kernel.  The launch cannot beat
+// the HBM floor (120 B per lattice update, 48 B when the populations are not written, at 5.5 TB/s, tools/membench.cu);
+// when several widths are HBM-bound the one with the fewest halo columns per CTA that still keeps >= 3 CTAs per SM wins
+// (measured at 8192^2: NT = 224 and 160 lead, 256 with 2 CTAs/SM trails by 4 %).
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   int dev = 0, nsm = 148;
   SW_CUDA(cudaGetDevice(&dev));
   SW_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int force_nt = env_int("SWALBE_NT", 0);
   const int rmax = std::max(1, env_int("SWALBE_RMAX", 128));
-  auto t_iter = [](double n) { return std::max(0.87, 0.56 + 0.00186 * n); };
-  const double hbm_floor = (double)Lx * (double)nrows * 120.0 / 5.5e6;  // us
+  const double flavour = (key.thermal ? 1.75 : 1.0) * (key.lean_pm > 0 ? 1.0 : 1.3);
+  auto t_iter = [&](int ctas_on_sm, int nt) {
+    return std::max(0.87, ctas_on_sm * nt * (1.80 + 0.0018 * nt) * 1e-3 * flavour);
+  };
+  const double hbm_floor = (double)Lx * (double)nrows * (key.lazy ? 48.0 : 120.0) / 5.5e6;  // us
+  double best_bound_eff = -1.0;  // best W/NT among HBM-bound candidates
   const int fill = 8 + FUSED_D;
   double best_cost = 1e300;
   for (int v = 0; v < g_nvariants; ++v) {
@@ -85,13 +92,23 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
       double cost;
       if (ctas <= slots) {  // a single, possibly partial wave: c CTAs share an SM
         const int c = (int)((ctas + nsm - 1) / nsm);
-        cost = (R + fill) * t_iter((double)c * var.nt);
+        // a single, possibly partial wave (small lattices): fit to the 100^2 .. 2048^2 sweeps
+        cost = (R + fill) * std::max(0.87, (0.56 + 0.00186 * c * var.nt) * flavour);
       } else {
         const double waves = (double)ctas / (double)slots;  // CTAs are re-issued as slots free up
-        cost = std::ceil(waves - 1e-9) * (R + fill) * t_iter((double)bps * var.nt);
+        cost = std::ceil(waves - 1e-9) * (R + fill) * t_iter(bps, var.nt);
       }
-      cost = std::max(cost, hbm_floor) + 0.01 * cost;
-      if (cost < best_cost) {
+      bool take;
+      if (cost <= 0.95 * hbm_floor && bps >= 3) {  // HBM-bound: prefer the least redundant strip decomposition
+        const double eff = (double)W / var.nt - 1e-6 * cost;
+        take = eff > best_bound_eff;
+        if (take) best_bound_eff = eff;
+        cost = hbm_floor;
+      } else {
+        cost = std::max(cost, hbm_floor) + 0.01 * cost;
+        take = best_bound_eff < 0.0 && cost < best_cost;
+      }
+      if (take) {
         best_cost = cost;
         g->nt = var.nt; g->variant = v; g->W = W; g->nstrips = nstrips; g->rows_per_cta = R; g->nchunks = nchunks;
         g->blocks_per_sm = bps;
@@ -146,6 +163,7 @@ KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   k.lean_pm = 0;
   k.bulk = false;
   k.gz = p.g == 0.0;
+  k.lazy = false;
   if (want_lean && k.tau1 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
       pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
@@ -178,15 +196,15 @@ using namespace swalbe;
 struct swalbe_plan {
   int Lx, Ly;
   double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
-  LaunchGeom geom[2][2][5][2][2];  // [tau1][thermal][lean_pm][bulk][gz]
-  bool geom_ok[2][2][5][2][2];
+  LaunchGeom geom[2][2][5][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy]
+  bool geom_ok[2][2][5][2][2][2];
 };
 
 static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
-  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz];
-  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz]) {
+  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy];
+  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy]) {
     if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
-    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz] = true;
+    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy] = true;
   }
   *g = &gg;
   return 0;
@@ -246,6 +264,7 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
   // compute-bound (1024^2, moments-only steps) -> used for large lattices whose populations are written every step.
   key_mid.bulk = key_mid.lean_pm > 0 && !key_mid.thermal && !lazy && bulk_eligible(Lx, N) && aligned16(st->height) &&
                  aligned16(st->velx) && aligned16(st->vely) && aligned16(plan->scratch);
+  key_mid.lazy = lazy;
   LaunchGeom *g_full = nullptr, *g_mid = nullptr;
   if (int e = plan_geometry(plan, key_full, &g_full)) return e;
   if (int e = plan_geometry(plan, key_mid, &g_mid)) return e;

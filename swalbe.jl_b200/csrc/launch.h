@@ -23,6 +23,7 @@ struct KernelKey {
   int lean_pm;
   bool bulk;  // lean non-thermal kernel whose row prefetch uses cp.async.bulk (needs even Lx >= NT and 16-B aligned planes)
   bool gz;    // gravity == 0: lean kernels with the (+-0)*h terms of the equilibrium folded away
+  bool lazy;  // populations are not written by this launch (geometry only: lower HBM floor)
 };
 
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);
