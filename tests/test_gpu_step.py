@@ -377,3 +377,42 @@ def test_bulk_copy_prefetch_variant_bitwise(sw, monkeypatch, Lx, Ly):
         sw.fused_steps(st, sysc, 6)
         oc.time_loop(ref, p, nsteps=6)
         _compare(st, ref, what=f"NT={nt}:")
+
+
+def test_large_odd_lattice_fused_equals_operator_kernels(sw):
+    """Odd extents at multi-strip / multi-wave scale (2049 x 1025: unaligned rows, LDGSTS prefetch, a last strip that
+    wraps): the fused loop against the seven per-operator kernels, both on the GPU, every field bit for bit."""
+    import torch
+
+    Lx, Ly = 2049, 1025
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(g=-0.0005, n=3, m=2, hmin=0.07))
+    st, st2 = sw.Sys(sysc, "GPU"), sw.Sys(sysc, "GPU")
+    gen = torch.Generator("cuda").manual_seed(11)
+    h0 = 1.0 + 0.05 * torch.randn((Ly, Lx), device="cuda", dtype=torch.float64, generator=gen)
+    for s in (st, st2):
+        s.height.t.copy_(h0)
+    sw.fused_steps(st, sysc, 5)
+    for _ in range(5):
+        sw.filmpressure(st2, sysc); sw.hgradp(st2); sw.slippage(st2, sysc); sw.update(st2)
+        sw.equilibrium(st2, sysc); sw.BGKandStream(st2, sysc); sw.moments(st2)
+    for name in STATE_FIELDS:
+        assert torch.equal(getattr(st, name).t, getattr(st2, name).t), name
+
+
+def test_non_default_stream_is_honoured(sw):
+    """Every entry point runs on the caller's stream: work queued on a side stream must be ordered with that stream's
+    other work (a fill that precedes it, a copy that follows it) without any device-wide synchronisation."""
+    import torch
+
+    st, sysc, ref, p = _mk(sw, 200, 64, seed=4, prm_kw=dict(g=-0.001))
+    side = torch.cuda.Stream()
+    h0 = st.height.numpy()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        st.height.t.mul_(1.0)            # same-stream producer
+        sw.fused_steps(st, sysc, 4)      # uses torch.cuda.current_stream() == side
+        out = st.height.t.clone()        # same-stream consumer
+    side.synchronize()
+    oc.time_loop(ref, p, nsteps=4)
+    assert np.array_equal(np.asfortranarray(out.cpu().numpy().T), ref.height)
+    assert not np.array_equal(h0, ref.height)
