@@ -10,21 +10,26 @@
 // `rows_per_cta` rows.  The three dependent stencils are software-pipelined over rows through shared-memory
 // rings, one __syncthreads per row:
 //
-//   iteration t:  prefetch  h row N(t+D), u rows F(t+D)   global -> smem with cp.async (LDGSTS) D rows ahead,
-//                                                          so no thread ever waits on a global load
+//   iteration t:  prefetch  h row N(t+D), u rows F(t+D)   global -> smem D rows ahead, asynchronously: per-thread
+//                                                          cp.async (LDGSTS), or -- BULK flavour, large even-Lx
+//                                                          lattices -- cp.async.bulk through the TMA unit, one
+//                                                          thread per row segment, completion on an mbarrier;
+//                                                          no thread ever waits on a global load
 //                 B: film pressure   row P = j0-5+t        reads h rows P-1..P+1 from the h ring     -> p ring
 //                 C: forces, feq, f* row F = j0-7+t        reads p rows F-1..F+1, h and u of row F   -> f* rings
 //                 D: pull + moments  row O = j0-9+t        reads f* rows O-1..O+1 (x-shifted)        -> HBM
 //
 // B, C and D of one iteration read only rows written in EARLIER iterations, so in the steady state (rows 9..R+4
 // of a chunk, instantiated without any stage predicate) the three instruction streams form one basic block and
-// interleave freely (ILP); nothing but addresses lives in registers across iterations.  Redundant work: the 8
-// halo columns per CTA and the 9-row pipeline fill per chunk of rows; nothing is recomputed in y inside a chunk.
+// interleave freely (ILP); only addresses and the three own-column populations f*0, f*2, f*4 live in registers across
+// iterations.  Redundant work: the 8 halo columns per CTA and the 9-row pipeline fill per chunk of rows; nothing is
+// recomputed in y inside a chunk.
 //
 // Two flavours per (NT, tau==1, thermal): PM >= 0 is the LEAN kernel for the steps in the middle of a
-// swalbe_time_loop call (scalar theta, standard slip, no inclination, no logs, no materialisation, pressure mode
-// PM fixed at compile time, optionally GZ: gravity == 0 folded in); PM == -1 is the FULL kernel with every option decided at run time (used for the
-// last step of a call, which materialises the reference's intermediate fields, and for all uncommon options).
+// swalbe_time_loop call (scalar theta, standard slip, no inclination, no logs, no materialisation, pressure mode PM
+// fixed at compile time, optionally GZ: gravity == 0 folded in, optionally BULK); PM == -1 is the FULL kernel with
+// every option decided at run time (used for the last step of a call, which materialises the reference's
+// intermediate fields, and for all uncommon options).  Instantiated per CTA width in fused_v*.cu (variants.h).
 //
 // All arithmetic comes from common.cuh (reference evaluation order, no FMA contraction).
 #pragma once
