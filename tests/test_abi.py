@@ -94,3 +94,19 @@ def test_taumucs_defaults():
     assert p.theta == 1 / 9 and p.hmin == 0.1 and p.hcrit == 0.05 and p.gamma == 0.01 and p.delta == 1.0
     with pytest.raises(TypeError):
         sw.SysConst(Lx=5, Ly=5)
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary must be consumable from C (and therefore from any FFI): no C++-isms outside the guards."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "swalbe_b200.h"\n'
+                   "int main(void) { swalbe_state s; swalbe_params p; swalbe_loop_logs l; (void)s; (void)p; (void)l;\n"
+                   "  return (int)sizeof(swalbe_state) - 17 * (int)sizeof(void *) + SWALBE_LOOP_SKIP_AUX - 2; }\n")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
+                           "-I", os.path.join(ROOT, "include"), str(src)])
