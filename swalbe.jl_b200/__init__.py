@@ -214,12 +214,23 @@ class _Plan:
             pass
 
 
-def Sys(sysc: SysConst, device: str, T=float, kind: str = "simple"):
-    """Sys(sysc, device; T, kind)  src/initialize.jl:491-572.  Only the "GPU" device string exists here."""
+def Sys(sysc: SysConst, device: str, *legacy, T=float, kind: str = "simple"):
+    """Sys(sysc, device; T, kind)  src/initialize.jl:491-572  -> CuState / CuState_thermal, and the older tuple form
+    Sys(sysc, device, exotic::Bool, T)  src/initialize.jl:358-475  -> (fout, ftemp, feq, height, velx, vely, vsq,
+    pressure, dgrad, Fx, Fy, slipx, slipy, h∇px, h∇py[, fthermalx, fthermaly]).  Only the "GPU" device string exists."""
     if device != "GPU":
         raise SwalbeError(f'Sys(sys, "{device}"): swalbe_b200 implements the "GPU" path only (no CPU fallback)')
+    if legacy:
+        if len(legacy) != 2 or not isinstance(legacy[0], bool):
+            raise TypeError("MethodError: no method matching Sys(::SysConst, ::String, ...) with these arguments")
+        exotic, T = legacy
     if T not in (float, np.float64, "Float64"):
         raise SwalbeError("swalbe_b200 is Float64 only")
+    if legacy:
+        st = CuState_thermal(sysc.Lx, sysc.Ly) if exotic else CuState(sysc.Lx, sysc.Ly)
+        fields = (st.fout, st.ftemp, st.feq, st.height, st.velx, st.vely, st.vsq, st.pressure, st.dgrad, st.Fx, st.Fy,
+                  st.slipx, st.slipy, st.hgradpx, st.hgradpy)
+        return fields + ((st.kbtx, st.kbty) if exotic else ())
     if kind == "simple":
         return CuState(sysc.Lx, sysc.Ly)
     if kind == "thermal":

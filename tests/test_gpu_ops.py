@@ -211,3 +211,35 @@ def test_exact_division_helper_matches_ieee_division(G):
     for seed in (1, 20261017):
         _lib.call("swalbe_selftest_division", 1 << 27, seed, C.c_void_p(out.data_ptr()), sw._stream())
         assert out.item() == 0, f"{out.item()} mismatching quotients (seed {seed})"
+
+
+def test_legacy_tuple_allocator_and_array_forms(G):
+    """Sys(sysc, "GPU", exotic, T) (src/initialize.jl:358-475) hands out bare arrays; a docs-style loop over the array
+    forms (docs/src/tutorials.md) must equal the oracle."""
+    import swalbe_b200 as sw
+
+    sysc = sw.SysConst(Lx=40, Ly=30, param=sw.Taumucs(n=3, m=2, hmin=0.07))
+    p = sysc.param
+    arrs = sw.Sys(sysc, "GPU", False, float)
+    assert len(arrs) == 15 and len(sw.Sys(sysc, "GPU", True, float)) == 17
+    fout, ftemp, feq, height, velx, vely, vsq, pressure, dgrad, Fx, Fy, slipx, slipy, hpx, hpy = arrs
+    assert np.all(height.numpy() == 1.0) and np.all(fout.numpy() == 0.0)
+    rng = np.random.default_rng(2)
+    h0 = np.asfortranarray(np.abs(1.0 + 0.1 * rng.standard_normal((40, 30))) + 0.06)
+    height.set(h0)
+    ref = onp.State(40, 30)
+    ref.height[...] = h0
+    op = onp.Params(n=3, m=2, hmin=0.07)
+    for _ in range(4):
+        sw.filmpressure(pressure, height, dgrad, p.gamma, p.theta, p.n, p.m, p.hmin, p.hcrit)
+        sw.gradf(hpx, hpy, pressure, dgrad, height)
+        sw.slippage(slipx, slipy, height, velx, vely, p.delta, p.mu)
+        st = sw.CuState.__new__(sw.CuState)
+        st.Lx, st.Ly, st.Fx, st.Fy, st.hgradpx, st.hgradpy, st.slipx, st.slipy = 40, 30, Fx, Fy, hpx, hpy, slipx, slipy
+        sw.update(st)
+        sw.equilibrium(feq, height, velx, vely, vsq, p.g)
+        sw.BGKandStream(fout, feq, ftemp, Fx, Fy, p.tau)
+        sw.moments(height, velx, vely, fout)
+        oc.step(ref, op, pvariant="fast")
+    for got, want in ((height, ref.height), (velx, ref.velx), (fout, ref.fout), (pressure, ref.pressure)):
+        assert np.array_equal(got.numpy(), want)
