@@ -154,8 +154,8 @@ bool bulk_eligible(int Lx, size_t ncells) {
   return mode >= 2 || ncells >= ((size_t)1 << 22);
 }
 
-// the lean kernels cover: tau == 1, scalar theta, standard slip, no inclination, a known (n, m) pressure mode
-// (with a further specialisation for gravity == 0)
+// the lean kernels cover: tau == 1 and a known (n, m) pressure mode (with a further specialisation for gravity == 0);
+// theta fields, slip variants and inclination are run-time options inside them
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   KernelKey k;
   k.tau1 = p.tau == 1.0;
@@ -164,8 +164,7 @@ KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   k.bulk = false;
   k.gz = p.g == 0.0;
   k.lazy = false;
-  if (want_lean && k.tau1 && !p.cospi_theta_field && p.slip_variant == SWALBE_SLIP_STANDARD && !p.use_inclination &&
-      pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
+  if (want_lean && k.tau1 && pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
   return k;
 }

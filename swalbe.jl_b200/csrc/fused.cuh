@@ -26,8 +26,8 @@
 // recomputed in y inside a chunk.
 //
 // Two flavours per (NT, tau==1, thermal): PM >= 0 is the LEAN kernel for the steps in the middle of a
-// swalbe_time_loop call (scalar theta, standard slip, no inclination, no logs, no materialisation, pressure mode PM
-// fixed at compile time, optionally GZ: gravity == 0 folded in, optionally BULK); PM == -1 is the FULL kernel with
+// swalbe_time_loop call (no logs, no materialisation, pressure mode PM fixed at compile time, optionally GZ: gravity
+// == 0 folded in, optionally BULK; theta field, slip variant and inclination stay run-time options); PM == -1 is the FULL kernel with
 // every option decided at run time (used for the last step of a call, which materialises the reference's
 // intermediate fields, and for all uncommon options).  Instantiated per CTA width in fused_v*.cu (variants.h).
 //
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   cN.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // h row N(0); prefetched D iterations ahead, starting at t = -D
   cU.init(j0 - 7, Lx, a.Ly, a.wrap_y, ci);  // u row F(0)
   cO.init(j0 - 9, Lx, a.Ly, a.wrap_y, ci);  // output row O(0)
-  cC.init(j0 - 5, Lx, a.Ly, a.wrap_y, ci);  // cospi(theta) field row P(0)
+  cC.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // cospi(theta) field: row P(1), loaded one iteration ahead
   cT.init(j0 - 6, Lx, a.Ly, a.wrap_y, ci);  // old populations (tau != 1): row F(1)
 
   // own-column populations that move along y only: f*0 of rows F(t-1), F(t-2); f*2 of F(t-1..t-3); f*4 of F(t-1)
@@ -225,14 +225,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   double ft_c[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) ft_c[k] = 0.0;
+  double ct_c = 0.0;  // cospi(theta) of the row stage B works on (register prefetch, one iteration ahead)
 
   double d_min = INFINITY, d_max = -INFINITY;
   unsigned int d_wet = 0;
   const bool logging = !LEAN && (a.log_min != nullptr || a.log_wet != nullptr);
-  const bool theta_field = !LEAN && a.ct_field != nullptr;
+  const bool theta_field = a.ct_field != nullptr;
   const bool aux = !LEAN && a.pressure != nullptr;
   const int pmode = LEAN ? PM : a.pc.pmode;
-  const int slipv = LEAN ? SWALBE_SLIP_STANDARD : a.sc.variant;
+  const int slipv = a.sc.variant;
   const long long fs_in8 = (long long)a.fstride_in * 8, fs_out8 = (long long)a.fstride_out * 8,
                   fs_out2_8 = (long long)a.fstride_out2 * 8;
 
@@ -287,10 +288,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
       const double *const ur = su + (t & 3) * RUS;         // u of row F(t)
 
       // ---- register prefetch of data that is not staged through smem ------------------------------------
-      double ct_c = 0.0;
       const bool doB = S || (t >= 3 && t <= R + 6);   // row P(t) = j0-5+t in [j0-2, j0+R+1]
-      if (!LEAN) {
-        if (theta_field && doB) ct_c = __ldg(at(a.ct_field, cC.off));
+      double ct_n = 0.0;
+      if (theta_field) {  // row P(t+1) = j0-4+t, needed for t+1 in [3, R+6]
+        if (S || (t >= 2 && t <= R + 5)) ct_n = __ldg(at(a.ct_field, cC.off));
         cC.advance(row_bytes, wrapLy, col_bytes);
       }
       double ft_n[9];
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
           Fx = Fx - kx;
           Fy = Fy - ky;
         }
-        if (!LEAN && a.use_incl) {
+        if (a.use_incl) {
           Fx = Fx + (hc * a.incl_ax) * a.incl_factor;
           Fy = Fy + (hc * a.incl_ay) * a.incl_factor;
         }
@@ -396,6 +397,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         }
       }
       cO.advance(row_bytes, wrapLy, col_bytes);
+      ct_c = ct_n;
       f0_b = f0_a; f0_a = fs0;
       f2_c = f2_b; f2_b = f2_a; f2_a = fs2;
       f4_a = fs4;
