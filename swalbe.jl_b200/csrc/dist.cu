@@ -199,7 +199,7 @@ static int dist_allocate(swalbe_dist *d, const void *id128, int rank, int nranks
   d->key = make_key(*prm, d->base.pc.pmode, true);
   d->key_edge = d->key;
   // interior kernel: bulk-copy row prefetch where it pays (slab planes are cudaMalloc'ed, ghost offset = GH*Lx*8 bytes)
-  d->key.bulk = d->key.lean_pm > 0 && !d->key.thermal && bulk_eligible(Lx, (size_t)Lx * Ly_loc);
+  d->key.bulk = d->key.lean_pm > 0 && !d->key.opts && !d->key.thermal && bulk_eligible(Lx, (size_t)Lx * Ly_loc);
   if (int e = choose_geometry(Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
   if (int e = choose_geometry(Lx, GH, d->key_edge, &d->g_edge)) return e;
   return 0;
@@ -357,7 +357,7 @@ int swalbe_dist_set_theta(swalbe_dist *d, const double *ct_slab, void *stream_) 
   d->key = make_key(d->prm, d->base.pc.pmode, true);
   d->key_edge = d->key;
   const int Ly_loc = d->Ly_loc;
-  d->key.bulk = d->key.lean_pm > 0 && !d->key.thermal && bulk_eligible(d->Lx, (size_t)d->Lx * Ly_loc);
+  d->key.bulk = d->key.lean_pm > 0 && !d->key.opts && !d->key.thermal && bulk_eligible(d->Lx, (size_t)d->Lx * Ly_loc);
   if (int e = choose_geometry(d->Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
   if (int e = choose_geometry(d->Lx, GH, d->key_edge, &d->g_edge)) return e;
   return 0;

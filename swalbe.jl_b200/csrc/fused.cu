@@ -23,6 +23,7 @@ static const Variant *const g_variants[] = {&g_variant_128, &g_variant_160, &g_v
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
+  if (k.lean_pm > 0 && k.opts) return var.opts[k.thermal ? 1 : 0][k.lean_pm];
   if (k.lean_pm > 0 && k.bulk) return var.bulk[k.lean_pm][k.gz ? 1 : 0];
   if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm][k.gz ? 1 : 0];
   return var.full[k.tau1 ? 1 : 0][k.thermal ? 1 : 0];
@@ -49,7 +50,8 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   SW_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int force_nt = env_int("SWALBE_NT", 0);
   const int rmax = std::max(1, env_int("SWALBE_RMAX", 128));
-  const double flavour = (key.thermal ? 1.75 : 1.0) * (key.lean_pm > 0 ? 1.0 : 1.3);
+  const double flavour0 = (key.thermal ? 1.75 : 1.0) * (key.lean_pm > 0 ? 1.0 : 1.3);
+  double flavour = flavour0;
   auto t_iter = [&](int ctas_on_sm, int nt) {
     return std::max(0.87, ctas_on_sm * nt * (1.80 + 0.0018 * nt) * 1e-3 * flavour);
   };
@@ -67,6 +69,10 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
     SW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, var.nt, smem));
     if (bps < 1) continue;
+    cudaFuncAttributes fattr;
+    SW_CUDA(cudaFuncGetAttributes(&fattr, fn));
+    const bool spills = fattr.localSizeBytes > 0;  // instantiations that spill under their register cap
+    flavour = flavour0 * (spills ? 1.12 : 1.0);
     const int wmax = var.nt - 8;
     const int nstrips = (Lx + wmax - 1) / wmax;
     int W = (Lx + nstrips - 1) / nstrips;
@@ -99,7 +105,7 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
         cost = std::ceil(waves - 1e-9) * (R + fill) * t_iter(bps, var.nt);
       }
       bool take;
-      if (cost <= 0.95 * hbm_floor && bps >= 3) {  // HBM-bound: prefer the least redundant strip decomposition
+      if (cost <= 0.95 * hbm_floor && bps >= 3 && !spills) {  // HBM-bound: prefer the least redundant strip decomposition
         const double eff = (double)W / var.nt - 1e-6 * cost;
         take = eff > best_bound_eff;
         if (take) best_bound_eff = eff;
@@ -154,8 +160,9 @@ bool bulk_eligible(int Lx, size_t ncells) {
   return mode >= 2 || ncells >= ((size_t)1 << 22);
 }
 
-// the lean kernels cover: tau == 1 and a known (n, m) pressure mode (with a further specialisation for gravity == 0);
-// theta fields, slip variants and inclination are run-time options inside them
+// the lean kernels cover: tau == 1 and a known (n, m) pressure mode: a strict flavour (scalar theta, standard slip, no
+// inclination, no logs; further specialised for gravity == 0 and bulk-copy prefetch) and an OPTS flavour that takes
+// those options at run time
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   KernelKey k;
   k.tau1 = p.tau == 1.0;
@@ -164,6 +171,7 @@ KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   k.bulk = false;
   k.gz = p.g == 0.0;
   k.lazy = false;
+  k.opts = p.cospi_theta_field != nullptr || p.slip_variant != SWALBE_SLIP_STANDARD || p.use_inclination != 0;
   if (want_lean && k.tau1 && pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
   return k;
@@ -195,15 +203,15 @@ using namespace swalbe;
 struct swalbe_plan {
   int Lx, Ly;
   double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
-  LaunchGeom geom[2][2][5][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy]
-  bool geom_ok[2][2][5][2][2][2];
+  LaunchGeom geom[2][2][5][2][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy][opts]
+  bool geom_ok[2][2][5][2][2][2][2];
 };
 
 static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
-  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy];
-  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy]) {
+  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts];
+  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts]) {
     if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
-    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy] = true;
+    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts] = true;
   }
   *g = &gg;
   return 0;
@@ -255,13 +263,13 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
   FusedArgs a = {};
   if (int e = fill_consts(a, *prm)) return e;
   const KernelKey key_full = make_key(*prm, a.pc.pmode, false);
-  const bool logs_on = logs && (logs->hmin || logs->wetted);
-  KernelKey key_mid = make_key(*prm, a.pc.pmode, !logs_on);  // lean kernel for the steps before the last
+  KernelKey key_mid = make_key(*prm, a.pc.pmode, true);  // lean kernel for the steps before the last
+  if (logs && (logs->hmin || logs->wetted)) key_mid.opts = true;
   // bulk-copy (TMA unit) row prefetch: needs 16-byte aligned row segments, i.e. even Lx and 16-B aligned planes
   auto aligned16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
   // Measured on B200: +3 % where the step is HBM-bound (8192^2: 43.2 vs 41.9 GLUPS), -2..3 % where it is latency- or
   // compute-bound (1024^2, moments-only steps) -> used for large lattices whose populations are written every step.
-  key_mid.bulk = key_mid.lean_pm > 0 && !key_mid.thermal && !lazy && bulk_eligible(Lx, N) && aligned16(st->height) &&
+  key_mid.bulk = key_mid.lean_pm > 0 && !key_mid.opts && !key_mid.thermal && !lazy && bulk_eligible(Lx, N) && aligned16(st->height) &&
                  aligned16(st->velx) && aligned16(st->vely) && aligned16(plan->scratch);
   key_mid.lazy = lazy;
   LaunchGeom *g_full = nullptr, *g_mid = nullptr;

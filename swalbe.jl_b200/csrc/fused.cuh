@@ -26,8 +26,9 @@
 // recomputed in y inside a chunk.
 //
 // Two flavours per (NT, tau==1, thermal): PM >= 0 is the LEAN kernel for the steps in the middle of a
-// swalbe_time_loop call (no logs, no materialisation, pressure mode PM fixed at compile time, optionally GZ: gravity
-// == 0 folded in, optionally BULK; theta field, slip variant and inclination stay run-time options); PM == -1 is the FULL kernel with
+// swalbe_time_loop call (no materialisation, pressure mode PM fixed at compile time; strict: scalar theta, standard
+// slip, no inclination, no logs, optionally GZ: gravity == 0 folded in and BULK; OPTS: theta field, slip variant,
+// inclination and per-step logs as run-time options -- they cost ~8 registers, which the strict kernels cannot spare); PM == -1 is the FULL kernel with
 // every option decided at run time (used for the last step of a call, which materialises the reference's
 // intermediate fields, and for all uncommon options).  Instantiated per CTA width in fused_v*.cu (variants.h).
 //
@@ -170,7 +171,7 @@ constexpr int FUSED_LINES = FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES + 4 * RU
 constexpr int FUSED_PAD = 2;
 constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2 * FUSED_PAD); }
 
-template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ>
+template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(16) double smem[];
   constexpr bool LEAN = PM >= 0;
@@ -229,11 +230,12 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
 
   double d_min = INFINITY, d_max = -INFINITY;
   unsigned int d_wet = 0;
-  const bool logging = !LEAN && (a.log_min != nullptr || a.log_wet != nullptr);
-  const bool theta_field = a.ct_field != nullptr;
+  // OPTS kernels take the uncommon options at run time; the strict lean kernels (OPTS == false) have them compiled out
+  const bool logging = OPTS && (a.log_min != nullptr || a.log_wet != nullptr);
+  const bool theta_field = OPTS && a.ct_field != nullptr;
   const bool aux = !LEAN && a.pressure != nullptr;
   const int pmode = LEAN ? PM : a.pc.pmode;
-  const int slipv = a.sc.variant;
+  const int slipv = OPTS ? a.sc.variant : SWALBE_SLIP_STANDARD;
   const long long fs_in8 = (long long)a.fstride_in * 8, fs_out8 = (long long)a.fstride_out * 8,
                   fs_out2_8 = (long long)a.fstride_out2 * 8;
 
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
           Fx = Fx - kx;
           Fy = Fy - ky;
         }
-        if (a.use_incl) {
+        if (OPTS && a.use_incl) {
           Fx = Fx + (hc * a.incl_ax) * a.incl_factor;
           Fy = Fy + (hc * a.incl_ay) * a.incl_factor;
         }
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         w2[R2_F7 * LW] = fs[7]; w2[R2_F8 * LW] = fs[8];
         fs0 = fs[0]; fs2 = fs[2]; fs4 = fs[4];
 
-        if (!LEAN) {
+        if (logging || aux) {
           const bool own = col_out && t >= 7 && t <= R + 6;  // row F(t) in [j0, j0+R-1]
           if (own) {
             if (logging) {
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   for (; t <= R + 6 - D; ++t) iter(t, std::true_type{});  // (the last prefetched h row is N(R+6))
   for (; t <= t_end; ++t) iter(t, std::false_type{});
 
-  if (!LEAN && logging) {  // CTA reduction of the pre-step height statistics, one atomic per CTA
+  if (logging) {  // CTA reduction of the pre-step height statistics, one atomic per CTA
     __shared__ double r_min[NT / 32], r_max[NT / 32];
     __shared__ unsigned int r_wet[NT / 32];
 #pragma unroll

@@ -24,6 +24,7 @@ struct KernelKey {
   bool bulk;  // lean non-thermal kernel whose row prefetch uses cp.async.bulk (needs even Lx >= NT and 16-B aligned planes)
   bool gz;    // gravity == 0: lean kernels with the (+-0)*h terms of the equilibrium folded away
   bool lazy;  // populations are not written by this launch (geometry only: lower HBM floor)
+  bool opts;  // lean kernel that takes theta field / slip variant / inclination / logs at run time
 };
 
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);
