@@ -118,6 +118,10 @@ int swalbe_inclination(double *Fx, double *Fy, const double *height, double alph
  * sum(state.height) src/simulate.jl:8-14; maximum-minimum :56; wetted! src/measures.jl:13-17. */
 int swalbe_field_stats(double *out4, const double *f, double thresh, int Lx, int Ly, void *stream);
 
+/* out[c] = cospi(theta[c]) (CUDA libdevice cospi, <= 1 ulp): what a host without Base.cospi on the device uses to turn a
+ * contact-angle field into the cospi_theta_field argument above (Julia hosts broadcast cospi.(theta) themselves). */
+int swalbe_cospi_field(double *out, const double *theta, size_t count, void *stream);
+
 /* self-test (diagnostics, not part of the reference's API): runs the library's exact-division helper (shared
  * reciprocal, zero-numerator fast path) against the compiler's IEEE `/` on n pseudo-random operand triples of every
  * class (all exponents, +-0, Inf, NaN, denormals, near-equal operands) and writes the number of bitwise mismatches to

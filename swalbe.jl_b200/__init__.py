@@ -29,7 +29,7 @@ __all__ = [
     "slippage2", "slippage_ring_riv", "thermal", "inclination", "update", "time_loop", "run_flat", "run_random",
     "run_rayleightaylor", "run_dropletrelax", "run_dropletpatterned", "run_dropletforced", "wetted", "snapshot",
     "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES", "viewdists", "viewneighbors", "power_broad", "power_2",
-    "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet",
+    "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field",
 ]
 
 
@@ -274,14 +274,20 @@ def moments(*args):
     _lib.call("swalbe_moments_d2q9", _ptr(h), _ptr(ux), _ptr(uy), _ptr(f), *_dims(h), _stream())
 
 
+def cospi_field(θ: "Field") -> "Field":
+    """cospi.(θ) on the device (swalbe_cospi_field); the result is what filmpressure!/time_loop take as the field."""
+    out = Field(*θ.shape[:2])
+    _lib.call("swalbe_cospi_field", out.ptr, θ.ptr, int(θ.t.numel()), _stream())
+    return out
+
+
 def _theta_args(θ):
-    """θ scalar -> (cospi θ, NULL); θ Field holding cospi.(θ)... the caller passes θ itself: a scalar, or a
-    Field of angles, for which cospi.(θ) is evaluated on the host once and cached on the Field."""
+    """θ scalar -> (cospi θ, NULL); θ Field of angles -> (0, device field cospi.(θ)), evaluated on the device once and
+    cached on the Field until the Field is modified (move_substrate! etc.)."""
     if isinstance(θ, Field):
         c = getattr(θ, "_cospi", None)
         if c is None or getattr(θ, "_cospi_version", None) != θ.t._version:
-            ang = θ.numpy()
-            c = Field(*θ.shape[:2]).set(np.vectorize(cospi)(ang))
+            c = cospi_field(θ)
             θ._cospi, θ._cospi_version = c, θ.t._version
         return 0.0, c.ptr
     return cospi(θ), None

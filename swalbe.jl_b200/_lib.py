@@ -70,6 +70,7 @@ SIGNATURES = {
     "swalbe_inclination": [_vp, _vp, _vp, _d, _d, _d, _i, _i, _vp],
     "swalbe_field_stats": [_vp, _vp, _d, _i, _i, _vp],
     "swalbe_selftest_division": [_u64, _u64, _vp, _vp],
+    "swalbe_cospi_field": [_vp, _vp, C.c_size_t, _vp],
     "swalbe_plan_create": [C.POINTER(_vp), _i, _i],
     "swalbe_plan_destroy": [_vp],
     "swalbe_time_loop": [_vp, C.POINTER(CState), C.POINTER(CParams), _i, _u64, _i, C.POINTER(CLogs), _vp],

@@ -182,6 +182,10 @@ __global__ void __launch_bounds__(BX *BY) k_inclination(double *__restrict__ Fx,
   Fy[c] = Fy[c] + (hc * ay) * factor;
 }
 
+__global__ void __launch_bounds__(256) k_cospi(double *__restrict__ out, const double *__restrict__ th, size_t n) {
+  for (size_t c = (size_t)blockIdx.x * 256 + threadIdx.x; c < n; c += (size_t)gridDim.x * 256) out[c] = cospi(th[c]);
+}
+
 // ---- field statistics: fixed-order two-pass reduction (deterministic) --------------------------
 constexpr int ST_THREADS = 256;
 struct Stat4 { double mn, mx, sm; unsigned long long cnt; };
@@ -392,6 +396,15 @@ int swalbe_inclination(double *Fx, double *Fy, const double *height, double alph
   if (int e = check_extent(Lx, Ly)) return e;
   REQUIRE(Fx); REQUIRE(Fy); REQUIRE(height);
   k_inclination<<<grid2(Lx, Ly), block2(), 0, (cudaStream_t)stream>>>(Fx, Fy, height, alpha_x, alpha_y, factor, Lx, Ly);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_cospi_field(double *out, const double *theta, size_t count, void *stream) {
+  REQUIRE(out); REQUIRE(theta);
+  if (count == 0) return 0;
+  const size_t blocks = (count + 255) / 256;
+  k_cospi<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(out, theta, count);
   SW_LAUNCH_CHECK();
   return 0;
 }

@@ -30,7 +30,7 @@ def main():
     sim.set_state(h, z1, z2)
     theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))  # same draw order as the single-GPU reference run
     if mode == "theta_field":
-        ct = np.asfortranarray(np.vectorize(sw.cospi)(theta))
+        ct = sw.cospi_field(sw.Field(Lx, Ly).set(theta)).numpy()  # same device cospi.(θ) as the single-GPU run
         sim.set_theta(sw.Field(Lx, n).set(slab_of(ct, sim.decomp, rank)))
     sim.time_loop(5)
     sim.time_loop(4, step0=5)

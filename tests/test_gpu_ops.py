@@ -243,3 +243,17 @@ def test_legacy_tuple_allocator_and_array_forms(G):
         oc.step(ref, op, pvariant="fast")
     for got, want in ((height, ref.height), (velx, ref.velx), (fout, ref.fout), (pressure, ref.pressure)):
         assert np.array_equal(got.numpy(), want)
+
+
+def test_cospi_field_on_device(G):
+    """swalbe_cospi_field (libdevice cospi, what CUDA.jl's cospi.(θ) broadcast calls) against the host cospi: exact at the
+    exact points, within 1 ulp elsewhere."""
+    import swalbe_b200 as sw
+
+    rng = np.random.default_rng(0)
+    th = np.asfortranarray(rng.random((64, 33)) * 2 - 0.5)
+    th[0, :8] = [0.0, 0.5, 1.0, 1.5, 2.0, 1 / 9, 1 / 6, 1 / 3]
+    got = sw.cospi_field(sw.Field(64, 33).set(th)).numpy()
+    want = np.vectorize(sw.cospi)(th)
+    assert list(got[0, :5]) == [1.0, 0.0, -1.0, 0.0, 1.0]
+    assert np.max(np.abs(got - want)) <= 1.2e-16

@@ -85,7 +85,7 @@ def test_fused_loop_variants_theta_field_slip_inclination(sw):
     Lx, Ly = 64, 50
     rng = np.random.default_rng(3)
     theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))
-    ct = np.asfortranarray(np.vectorize(sw.cospi)(theta))
+    ct = sw.cospi_field(sw.Field(Lx, Ly).set(theta)).numpy()  # the device's cospi.(θ) is handed to the oracle as data
     for sv in (0, 1, 2):
         st, sysc, ref, p = _mk(sw, Lx, Ly, seed=sv, prm_kw=dict(n=3, m=2, hmin=0.07))
         thf = sw.Field(Lx, Ly).set(theta)
