@@ -122,6 +122,45 @@ int swalbe_field_stats(double *out4, const double *f, double thresh, int Lx, int
  * contact-angle field into the cospi_theta_field argument above (Julia hosts broadcast cospi.(theta) themselves). */
 int swalbe_cospi_field(double *out, const double *theta, size_t count, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * On-device initial conditions and substrate motion.  The reference builds these on one host
+ * thread and uploads them; here every rank fills its own row slab: rows [j_begin, j_begin + Ly_local) of the global
+ * lattice, `height` pointing at the slab's first row (single GPU: j_begin = 0, Ly_local = Ly).  Coordinates are the
+ * reference's 1-based (i, j).  cospi_theta is cospi(θ) evaluated by the caller, as everywhere in this ABI.
+ * sin/cos/asin are CUDA's: equal to Julia's openlibm within a few ulp, not bit for bit.
+ * ------------------------------------------------------------------------------------------- */
+
+/* singledroplet(height, radius, θ, center)                    src/initialvalues.jl:203-224
+ * spherical cap (cos(asin(r/radius)) - cospi θ)*radius inside r <= radius, `precursor` (0.05 upstream) elsewhere and
+ * wherever the cap is negative. */
+int swalbe_ic_singledroplet(double *height, double radius, double cospi_theta, double cx, double cy, double precursor,
+                            int Lx, int Ly_local, int j_begin, void *stream);
+
+/* torus(lx, ly, r1, R2, θ, center, hmin; noise)               src/initialvalues.jl:144-168
+ * noise != 0 adds noise*N(0,1) from the counter-based generator keyed on (seed, global cell). */
+int swalbe_ic_torus(double *height, double r1, double R2, double cospi_theta, double cx, double cy, double hmin,
+                    double noise, unsigned long long seed, int Lx, int Ly_local, int j_begin, void *stream);
+
+/* rivulet(Lx, Ly, radius, θ, orientation, center, hmin; noise) src/initialvalues.jl:69-104
+ * orientation 0 = :y (profile varies with i, ridge along j), 1 = :x. */
+int swalbe_ic_rivulet(double *height, double radius, double cospi_theta, int orientation, double center, double hmin,
+                      double noise, unsigned long long seed, int Lx, int Ly_local, int j_begin, void *stream);
+
+/* the initial condition of run_rayleightaylor                 src/simulate.jl:350-353
+ * h0*(1 + eps*sin(2π kx i/(Lx-1))*sin(2π ky j/(Ly-1))); Ly is the GLOBAL extent (the divisor), Ly_local the slab. */
+int swalbe_ic_sinewave2d(double *height, double h0, double eps, double kx, double ky, int Lx, int Ly, int Ly_local,
+                         int j_begin, void *stream);
+
+/* randinterface!(height, h0, eps)                              src/initialvalues.jl:23-33
+ * h0*(1 + eps*N(0,1)); Julia's unseeded randn! stream is not reproducible, the normals come from Philox4x32-10 keyed
+ * on (seed, global cell) -- identical for every decomposition, compared with the reference statistically. */
+int swalbe_ic_randinterface(double *height, double h0, double eps, unsigned long long seed, int Lx, int Ly_local,
+                            int j_begin, void *stream);
+
+/* circshift!(dst, src, (sx, sy)): dst[i,j] = src[i-sx, j-sy] periodic -- the body of move_substrate!
+ * (scripts/Moving_wettability_structs.jl:139-152: circshift!(θ, input, (1,1)); input .= θ).  dst must not alias src. */
+int swalbe_circshift(double *dst, const double *src, int sx, int sy, int Lx, int Ly, void *stream);
+
 /* self-test (diagnostics, not part of the reference's API): runs the library's exact-division helper (shared
  * reciprocal, zero-numerator fast path) against the compiler's IEEE `/` on n pseudo-random operand triples of every
  * class (all exponents, +-0, Inf, NaN, denormals, near-equal operands) and writes the number of bitwise mismatches to

@@ -363,3 +363,26 @@ def singledroplet(Lx, Ly, radius, theta, center):
 def randinterface(Lx, Ly, h0, eps, rng):
     """src/initialvalues.jl:23-33 with a NumPy generator in place of Julia's unseeded randn!."""
     return np.asfortranarray(h0 * (1.0 + eps * rng.standard_normal((Lx, Ly))))
+
+
+def torus(lx, ly, r1, R2, theta, center, hmin=0.05):
+    """src/initialvalues.jl:144-168 (noise = 0)."""
+    i = np.arange(1, lx + 1, dtype=np.float64)[:, None]
+    j = np.arange(1, ly + 1, dtype=np.float64)[None, :]
+    coord = np.sqrt((i - center[0]) ** 2 + (j - center[1]) ** 2)
+    half = r1 ** 2 - (coord - R2) ** 2
+    h = np.where(half <= 0.0, hmin, np.sqrt(np.where(half <= 0.0, 0.0, half)))
+    corr = h - r1 * cospi(theta)
+    return np.asfortranarray(np.where(corr < hmin, hmin, corr))
+
+
+def rivulet(Lx, Ly, radius, theta, orientation, center, hmin=0.05):
+    """src/initialvalues.jl:69-104 (noise = 0); orientation "y" -> profile in i, "x" -> profile in j."""
+    i = np.arange(1, Lx + 1, dtype=np.float64)[:, None] + np.zeros((1, Ly))
+    j = np.arange(1, Ly + 1, dtype=np.float64)[None, :] + np.zeros((Lx, 1))
+    circ = np.sqrt(((i if orientation == "y" else j) - center) ** 2)
+    inside = circ <= radius
+    cap = (np.cos(np.arcsin(np.where(inside, circ / radius, 0.0))) - cospi(theta)) * radius
+    h = np.where(inside, cap, hmin)
+    return np.asfortranarray(np.where(h <= hmin, hmin, h))
+

@@ -29,7 +29,8 @@ __all__ = [
     "slippage2", "slippage_ring_riv", "thermal", "inclination", "update", "time_loop", "run_flat", "run_random",
     "run_rayleightaylor", "run_dropletrelax", "run_dropletpatterned", "run_dropletforced", "wetted", "snapshot",
     "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES", "viewdists", "viewneighbors", "power_broad", "power_2",
-    "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field",
+    "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field", "torus", "rivulet", "sinewave2d", "randinterface", "circshift",
+    "move_substrate",
 ]
 
 
@@ -120,6 +121,14 @@ class Field:
         tshape = (Ly, Lx) if K is None else (K, Ly, Lx)
         self.t = torch.full(tshape, float(fill), dtype=torch.float64, device="cuda")
         self.jl = self.t.permute(*reversed(range(self.t.dim())))
+        self._gen = 0  # bumped by touch(): writes through the raw pointer that torch's version counter cannot see
+
+    def touch(self) -> "Field":
+        self._gen += 1
+        return self
+
+    def _stamp(self):
+        return (self.t._version, self._gen)
 
     @property
     def ptr(self) -> C.c_void_p:
@@ -286,9 +295,9 @@ def _theta_args(θ):
     cached on the Field until the Field is modified (move_substrate! etc.)."""
     if isinstance(θ, Field):
         c = getattr(θ, "_cospi", None)
-        if c is None or getattr(θ, "_cospi_version", None) != θ.t._version:
+        if c is None or getattr(θ, "_cospi_version", None) != θ._stamp():
             c = cospi_field(θ)
-            θ._cospi, θ._cospi_version = c, θ.t._version
+            θ._cospi, θ._cospi_version = c, θ._stamp()
         return 0.0, c.ptr
     return cospi(θ), None
 
@@ -572,15 +581,81 @@ def run_rayleightaylor(sys_: SysConst, device: str, kx=15, ky=18, h0=1.0, ϵ=0.0
     return st.height, diff
 
 
-def singledroplet(Lx, Ly, radius, θ, center):
-    """singledroplet  src/initialvalues.jl:203-224 (host-side initial condition, precursor 0.05)"""
+def _slab(field, j_begin, Ly):
+    Lx, Lyl = field.shape[:2]
+    return Lx, Lyl, int(j_begin), int(Ly if Ly is not None else j_begin + Lyl)
+
+
+def singledroplet(*args, precursor=0.05, j_begin=0):
+    """singledroplet(height, radius, θ, center)  src/initialvalues.jl:203-224.
+
+    ``singledroplet(field, radius, θ, center)`` fills the device Field in place (swalbe_ic_singledroplet; ``j_begin``
+    places a row slab in the global lattice); ``singledroplet(Lx, Ly, radius, θ, center)`` is the reference's
+    host-side construction and returns a NumPy array (what the run_* drivers upload, like upstream)."""
+    if isinstance(args[0], Field):
+        f, radius, θ, center = args
+        Lx, Lyl, jb, _ = _slab(f, j_begin, None)
+        _lib.call("swalbe_ic_singledroplet", f.ptr, float(radius), cospi(θ), float(center[0]), float(center[1]),
+                  float(precursor), Lx, Lyl, jb, _stream())
+        return f.touch()
+    Lx, Ly, radius, θ, center = args
     i = np.arange(1, Lx + 1, dtype=np.float64)[:, None]
     j = np.arange(1, Ly + 1, dtype=np.float64)[None, :]
     circ = np.sqrt((i - center[0]) ** 2 + (j - center[1]) ** 2)
     inside = circ <= radius
     cap = (np.cos(np.arcsin(np.where(inside, circ / radius, 0.0))) - cospi(θ)) * radius
-    h = np.where(inside, cap, 0.05)
-    return np.where(h < 0, 0.05, h)
+    h = np.where(inside, cap, precursor)
+    return np.where(h < 0, precursor, h)
+
+
+def torus(field: "Field", r1, R2, θ, center, hmin=0.05, noise=0.0, seed=0, j_begin=0):
+    """torus(lx, ly, r₁, R₂, θ, center, hmin; noise)  src/initialvalues.jl:144-168, written into a device Field."""
+    Lx, Lyl, jb, _ = _slab(field, j_begin, None)
+    _lib.call("swalbe_ic_torus", field.ptr, float(r1), float(R2), cospi(θ), float(center[0]), float(center[1]),
+              float(hmin), float(noise), int(seed), Lx, Lyl, jb, _stream())
+    return field.touch()
+
+
+def rivulet(field: "Field", radius, θ, orientation, center, hmin=0.05, noise=0.0, seed=0, j_begin=0):
+    """rivulet(Lx, Ly, radius, θ, orientation, center, hmin; noise)  src/initialvalues.jl:69-104 (orientation "y"|"x",
+    Julia's :y / :x), written into a device Field."""
+    if orientation not in ("y", "x"):
+        raise ValueError("orientation must be 'y' or 'x'")
+    Lx, Lyl, jb, _ = _slab(field, j_begin, None)
+    _lib.call("swalbe_ic_rivulet", field.ptr, float(radius), cospi(θ), 0 if orientation == "y" else 1, float(center),
+              float(hmin), float(noise), int(seed), Lx, Lyl, jb, _stream())
+    return field.touch()
+
+
+def sinewave2d(field: "Field", h0=1.0, ϵ=0.001, kx=15, ky=18, j_begin=0, Ly=None):
+    """The initial condition loop of run_rayleightaylor (src/simulate.jl:350-353) on the device."""
+    Lx, Lyl, jb, Lyg = _slab(field, j_begin, Ly)
+    _lib.call("swalbe_ic_sinewave2d", field.ptr, float(h0), float(ϵ), float(kx), float(ky), Lx, Lyg, Lyl, jb, _stream())
+    return field.touch()
+
+
+def randinterface(field: "Field", h0, ϵ, seed=0, j_begin=0):
+    """randinterface!(height, h₀, ϵ)  src/initialvalues.jl:23-33 with seeded counter-based normals on the device."""
+    Lx, Lyl, jb, _ = _slab(field, j_begin, None)
+    _lib.call("swalbe_ic_randinterface", field.ptr, float(h0), float(ϵ), int(seed), Lx, Lyl, jb, _stream())
+    return field.touch()
+
+
+def circshift(dst: "Field", src: "Field", shifts):
+    """circshift!(dst, src, (sx, sy)) on device Fields: dst[i, j] = src[i - sx, j - sy] (periodic)."""
+    if dst.shape != src.shape or len(dst.shape) != 2:
+        raise ValueError(f"DimensionMismatch: {dst.shape} vs {src.shape}")
+    _lib.call("swalbe_circshift", dst.ptr, src.ptr, int(shifts[0]), int(shifts[1]), *dst.shape, _stream())
+    return dst.touch()
+
+
+def move_substrate(θ: "Field", input: "Field", t, tmove, direction="diagonal"):
+    """move_substrate!(θ, input, t, tmove; direction)  scripts/Moving_wettability_structs.jl:139-152."""
+    if (t % tmove == 0) and (t > 0):
+        shift = {"diagonal": (1, 1), "x": (1, 0), "y": (0, 1)}.get(direction)
+        if shift is not None:
+            circshift(θ, input, shift)
+        input.set(θ)
 
 
 def run_dropletrelax(sys_: SysConst, device: str, radius=20, θ0=1 / 6, center=None, verbos=True):
@@ -632,5 +707,6 @@ JULIA_NAMES = {
     "run_dropletpatterned": run_dropletpatterned, "run_dropletforced": run_dropletforced, "Sys": Sys,
     "SysConst": SysConst, "Sys_const": Sys_const, "Taumucs": Taumucs, "CuState": CuState,
     "CuState_thermal": CuState_thermal, "Swalbe_state": Swalbe_state, "viewdists": viewdists,
-    "viewneighbors": viewneighbors, "power_broad": power_broad, "fast_93": fast_93, "fast_32": fast_32,
+    "viewneighbors": viewneighbors, "singledroplet": singledroplet, "torus": torus, "rivulet": rivulet,
+    "randinterface!": randinterface, "circshift!": circshift, "move_substrate!": move_substrate, "power_broad": power_broad, "fast_93": fast_93, "fast_32": fast_32,
 }

@@ -71,6 +71,12 @@ SIGNATURES = {
     "swalbe_field_stats": [_vp, _vp, _d, _i, _i, _vp],
     "swalbe_selftest_division": [_u64, _u64, _vp, _vp],
     "swalbe_cospi_field": [_vp, _vp, C.c_size_t, _vp],
+    "swalbe_ic_singledroplet": [_vp, _d, _d, _d, _d, _d, _i, _i, _i, _vp],
+    "swalbe_ic_torus": [_vp, _d, _d, _d, _d, _d, _d, _d, _u64, _i, _i, _i, _vp],
+    "swalbe_ic_rivulet": [_vp, _d, _d, _i, _d, _d, _d, _u64, _i, _i, _i, _vp],
+    "swalbe_ic_sinewave2d": [_vp, _d, _d, _d, _d, _i, _i, _i, _i, _vp],
+    "swalbe_ic_randinterface": [_vp, _d, _d, _u64, _i, _i, _i, _vp],
+    "swalbe_circshift": [_vp, _vp, _i, _i, _i, _i, _vp],
     "swalbe_plan_create": [C.POINTER(_vp), _i, _i],
     "swalbe_plan_destroy": [_vp],
     "swalbe_time_loop": [_vp, C.POINTER(CState), C.POINTER(CParams), _i, _u64, _i, C.POINTER(CLogs), _vp],

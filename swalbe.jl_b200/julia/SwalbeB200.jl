@@ -230,6 +230,58 @@ function Swalbe.time_loop(sys::SysConst, state::CuState, Δh::Vector; verbose = 
     return state
 end
 
+
+# ---- on-device initial conditions and substrate motion (include/swalbe_b200.h, "initial conditions") ----------
+# Methods on CuArray heights: `Swalbe.singledroplet(state.height, r, θ, c)` fills the device array without the host
+# loop + upload of src/initialvalues.jl:203-224.  `j_begin` places a row slab in the global lattice (multi-GPU).
+function Swalbe.singledroplet(height::CuArray{Float64,2}, radius, θ, center; precursor = 0.05, j_begin = 0)
+    Lx, Ly = dims(height)
+    check(ccall((:swalbe_ic_singledroplet, lib), Cint,
+        (CuPtr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cint, Cint, Cint, Ptr{Cvoid}),
+        height, radius, cospi(θ), center[1], center[2], precursor, Lx, Ly, j_begin, stream()))
+    return height
+end
+
+function torus!(height::CuArray{Float64,2}, r₁, R₂, θ, center, hmin = 0.05; noise = 0.0, seed = 0, j_begin = 0)  # src/initialvalues.jl:144
+    Lx, Ly = dims(height)
+    check(ccall((:swalbe_ic_torus, lib), Cint,
+        (CuPtr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Culonglong, Cint, Cint, Cint, Ptr{Cvoid}),
+        height, r₁, R₂, cospi(θ), center[1], center[2], hmin, noise, seed, Lx, Ly, j_begin, stream()))
+    return height
+end
+
+function rivulet!(height::CuArray{Float64,2}, radius, θ, orientation::Symbol, center, hmin = 0.05; noise = 0.0, seed = 0, j_begin = 0)  # :69
+    Lx, Ly = dims(height)
+    check(ccall((:swalbe_ic_rivulet, lib), Cint,
+        (CuPtr{Float64}, Cdouble, Cdouble, Cint, Cdouble, Cdouble, Cdouble, Culonglong, Cint, Cint, Cint, Ptr{Cvoid}),
+        height, radius, cospi(θ), orientation == :y ? 0 : 1, center, hmin, noise, seed, Lx, Ly, j_begin, stream()))
+    return height
+end
+
+function sinewave2d!(height::CuArray{Float64,2}, h₀, ϵ, kx, ky; j_begin = 0, Ly = size(height, 2))   # src/simulate.jl:350-353
+    Lx, Lyl = dims(height)
+    check(ccall((:swalbe_ic_sinewave2d, lib), Cint,
+        (CuPtr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+        height, h₀, ϵ, kx, ky, Lx, Ly, Lyl, j_begin, stream()))
+    return height
+end
+
+function Swalbe.randinterface!(height::CuArray{Float64,2}, h₀, ϵ; seed = 0, j_begin = 0)              # src/initialvalues.jl:23
+    Lx, Ly = dims(height)
+    check(ccall((:swalbe_ic_randinterface, lib), Cint,
+        (CuPtr{Float64}, Cdouble, Cdouble, Culonglong, Cint, Cint, Cint, Ptr{Cvoid}),
+        height, h₀, ϵ, seed, Lx, Ly, j_begin, stream()))
+end
+
+# circshift!(dest, src, shifts) on device matrices: the body of move_substrate! (scripts/Moving_wettability_structs.jl:139)
+function Base.circshift!(dest::CuArray{Float64,2}, src::CuArray{Float64,2}, shifts::Tuple{Integer,Integer})
+    Lx, Ly = dims(dest)
+    check(ccall((:swalbe_circshift, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+        dest, src, shifts[1], shifts[2], Lx, Ly, stream()))
+    return dest
+end
+
 # north_star aliases
 const Sys_const = Swalbe.SysConst
 const Swalbe_state = Swalbe.CuState

@@ -175,3 +175,24 @@ def test_sliding_droplet():  # test/simulate.jl:147-155 (inclination! in the cal
     i, j = np.unravel_index(np.argmax(st.height), st.height.shape)
     assert i + 1 != 75 and j + 1 == 75
     assert np.all(st.velx < 0.1) and np.all(st.vely < 0.1)
+
+
+def _findmax_index(a):  # Julia's findmax: first maximum in column-major order, as a 0-based (i, j)
+    return tuple(int(v) for v in np.unravel_index(a.ravel(order="F").argmax(), a.shape, order="F"))
+
+
+def test_initial_conditions_known_answers():  # test/initialvalues.jl:16-76
+    h = onp.singledroplet(100, 100, 50, 1 / 3, (50, 50))
+    assert h.max() == 50 * (1 - onp.cospi(1 / 3)) and _findmax_index(h) == (49, 49)
+    rad, th, lx, ly, c = 45, 1 / 4, 150, 200, 80
+    top = rad * (1 - onp.cospi(th))
+    r = onp.rivulet(lx, ly, rad, th, "y", c, 0.05)
+    assert r.shape == (lx, ly) and abs(r.max() - top) < 1e-4 and abs(r[c - 1, :].sum() - top * ly) < 1e-4
+    r = onp.rivulet(lx, ly, rad, th, "x", c, 0.05)
+    assert abs(r[:, c - 1].sum() - top * lx) < 1e-4
+    t = onp.torus(lx, ly, 10, 45, 1 / 9, (80, 80), 0.05)
+    assert t.min() == 0.05 and np.isclose(t.max(), (1 - onp.cospi(1 / 9)) * 10)
+    assert _findmax_index(t) == (79, 34)  # CartesianIndex(80, 35)
+    t = onp.torus(256, 256, 45, 80, 1 / 9, (128, 128))  # doctest src/initialvalues.jl:126-137
+    assert np.isclose(t.max(), 45 * (1 - onp.cospi(1 / 9))) and _findmax_index(t) == (127, 47)
+

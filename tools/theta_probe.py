@@ -12,7 +12,6 @@ i = torch.arange(L, device="cuda", dtype=torch.float64)
 theta = sw.Field(L, L)
 theta.t.copy_(1 / 9 + 1 / 36 * torch.sin(4 * np.pi * i / L)[None, :] * torch.sin(4 * np.pi * i / L)[:, None])
 ct = sw.Field(L, L); ct.t.copy_(torch.cos(np.pi * theta.t))
-theta._cospi, theta._cospi_version = ct, theta.t._version   # (skip the host-side cospi of 67M angles)
 def timeit(tag, **kw):
     st.height.set(bench.initial_height(L)); st.velx.t.zero_(); st.vely.t.zero_()
     sw.fused_steps(st, sysc, 10, **kw)
