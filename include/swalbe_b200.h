@@ -167,6 +167,11 @@ int swalbe_circshift(double *dst, const double *src, int sx, int sy, int Lx, int
  * *mismatches (device). Must be 0. */
 int swalbe_selftest_division(unsigned long long n, unsigned long long seed, unsigned long long *mismatches, void *stream);
 
+/* self-test: one block of the library's Philox4x32-10 (the generator behind swalbe_thermal, the thermal time loop and
+ * the noisy initial conditions) for counter ctr[4] and key key[2] (host arrays); the four output words go to out4
+ * (device).  Checked against the published known-answer vectors of the Random123 distribution. */
+int swalbe_selftest_philox(const unsigned int ctr[4], const unsigned int key[2], unsigned int *out4, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused time loop (what time_loop / run_* call when the device string is "GPU").
  * ------------------------------------------------------------------------------------------- */

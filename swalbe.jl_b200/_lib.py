@@ -70,6 +70,7 @@ SIGNATURES = {
     "swalbe_inclination": [_vp, _vp, _vp, _d, _d, _d, _i, _i, _vp],
     "swalbe_field_stats": [_vp, _vp, _d, _i, _i, _vp],
     "swalbe_selftest_division": [_u64, _u64, _vp, _vp],
+    "swalbe_selftest_philox": [C.POINTER(C.c_uint * 4), C.POINTER(C.c_uint * 2), _vp, _vp],
     "swalbe_cospi_field": [_vp, _vp, C.c_size_t, _vp],
     "swalbe_ic_singledroplet": [_vp, _d, _d, _d, _d, _d, _i, _i, _i, _vp],
     "swalbe_ic_torus": [_vp, _d, _d, _d, _d, _d, _d, _d, _u64, _i, _i, _i, _vp],

@@ -192,7 +192,7 @@ int fill_consts(FusedArgs &a, const swalbe_params &p) {
   volatile double om = 1.0 - it;
   a.invtau = it; a.omega = om;
   a.use_incl = p.use_inclination; a.incl_ax = p.incl_ax; a.incl_ay = p.incl_ay; a.incl_factor = p.incl_factor;
-  a.seed = p.seed;
+  a.pk = make_philox_key(p.seed);
   return 0;
 }
 

@@ -67,7 +67,8 @@ struct FusedArgs {
   double omega, invtau;
   double incl_ax, incl_ay, incl_factor;
   int use_incl;
-  unsigned long long seed, step;
+  PhiloxKey pk;  // round keys of the noise generator (seed expanded on the host)
+  unsigned long long step;
   // per-step logs (slot pointers for THIS step, NULL = off)
   double *log_min, *log_max;
   unsigned long long *log_wet;
@@ -203,6 +204,13 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   // bulk-copy variant: one mbarrier per in-flight prefetch group (4 >= D+1), armed and fed by thread 0 only.
   // The strip's NT columns are one contiguous run of the row, or two when the strip crosses the periodic x boundary.
   __shared__ unsigned long long s_bar[4];
+  // log / sincos tables of the in-kernel noise (3 KB, thermal instantiations only)
+  __shared__ __align__(16) unsigned char s_nt_raw[THERMAL ? sizeof(NormalTables) : 16];
+  NormalTables &s_nt = *reinterpret_cast<NormalTables *>(s_nt_raw);
+  if (THERMAL) {
+    normal_tables_fill(s_nt, tid, NT);
+    __syncthreads();
+  }
   int seg_a = 0;  // columns [c_start, c_start + seg_a) then [0, NT - seg_a)
   if (BULK) {
     seg_a = min(NT, Lx - ci);  // (thread 0: ci == c_start; only thread 0 uses it)
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         if (THERMAL) {
           long long jg = (a.jglobal0 + rF) % a.Ly_global;
           if (jg < 0) jg += a.Ly_global;
-          thermal_pair(hc, a.tc, a.seed, a.step, (unsigned long long)ci + (unsigned long long)Lx * (unsigned long long)jg, kx, ky);
+          thermal_pair(hc, a.tc, a.pk, a.step, (unsigned long long)ci + (unsigned long long)Lx * (unsigned long long)jg, s_nt, kx, ky);
           Fx = Fx - kx;
           Fy = Fy - ky;
         }

@@ -25,15 +25,16 @@ __device__ __forceinline__ bool cell_of(size_t idx, int Lx, int Ly_local, int j_
 }
 
 // one standard normal per (seed, stream id, global cell): Philox4x32-10 + Box-Muller (decomposition independent)
-__device__ __forceinline__ double normal_of(unsigned long long seed, unsigned long long stream_id, unsigned long long cell) {
-  uint32_t r[4];
-  philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), (uint32_t)seed,
-                (uint32_t)(seed >> 32), r);
-  const double two_m53 = 1.1102230246251565e-16;
-  const double u1 = ((double)((((unsigned long long)r[0]) << 21) ^ (r[1] >> 11)) + 0.5) * two_m53;  // (0,1]
-  const double u2 = ((double)((((unsigned long long)r[2]) << 21) ^ (r[3] >> 11)) + 0.5) * two_m53;
-  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+__device__ __forceinline__ double normal_of(const PhiloxKey &key, unsigned long long stream_id, unsigned long long cell,
+                                            const NormalTables &T) {
+  double z0, z1;
+  normal_pair(key, stream_id, cell, T, z0, z1);
+  return z0;
 }
+#define IC_NORMAL_TABLES()                        \
+  __shared__ NormalTables s_nt;                   \
+  normal_tables_fill(s_nt, threadIdx.x, IB);      \
+  __syncthreads()
 
 // singledroplet  src/initialvalues.jl:203-224
 __global__ void k_ic_singledroplet(double *h, double radius, double ct, double cx, double cy, double precursor, int Lx,
@@ -51,7 +52,8 @@ __global__ void k_ic_singledroplet(double *h, double radius, double ct, double c
 
 // torus  src/initialvalues.jl:144-168
 __global__ void k_ic_torus(double *h, double r1, double R2, double ct, double cx, double cy, double hmin, double noise,
-                           unsigned long long seed, int Lx, int Ly_local, int j_begin) {
+                           PhiloxKey seed, int Lx, int Ly_local, int j_begin) {
+  IC_NORMAL_TABLES();
   double i1, j1; unsigned long long g;
   const size_t idx = (size_t)blockIdx.x * IB + threadIdx.x;
   if (!cell_of(idx, Lx, Ly_local, j_begin, i1, j1, g)) return;
@@ -61,13 +63,14 @@ __global__ void k_ic_torus(double *h, double r1, double R2, double ct, double cx
   double v = half <= 0.0 ? hmin : sqrt(half);
   const double corr = v - r1 * ct;
   if (corr < hmin) v = hmin;
-  else v = noise != 0.0 ? corr + normal_of(seed, 0x746f727573ull, g) * noise : corr;
+  else v = noise != 0.0 ? corr + normal_of(seed, 0x746f727573ull, g, s_nt) * noise : corr;
   h[idx] = v;
 }
 
 // rivulet  src/initialvalues.jl:69-104   (orientation 0 = :y, the ridge runs along j; 1 = :x)
 __global__ void k_ic_rivulet(double *h, double radius, double ct, int orientation, double center, double hmin, double noise,
-                             unsigned long long seed, int Lx, int Ly_local, int j_begin) {
+                             PhiloxKey seed, int Lx, int Ly_local, int j_begin) {
+  IC_NORMAL_TABLES();
   double i1, j1; unsigned long long g;
   const size_t idx = (size_t)blockIdx.x * IB + threadIdx.x;
   if (!cell_of(idx, Lx, Ly_local, j_begin, i1, j1, g)) return;
@@ -76,7 +79,7 @@ __global__ void k_ic_rivulet(double *h, double radius, double ct, int orientatio
   double v = hmin;
   if (circ <= radius) {
     v = (cos(asin(circ / radius)) - ct) * radius;
-    if (noise != 0.0) v = v + normal_of(seed, 0x726976756c6574ull, g) * noise;
+    if (noise != 0.0) v = v + normal_of(seed, 0x726976756c6574ull, g, s_nt) * noise;
   }
   if (v <= hmin) v = hmin;
   h[idx] = v;
@@ -95,11 +98,12 @@ __global__ void k_ic_sine(double *h, double h0, double eps, double kx, double ky
 }
 
 // randinterface!  src/initialvalues.jl:23-33 with counter-based normals in place of Julia's unseeded randn!
-__global__ void k_ic_rand(double *h, double h0, double eps, unsigned long long seed, int Lx, int Ly_local, int j_begin) {
+__global__ void k_ic_rand(double *h, double h0, double eps, PhiloxKey seed, int Lx, int Ly_local, int j_begin) {
+  IC_NORMAL_TABLES();
   double i1, j1; unsigned long long g;
   const size_t idx = (size_t)blockIdx.x * IB + threadIdx.x;
   if (!cell_of(idx, Lx, Ly_local, j_begin, i1, j1, g)) return;
-  h[idx] = h0 * (1.0 + eps * normal_of(seed, 0x72616e64ull, g));
+  h[idx] = h0 * (1.0 + eps * normal_of(seed, 0x72616e64ull, g, s_nt));
 }
 
 // circshift!(dst, src, (sx, sy)):  dst[i, j] = src[i - sx, j - sy]  (periodic)
@@ -148,7 +152,7 @@ int swalbe_ic_torus(double *height, double r1, double R2, double cospi_theta, do
   if (int e = check_slab(Lx, Ly_local, j_begin)) return e;
   REQUIRE(height);
   k_ic_torus<<<blocks_for(Lx, Ly_local), IB, 0, (cudaStream_t)stream>>>(height, r1, R2, cospi_theta, cx, cy, hmin, noise,
-                                                                         seed, Lx, Ly_local, j_begin);
+                                                                         make_philox_key(seed), Lx, Ly_local, j_begin);
   SW_LAUNCH_CHECK();
   return 0;
 }
@@ -160,7 +164,7 @@ int swalbe_ic_rivulet(double *height, double radius, double cospi_theta, int ori
   if (orientation != 0 && orientation != 1)
     return set_error(SWALBE_ERR_ARG, "rivulet: orientation must be 0 (:y) or 1 (:x), got %d", orientation);
   k_ic_rivulet<<<blocks_for(Lx, Ly_local), IB, 0, (cudaStream_t)stream>>>(height, radius, cospi_theta, orientation, center,
-                                                                           hmin, noise, seed, Lx, Ly_local, j_begin);
+                                                                           hmin, noise, make_philox_key(seed), Lx, Ly_local, j_begin);
   SW_LAUNCH_CHECK();
   return 0;
 }
@@ -181,7 +185,7 @@ int swalbe_ic_randinterface(double *height, double h0, double eps, unsigned long
                             int j_begin, void *stream) {
   if (int e = check_slab(Lx, Ly_local, j_begin)) return e;
   REQUIRE(height);
-  k_ic_rand<<<blocks_for(Lx, Ly_local), IB, 0, (cudaStream_t)stream>>>(height, h0, eps, seed, Lx, Ly_local, j_begin);
+  k_ic_rand<<<blocks_for(Lx, Ly_local), IB, 0, (cudaStream_t)stream>>>(height, h0, eps, make_philox_key(seed), Lx, Ly_local, j_begin);
   SW_LAUNCH_CHECK();
   return 0;
 }

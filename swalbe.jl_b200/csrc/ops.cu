@@ -165,10 +165,13 @@ __global__ void __launch_bounds__(BX *BY) k_force_sum(double *__restrict__ Fx, d
 
 __global__ void __launch_bounds__(BX *BY) k_thermal(double *__restrict__ kx, double *__restrict__ ky,
                                                      const double *__restrict__ h, ThermalConsts tc,
-                                                     unsigned long long seed, unsigned long long step, int Lx, int Ly) {
+                                                     PhiloxKey key, unsigned long long step, int Lx, int Ly) {
+  __shared__ NormalTables s_nt;
+  normal_tables_fill(s_nt, threadIdx.y * BX + threadIdx.x, BX * BY);
+  __syncthreads();
   SITE_GUARD();
   double a, b;
-  thermal_pair(h[c], tc, seed, step, (unsigned long long)c, a, b);
+  thermal_pair(h[c], tc, key, step, (unsigned long long)c, s_nt, a, b);
   kx[c] = a;
   ky[c] = b;
 }
@@ -242,6 +245,12 @@ __device__ __forceinline__ bool same_double(double x, double y) {
   if (x != x && y != y) return true;  // NaN == NaN for this purpose
   return __double_as_longlong(x) == __double_as_longlong(y);
 }
+__global__ void k_selftest_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key, unsigned int *out4) {
+  uint32_t r[4];
+  philox4x32_10(c0, c1, c2, c3, key, r);
+  if (threadIdx.x < 4) out4[threadIdx.x] = r[threadIdx.x];
+}
+
 __global__ void k_selftest_division(unsigned long long n, unsigned long long seed, unsigned long long *mismatch) {
   unsigned long long bad = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -386,7 +395,7 @@ int swalbe_thermal(double *kbtx, double *kbty, const double *height, double kbt,
                    unsigned long long seed, unsigned long long step, int Lx, int Ly, void *stream) {
   if (int e = check_extent(Lx, Ly)) return e;
   REQUIRE(kbtx); REQUIRE(kbty); REQUIRE(height);
-  k_thermal<<<grid2(Lx, Ly), block2(), 0, (cudaStream_t)stream>>>(kbtx, kbty, height, make_thermal(kbt, mu, delta), seed, step, Lx, Ly);
+  k_thermal<<<grid2(Lx, Ly), block2(), 0, (cudaStream_t)stream>>>(kbtx, kbty, height, make_thermal(kbt, mu, delta), make_philox_key(seed), step, Lx, Ly);
   SW_LAUNCH_CHECK();
   return 0;
 }
@@ -405,6 +414,14 @@ int swalbe_cospi_field(double *out, const double *theta, size_t count, void *str
   if (count == 0) return 0;
   const size_t blocks = (count + 255) / 256;
   k_cospi<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(out, theta, count);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_selftest_philox(const unsigned int ctr[4], const unsigned int key[2], unsigned int *out4, void *stream) {
+  REQUIRE(ctr); REQUIRE(key); REQUIRE(out4);
+  const unsigned long long seed = (unsigned long long)key[0] | ((unsigned long long)key[1] << 32);
+  k_selftest_philox<<<1, 32, 0, (cudaStream_t)stream>>>(ctr[0], ctr[1], ctr[2], ctr[3], make_philox_key(seed), out4);
   SW_LAUNCH_CHECK();
   return 0;
 }

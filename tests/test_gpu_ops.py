@@ -257,3 +257,56 @@ def test_cospi_field_on_device(G):
     want = np.vectorize(sw.cospi)(th)
     assert list(got[0, :5]) == [1.0, 0.0, -1.0, 0.0, 1.0]
     assert np.max(np.abs(got - want)) <= 1.2e-16
+
+
+def test_philox_known_answers(G):
+    """The device's Philox4x32-10 against the known-answer vectors shipped with Random123 (kat_vectors)."""
+    import ctypes as C
+
+    import torch
+
+    from swalbe_b200 import _lib
+
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    out = torch.zeros(4, dtype=torch.int32, device="cuda")
+    for ctr, key, want in kat:
+        _lib.call("swalbe_selftest_philox", C.byref((C.c_uint * 4)(*ctr)), C.byref((C.c_uint * 2)(*key)),
+                  C.c_void_p(out.data_ptr()), None)
+        got = tuple(int(v) & 0xffffffff for v in out.cpu().tolist())
+        assert got == want, (ctr, key, [hex(g) for g in got])
+
+
+def test_thermal_normals_distribution(G):
+    """Distribution of the in-kernel normals through swalbe_thermal on a flat film (k = N * const): moments to 6th order,
+    tail fractions, Kolmogorov-Smirnov distance, independence of the two components and of neighbouring cells/steps."""
+    import swalbe_b200 as sw
+    from scipy import stats
+
+    L = 2048
+    sysc = sw.SysConst(Lx=L, Ly=L, param=sw.Taumucs(kbt=1e-6))
+    st = sw.Sys(sysc, "GPU", kind="thermal")
+    st.height.set(1.0)
+    p = sysc.param
+    amp = np.sqrt(2 * p.kbt * p.μ * 6 * 1.0 / (2 * 1.0 + 6 * 1.0 * p.δ + 3 * p.δ * p.δ))
+    sw.thermal(st, sysc, seed=99, step=5)
+    zx, zy = st.kbtx.numpy() / amp, st.kbty.numpy() / amp
+    n = zx.size
+    for z in (zx, zy):
+        assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n)
+        assert abs((z ** 3).mean()) < 4 * np.sqrt(15 / n) and abs((z ** 4).mean() - 3) < 4 * np.sqrt(96 / n)
+        assert abs((z ** 6).mean() - 15) < 4 * np.sqrt(10170 / n)
+        for t, pt in ((3.0, 2.6998e-3), (4.0, 6.334e-5)):
+            frac = (np.abs(z) > t).mean()
+            assert abs(frac - pt) < 5 * np.sqrt(pt / n), (t, frac)
+        assert stats.kstest(z.ravel()[:2_000_000], "norm").statistic < 1.63 / np.sqrt(2_000_000)  # 1 % level
+    c = lambda a, b: abs(np.mean(a * b))  # noqa: E731
+    lim = 4 / np.sqrt(n)
+    assert c(zx, zy) < lim and c(zx[1:, :], zx[:-1, :]) < lim and c(zx[:, 1:], zx[:, :-1]) < lim
+    assert c(zx * zx - 1, zy * zy - 1) < 4 * 2 / np.sqrt(n)
+    sw.thermal(st, sysc, seed=99, step=6)
+    assert c(zx, st.kbtx.numpy() / amp) < lim
+    sw.thermal(st, sysc, seed=99, step=5)
+    assert np.array_equal(zx, st.kbtx.numpy() / amp)  # counter-based: reproducible
