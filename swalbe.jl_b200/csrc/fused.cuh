@@ -229,6 +229,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   cC.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // cospi(theta) field: row P(1), loaded one iteration ahead
   cT.init(j0 - 6, Lx, a.Ly, a.wrap_y, ci);  // old populations (tau != 1): row F(1)
 
+  // thermal noise counter: global cell index of (row F(t), own column), advanced one row per iteration from t = 0
+  long long g_row = 0;
+  unsigned long long g_cell = 0;
+  if (THERMAL) {
+    g_row = (a.jglobal0 + (long long)(j0 - 7)) % a.Ly_global;
+    if (g_row < 0) g_row += a.Ly_global;
+    g_cell = (unsigned long long)Lx * (unsigned long long)g_row + (unsigned long long)ci;
+  }
+
   // own-column populations that move along y only: f*0 of rows F(t-1), F(t-2); f*2 of F(t-1..t-3); f*4 of F(t-1)
   double f0_a = 0, f0_b = 0, f2_a = 0, f2_b = 0, f2_c = 0, f4_a = 0;
   double ft_c[9];
@@ -344,9 +353,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         double kx = 0.0, ky = 0.0;
         const int rF = j0 - 7 + t;
         if (THERMAL) {
-          long long jg = (a.jglobal0 + rF) % a.Ly_global;
-          if (jg < 0) jg += a.Ly_global;
-          thermal_pair(hc, a.tc, a.pk, a.step, (unsigned long long)ci + (unsigned long long)Lx * (unsigned long long)jg, s_nt, kx, ky);
+          thermal_pair(hc, a.tc, a.pk, a.step, g_cell, s_nt, kx, ky);
           Fx = Fx - kx;
           Fy = Fy - ky;
         }
@@ -407,6 +414,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         }
       }
       cO.advance(row_bytes, wrapLy, col_bytes);
+      if (THERMAL) {  // global (row F(t+1), own column)
+        g_cell += (unsigned long long)Lx;
+        if (++g_row == a.Ly_global) { g_row = 0; g_cell = (unsigned long long)ci; }
+      }
       ct_c = ct_n;
       f0_b = f0_a; f0_a = fs0;
       f2_c = f2_b; f2_b = f2_a; f2_a = fs2;

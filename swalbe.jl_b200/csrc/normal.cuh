@@ -26,6 +26,23 @@ struct NormalTables {
   double2 sc[NRM_ANG_N];  // (cos, sin) of the sector centres 2π(k+1/2)/64
 };
 
+// polynomial coefficients: in device code they sit in the constant bank (operands of the FP64 instructions, no moves)
+struct NrmConsts {
+  double l6, l5, l3, mln2, dsc, s7, s5, s3, c8, c6, c4;
+};
+#define NRM_CONSTS_INIT                                                                                              \
+  {-1.0 / 6.0,    0.2,         1.0 / 3.0,  -0.6931471805599453, 6.283185307179586 / 4294967296.0, -1.0 / 5040.0, \
+   1.0 / 120.0,   -1.0 / 6.0,  1.0 / 40320.0, -1.0 / 720.0,     1.0 / 24.0}
+#ifdef __CUDACC__
+static __constant__ NrmConsts nrm_kd = NRM_CONSTS_INIT;
+#endif
+static const NrmConsts nrm_kh = NRM_CONSTS_INIT;
+#ifdef __CUDA_ARCH__
+#define NRM_K ::swalbe::nrm_kd
+#else
+#define NRM_K ::swalbe::nrm_kh
+#endif
+
 SW_HD void normal_table_entry(NormalTables &T, int k) {
   if (k < NRM_LOG_N) {
     const float invc = 1.0f / (1.0f + ((float)k + 0.5f) * (1.0f / NRM_LOG_N));  // any float near 1/c_k will do
@@ -77,21 +94,21 @@ SW_HD void normal_polar_from_bits(const uint32_t r[4], const NormalTables &T, do
   const double m = nrm_hilo(0x3ff00000u | (r[1] >> 12), (r[1] << 20) | (r[2] >> 12));
   const double2 lt = T.lg[r[1] >> (32 - NRM_LOG_BITS)];
   const double x = fma(m, lt.x, -1.0);  // m/c - 1, |x| < 2^-7.9;  log1p(x) to x^6
-  double p = fma(x, -1.0 / 6.0, 0.2);
+  double p = fma(x, NRM_K.l6, NRM_K.l5);
   p = fma(x, p, -0.25);
-  p = fma(x, p, 1.0 / 3.0);
+  p = fma(x, p, NRM_K.l3);
   p = fma(x, p, -0.5);
   const double ln_m = lt.y + fma(x * x, p, x);
-  m2lnu = -2.0 * fma((double)(e + 1), -0.6931471805599453, ln_m);
+  m2lnu = -2.0 * fma((double)(e + 1), NRM_K.mln2, ln_m);
   const double2 cs = T.sc[r[3] >> (32 - NRM_ANG_BITS)];
   const int rho = (int)(r[3] & ((1u << (32 - NRM_ANG_BITS)) - 1u)) - (1 << (31 - NRM_ANG_BITS));
-  const double d = ((double)rho + 0.5) * (6.283185307179586 / 4294967296.0);  // offset from the sector centre
+  const double d = ((double)rho + 0.5) * NRM_K.dsc;  // offset from the sector centre
   const double d2 = d * d;
-  double ps = fma(d2, -1.0 / 5040.0, 1.0 / 120.0);
-  ps = fma(d2, ps, -1.0 / 6.0);
+  double ps = fma(d2, NRM_K.s7, NRM_K.s5);
+  ps = fma(d2, ps, NRM_K.s3);
   const double sd = fma(d * d2, ps, d);  // sin δ
-  double pc = fma(d2, 1.0 / 40320.0, -1.0 / 720.0);
-  pc = fma(d2, pc, 1.0 / 24.0);
+  double pc = fma(d2, NRM_K.c8, NRM_K.c6);
+  pc = fma(d2, pc, NRM_K.c4);
   pc = fma(d2, pc, -0.5);
   const double cm1 = d2 * pc;  // cos δ - 1
   c = fma(-cs.y, sd, fma(cs.x, cm1, cs.x));
