@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libswalbe_b200.so")
+SO_PATH = os.environ.get("SWALBE_B200_SO") or os.path.join(_HERE, "libswalbe_b200.so")  # (override: A/B builds)
 
 OK, ERR_DOMAIN, ERR_EXTENT, ERR_CUDA, ERR_NCCL, ERR_ARG = range(6)
 

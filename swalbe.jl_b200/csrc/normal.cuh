@@ -37,7 +37,7 @@ struct NrmConsts {
 static __constant__ NrmConsts nrm_kd = NRM_CONSTS_INIT;
 #endif
 static const NrmConsts nrm_kh = NRM_CONSTS_INIT;
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(NRM_LITERAL_CONSTS)
 #define NRM_K ::swalbe::nrm_kd
 #else
 #define NRM_K ::swalbe::nrm_kh
