@@ -30,7 +30,7 @@ __all__ = [
     "run_rayleightaylor", "run_dropletrelax", "run_dropletpatterned", "run_dropletforced", "wetted", "snapshot",
     "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES", "viewdists", "viewneighbors", "power_broad", "power_2",
     "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field", "torus", "rivulet", "sinewave2d", "randinterface", "circshift",
-    "move_substrate",
+    "move_substrate", "restart_from_height", "save_heights", "dump_height_slab", "load_height_slab",
 ]
 
 
@@ -698,6 +698,8 @@ def run_dropletforced(sys_: SysConst, device: str, radius=20, θ0=1 / 6, center=
     return st.height, st.velx, st.vely
 
 
+from .io import dump_height_slab, load_height_slab, restart_from_height, save_heights  # noqa: E402
+
 JULIA_NAMES = {
     "equilibrium!": equilibrium, "BGKandStream!": BGKandStream, "moments!": moments, "filmpressure!": filmpressure,
     "h∇p!": hgradp, "∇f!": gradf, "∇²f!": laplacianf, "slippage!": slippage, "slippage2!": slippage2,
@@ -708,5 +710,5 @@ JULIA_NAMES = {
     "SysConst": SysConst, "Sys_const": Sys_const, "Taumucs": Taumucs, "CuState": CuState,
     "CuState_thermal": CuState_thermal, "Swalbe_state": Swalbe_state, "viewdists": viewdists,
     "viewneighbors": viewneighbors, "singledroplet": singledroplet, "torus": torus, "rivulet": rivulet,
-    "randinterface!": randinterface, "circshift!": circshift, "move_substrate!": move_substrate, "power_broad": power_broad, "fast_93": fast_93, "fast_32": fast_32,
+    "randinterface!": randinterface, "circshift!": circshift, "move_substrate!": move_substrate, "restart_from_height": restart_from_height, "power_broad": power_broad, "fast_93": fast_93, "fast_32": fast_32,
 }
