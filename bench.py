@@ -384,7 +384,11 @@ def main():
                      "frac": round(achieved / peak, 4), "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                      "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), "per_gpu": True,
-                     "alg_bytes_per_launch": B_ALG * L * rows},
+                     "alg_bytes_per_launch": B_ALG * L * rows,
+                     # what the kernel really moves (ncu DRAM bytes of one launch / the same live kernel time): the
+                     # tau = 1 kernel never reads the old populations, so it moves ~120 B/LU against the 144 B convention
+                     "dram_gbs": round(traffic / (kernel_ms * 1e-3) / 1e9, 1) if traffic and world == 1 else None,
+                     "dram_frac": round(traffic / (kernel_ms * 1e-3) / 1e9 / peak, 4) if traffic and world == 1 else None},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         "mass_drift_rel": mass_drift,
     }

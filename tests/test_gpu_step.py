@@ -277,6 +277,39 @@ def test_large_grid_properties(sw, L):
     torch.cuda.empty_cache()
 
 
+def test_wide_slab_32768_tiling_equivariance(sw):
+    """The per-GPU slab of the 32768^2 scaling config (32768 x 4096, 1 GiB per plane, > 2^32 bytes into the population
+    block): an initial condition made of four identical 8192-column tiles must stay four identical tiles, bit for bit,
+    and equal the 8192 x 4096 periodic lattice started from one tile (strip seams fall differently in each copy);
+    mass is conserved to round-off."""
+    import torch
+
+    Lt, Ly, ntile = 8192, 4096, 4
+    g = torch.Generator("cuda").manual_seed(7)
+    i = torch.arange(Lt, device="cuda", dtype=torch.float64)
+    j = torch.arange(Ly, device="cuda", dtype=torch.float64)
+    tile = 1.0 + 1e-2 * torch.sin(2 * math.pi * 3 * j / Ly)[:, None] * torch.sin(2 * math.pi * 5 * i / Lt)[None, :]
+    tile += 1e-3 * torch.rand((Ly, Lt), device="cuda", dtype=torch.float64, generator=g)
+    small = sw.SysConst(Lx=Lt, Ly=Ly, param=sw.Taumucs())
+    st1 = sw.Sys(small, "GPU")
+    st1.height.t.copy_(tile)
+    sw.fused_steps(st1, small, 6)
+    want_h, want_f = st1.height.t.clone(), st1.fout.t[8].clone()
+    del st1
+    torch.cuda.empty_cache()
+    wide = sw.SysConst(Lx=Lt * ntile, Ly=Ly, param=sw.Taumucs())
+    st = sw.Sys(wide, "GPU")
+    st.height.t.copy_(tile.repeat(1, ntile))
+    m0 = st.height.t.sum().item()
+    sw.fused_steps(st, wide, 6)
+    assert abs(st.height.t.sum().item() - m0) / m0 < 1e-13
+    for q in range(ntile):
+        assert torch.equal(st.height.t[:, q * Lt:(q + 1) * Lt], want_h), q
+        assert torch.equal(st.fout.t[8][:, q * Lt:(q + 1) * Lt], want_f), q  # last population plane: offsets > 2^32 B
+    del st
+    torch.cuda.empty_cache()
+
+
 def test_skip_aux_keeps_moments_and_populations_current(sw):
     """SWALBE_LOOP_SKIP_AUX: intermediate chunks of a driver skip the materialisation of feq/pressure/h∇p/slip/F; the
     moments and fout == ftemp are still exactly the reference's, and a later default call materialises everything."""
