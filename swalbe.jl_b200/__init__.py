@@ -29,8 +29,9 @@ __all__ = [
     "slippage2", "slippage_ring_riv", "thermal", "inclination", "update", "time_loop", "run_flat", "run_random",
     "run_rayleightaylor", "run_dropletrelax", "run_dropletpatterned", "run_dropletforced", "wetted", "snapshot",
     "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES", "viewdists", "viewneighbors", "power_broad", "power_2",
-    "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field", "torus", "rivulet", "sinewave2d", "randinterface", "circshift",
-    "move_substrate", "restart_from_height", "save_heights", "dump_height_slab", "load_height_slab",
+    "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field", "torus", "rivulet", "sinewave2d",
+    "randinterface", "circshift", "move_substrate", "restart_from_height", "save_heights", "dump_height_slab",
+    "load_height_slab",
 ]
 
 

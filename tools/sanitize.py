@@ -32,6 +32,18 @@ sim.close()
 for op in ("filmpressure", "hgradp", "slippage", "update", "equilibrium", "BGKandStream", "moments"):
     f = getattr(sw, op)
     f(st, sysc) if op not in ("hgradp", "update", "moments") else f(st)
+sw.thermal(st, sysc, seed=3, step=1)  # per-operator thermal kernel (shared-memory noise tables)
+# on-device initial conditions (slab offsets, noisy variants with the shared-memory tables), circshift, cospi
+for jb, rows in ((0, 24), (7, 10)):
+    f = sw.Field(200, rows)
+    sw.singledroplet(f, 40, 1 / 6, (100, 12), j_begin=jb)
+    sw.torus(f, 8, 30, 1 / 9, (100, 12), noise=0.01, seed=2, j_begin=jb)
+    sw.rivulet(f, 10, 1 / 9, "x", 12, noise=0.01, seed=2, j_begin=jb)
+    sw.sinewave2d(f, 1.0, 0.01, 3, 2, j_begin=jb, Ly=24)
+    sw.randinterface(f, 1.0, 0.01, seed=4, j_begin=jb)
+g = sw.Field(200, 24)
+sw.circshift(g, h, (3, -5))
+sw.cospi_field(g)
 print("stats", sw.field_stats(st.height))
 import torch
 torch.cuda.synchronize()
