@@ -51,7 +51,32 @@ def initial_height(L, Ly=None, j0=0, Ly_global=None, workload="film"):
     if workload == "spinodal":
         rng = np.random.default_rng([20261017, j0])
         return np.asfortranarray(1.0 + 0.01 * rng.standard_normal((L, Ly)))
-    return np.asfortranarray(1.0 + 1e-3 * np.sin(2 * np.pi * i / L) * np.sin(2 * np.pi * j / Ly_global))
+    amp = 0.1 if workload == "thermal_moving" else 1e-3
+    return np.asfortranarray(1.0 + amp * np.sin(2 * np.pi * i / L) * np.sin(2 * np.pi * j / Ly_global))
+
+
+TMOVE = 98  # C4: the contact-angle pattern moves by (1, 1) every 98 steps (scripts/Moving_wettability_structs.jl:182-200)
+
+
+def theta_pattern(L, Ly=None, j0=0, Ly_global=None):
+    """C4 contact-angle field θ[i,j] = 1/9 + (1/36) sin(2π 2(i-1)/Lx) sin(2π 2(j-1)/Ly) (rows j0 .. j0+Ly)."""
+    import numpy as np
+
+    Ly = Ly or L
+    Ly_global = Ly_global or Ly
+    i = np.arange(L, dtype=np.float64)[:, None]
+    j = (j0 + np.arange(Ly, dtype=np.float64))[None, :]
+    return np.asfortranarray(1 / 9 + (1 / 36) * np.sin(2 * np.pi * 2 * i / L) * np.sin(2 * np.pi * 2 * j / Ly_global))
+
+
+def segments(s0, n, period=TMOVE):
+    """Split steps [s0, s0+n) at the multiples of `period`: [(first step, count, move the substrate afterwards?)]."""
+    out, t, end = [], s0, s0 + n
+    while t < end:
+        nxt = min(end, (t // period + 1) * period)
+        out.append((t, nxt - t, nxt % period == 0))
+        t = nxt
+    return out
 
 
 def workload_params(args, K):
@@ -59,6 +84,8 @@ def workload_params(args, K):
     kw = dict(Tmax=K, tdump=max(1, K // 2))
     if args.workload == "thermal":
         kw.update(kbt=1e-7)
+    elif args.workload == "thermal_moving":
+        kw.update(kbt=1e-7, γ=0.01, δ=1.0, μ=1 / 12, n=3, m=2, hmin=0.07)
     elif args.workload == "droplet":
         kw.update(n=3, m=2, hmin=0.07, δ=1.0)
     elif args.workload == "spinodal":
@@ -132,11 +159,17 @@ def cpu_baseline_run(L, steps, threads, warmup=1, workload="film"):
     oc.build()
     st = onp.State(L, L)
     st.height[...] = initial_height(L, workload=workload)
-    okw = {"droplet": dict(n=3, m=2, hmin=0.07), "spinodal": dict(n=3, m=2, hmin=0.07, gamma=0.01)}.get(workload, {})
+    okw = {"droplet": dict(n=3, m=2, hmin=0.07), "spinodal": dict(n=3, m=2, hmin=0.07, gamma=0.01),
+           "thermal_moving": dict(n=3, m=2, hmin=0.07, gamma=0.01, mu=1 / 12)}.get(workload, {})
     p = onp.Params(**okw)
-    oc.time_loop(st, p, nsteps=warmup, threads=threads)
+    lkw = dict(threads=threads)
+    if workload == "thermal_moving":  # the contact-angle field (cospi evaluated once on the host, as the oracle takes it)
+        import numpy as np
+
+        lkw["cospi_theta"] = np.asfortranarray(np.cos(np.pi * theta_pattern(L)))
+    oc.time_loop(st, p, nsteps=warmup, **lkw)
     t0 = time.perf_counter()
-    oc.time_loop(st, p, nsteps=steps, threads=threads)
+    oc.time_loop(st, p, nsteps=steps, **lkw)
     dt = time.perf_counter() - t0
     return L * L * steps / dt / 1e6, dt
 
@@ -168,7 +201,9 @@ def run_reference(args, rank):
 
 def workload_config(args):
     what = {"film": "Taumucs defaults (n=9,m=3,theta=1/9), flat film + sine perturbation (SURVEY 8d C5)",
-            "thermal": "Taumucs defaults + thermal noise kbt=1e-7 generated in-kernel (Philox), flat film + sine (C4)",
+            "thermal": "Taumucs defaults + thermal noise kbt=1e-7 generated in-kernel (Philox), flat film + sine (C4 noise only)",
+            "thermal_moving": "C4 complete: thermal noise kbt=1e-7 (Philox, in-kernel) + contact-angle pattern theta(x,y) moved "
+                              "by (1,1) every 98 steps on the device, n=3,m=2,hmin=0.07,gamma=0.01,mu=1/12, h=1+0.1 sin sin",
             "droplet": "n=3,m=2,hmin=0.07,theta=1/9, spherical-cap droplet radius min(L/4,256) on a 0.05 precursor (C2)",
             "spinodal": "n=3,m=2,hmin=0.07,gamma=0.01, randomly perturbed film h=1+0.01 N(0,1) (C3)"}[args.workload]
     weak = args.gpus == 1 or getattr(args, "scaling", "weak") == "weak"
@@ -186,8 +221,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--L", type=int, default=8192)
-    ap.add_argument("--workload", default="film", choices=["film", "thermal", "droplet", "spinodal"],
-                    help="film: C5 flat film + sine (default); thermal: C4 (+Philox noise); droplet: C2 spherical cap, "
+    ap.add_argument("--workload", default="film", choices=["film", "thermal", "thermal_moving", "droplet", "spinodal"],
+                    help="film: C5 flat film + sine (default); thermal: film + Philox noise; thermal_moving: the complete C4 "
+                         "(noise + contact-angle pattern moved by (1,1) every 98 steps, n=3,m=2,hmin=0.07,mu=1/12); droplet: C2 spherical cap, "
                          "n=3,m=2,hmin=0.07 (use --L 1024); spinodal: C3 random film, n=3,m=2,hmin=0.07,gamma=0.01 (--L 4096)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = L x L per rank (default, the contract), strong = L x L in total (L/N rows per rank)")
@@ -227,15 +263,28 @@ def main():
     sysc = sw.SysConst(Lx=L, Ly=L, param=prm)
     rows = L if (world == 1 or args.scaling == "weak") else L // world   # rows per rank
     Ly_glob = rows * world
-    thermal_seed = 1234 if args.workload == "thermal" else None
+    thermal_seed = 1234 if args.workload in ("thermal", "thermal_moving") else None
+    moving = args.workload == "thermal_moving"
     e2e = None
 
     if world == 1:
         st = sw.Sys(sysc, "GPU", kind="thermal" if thermal_seed is not None else "simple")
         h0 = initial_height(L, workload=args.workload)
         st.height.set(h0)
-        run = lambda n, s0=0: sw.fused_steps(st, sysc, n, thermal_seed=thermal_seed, step0=s0,  # noqa: E731
-                                             pressure_variant=_lib.PRESSURE_POWER_BROAD)
+        th = inp = None
+        if moving:
+            th, inp = sw.Field(L, L).set(theta_pattern(L)), sw.Field(L, L)
+            inp.set(th)
+
+        def run(n, s0=0, **kw):
+            if not moving:
+                return sw.fused_steps(st, sysc, n, thermal_seed=thermal_seed, step0=s0,
+                                      pressure_variant=_lib.PRESSURE_POWER_BROAD, **kw)
+            for t0, cnt, move in segments(s0, n):
+                sw.fused_steps(st, sysc, cnt, thermal_seed=thermal_seed, step0=t0, θ=th,
+                               pressure_variant=_lib.PRESSURE_POWER_BROAD, **kw)
+                if move:
+                    sw.move_substrate(th, inp, t0 + cnt, TMOVE)
         sampler = early_sampler
         run(W)
         torch.cuda.synchronize()
@@ -253,9 +302,9 @@ def main():
         lu = L * L * K
         # moments-only row (populations materialised on the last step only), reported separately
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sw.fused_steps(st, sysc, W, thermal_seed=thermal_seed, lazy_populations=True)
+        run(W, lazy_populations=True)
         e2.record()
-        sw.fused_steps(st, sysc, K, thermal_seed=thermal_seed, lazy_populations=True)
+        run(K, W, lazy_populations=True)
         e3.record()
         torch.cuda.synchronize()
         lazy_mlups = lu / (e2.elapsed_time(e3) * 1e-3) / 1e6
@@ -271,7 +320,7 @@ def main():
                 if thermal_seed is None:
                     sw.time_loop(sysc, st)
                 else:
-                    sw.fused_steps(st, sysc, K, thermal_seed=thermal_seed)
+                    run(sysc.param.Tmax)
                 out_host.copy_(st.height.t, non_blocking=True)
                 torch.cuda.synchronize()
 
@@ -312,15 +361,28 @@ def main():
         zero = sw.Field(L, rows)
         stream = sw._stream()
         _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
+
+        def set_theta():
+            if moving:  # this rank's rows of the pattern; cospi.(θ) on the device
+                ct = sw.cospi_field(sw.Field(L, rows).set(theta_pattern(L, rows, rank * rows, Ly_glob)))
+                _lib.call("swalbe_dist_set_theta", handle, ct.ptr, stream)
+
+        def dist_run(n, s0):
+            for t0, cnt, move in (segments(s0, n) if moving else [(s0, n, False)]):
+                _lib.call("swalbe_dist_time_loop", handle, cnt, t0, stream)
+                if move:
+                    _lib.call("swalbe_dist_shift_theta", handle, 1, 1, stream)
+
+        set_theta()
         sampler = early_sampler
-        _lib.call("swalbe_dist_time_loop", handle, W, 0, stream)
+        dist_run(W, 0)
         torch.cuda.synchronize()
         dist.barrier()
         l0 = lib.swalbe_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with sampler as clocks:
             e0.record()
-            _lib.call("swalbe_dist_time_loop", handle, K, W, stream)
+            dist_run(K, W)
             e1.record()
             torch.cuda.synchronize()
         dist.barrier()
@@ -343,7 +405,8 @@ def main():
             t0 = time.perf_counter()
             hd.t.copy_(h_host, non_blocking=True)
             _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
-            _lib.call("swalbe_dist_time_loop", handle, K, 0, stream)
+            set_theta()
+            dist_run(K, 0)
             _lib.call("swalbe_dist_get_state", handle, hd.ptr, None, None, None, stream)
             out_host.copy_(hd.t, non_blocking=True)
             torch.cuda.synchronize()

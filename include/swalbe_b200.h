@@ -249,6 +249,12 @@ int swalbe_dist_set_state(swalbe_dist *dist, const double *height, const double 
 /* contact-angle field: this rank's rows of cospi.(theta) (Lx * j_count, device); NULL switches back to the scalar of
  * `params`.  Ghost rows are exchanged once here; call again after moving the substrate. */
 int swalbe_dist_set_theta(swalbe_dist *dist, const double *cospi_theta_slab, void *stream);
+
+/* move_substrate! on the slab runtime (scripts/Moving_wettability_structs.jl:139-152): the contact-angle field of the
+ * whole lattice is shifted periodically by (sx, sy), theta[i,j] <- theta[i-sx, j-sy].  Rows that cross a slab boundary
+ * come out of the ghost rows, so |sy| <= 3; the ghost rows are exchanged again afterwards.  Collective: every rank
+ * calls it with the same shift. */
+int swalbe_dist_shift_theta(swalbe_dist *d, int sx, int sy, void *stream);
 /* min / max / sum / count(h > thresh) of this rank's rows of the height field -> out4[4] (device); combine across
  * ranks on the host (min, max, +, +).  sum(state.height) src/simulate.jl:8-14, wetted! src/measures.jl:13-17 */
 int swalbe_dist_height_stats(swalbe_dist *dist, double *out4, double thresh, void *stream);

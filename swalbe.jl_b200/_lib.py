@@ -87,6 +87,7 @@ SIGNATURES = {
     "swalbe_dist_local_rows": [_vp, C.POINTER(_i), C.POINTER(_i)],
     "swalbe_dist_set_state": [_vp, _vp, _vp, _vp, _vp, _vp],
     "swalbe_dist_set_theta": [_vp, _vp, _vp],
+    "swalbe_dist_shift_theta": [_vp, _i, _i, _vp],
     "swalbe_dist_height_stats": [_vp, _vp, _d, _vp],
     "swalbe_dist_time_loop": [_vp, _i, _u64, _vp],
     "swalbe_dist_get_state": [_vp, _vp, _vp, _vp, _vp, _vp],

@@ -77,6 +77,7 @@ struct swalbe_dist {
   double *m[2][3];        // ping-pong sets of (h, ux, uy)
   double *f[2];           // population sets (tau == 1: only f[0], no ghosts)
   double *ct;             // cospi(theta) slab with GH ghost rows (NULL: scalar theta)
+  double *ct_alt;         // second buffer of the same shape: target of swalbe_dist_shift_theta (allocated on first use)
   int cur;                // index of the set holding the current moments
   int fcur;               // index of the set holding the current populations (tau != 1)
   ncclComm_t comm;
@@ -87,6 +88,17 @@ struct swalbe_dist {
   FusedArgs base;
   float last_ms;
 };
+
+// dst[j, i] = src[j - sy, i - sx] for the owned rows j in [0, Ly_loc) of a ghosted slab plane (|sy| <= GH: the source rows
+// come from the ghost rows, which the last exchange made current); x is periodic inside the slab
+__global__ void k_shift_slab(double *__restrict__ dst, const double *__restrict__ src, int sx, int sy, int Lx, int Ly_loc) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Lx * (size_t)Ly_loc) return;
+  const int j = (int)(idx / (size_t)Lx), i = (int)(idx - (size_t)j * Lx);
+  int is = i - sx;
+  is += is < 0 ? Lx : 0;
+  dst[(size_t)(j + GH) * Lx + i] = src[(size_t)(j + GH - sy) * Lx + is];
+}
 
 static int exchange_rows(swalbe_dist *d, double *plane, int gh, size_t rows_total) {
   // plane has rows [-gh, Ly_loc+gh) stored at physical rows [0, Ly_loc+2gh); send the gh top/bottom owned rows,
@@ -214,6 +226,7 @@ int swalbe_dist_destroy(swalbe_dist *d) {
     cudaFree(d->f[s]);
   }
   cudaFree(d->ct);
+  cudaFree(d->ct_alt);
   if (d->s_comp) cudaStreamDestroy(d->s_comp);
   if (d->s_comm) cudaStreamDestroy(d->s_comm);
   if (d->s_edge) cudaStreamDestroy(d->s_edge);
@@ -360,6 +373,36 @@ int swalbe_dist_set_theta(swalbe_dist *d, const double *ct_slab, void *stream_) 
   d->key.bulk = d->key.lean_pm > 0 && !d->key.opts && !d->key.thermal && bulk_eligible(d->Lx, (size_t)d->Lx * Ly_loc);
   if (int e = choose_geometry(d->Lx, Ly_loc - 2 * GH > 0 ? Ly_loc - 2 * GH : Ly_loc, d->key, &d->g_int)) return e;
   if (int e = choose_geometry(d->Lx, GH, d->key_edge, &d->g_edge)) return e;
+  return 0;
+}
+
+int swalbe_dist_shift_theta(swalbe_dist *d, int sx, int sy, void *stream_) {
+  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
+  if (!d->ct) return set_error(SWALBE_ERR_ARG, "swalbe_dist_shift_theta: no theta field is set (swalbe_dist_set_theta)");
+  if (sy < -GH || sy > GH) return set_error(SWALBE_ERR_ARG, "swalbe_dist_shift_theta: |sy| = %d exceeds the ghost depth %d", sy, GH);
+  cudaStream_t user = (cudaStream_t)stream_;
+  if (!d->ct_alt) {
+    SW_CUDA(cudaMalloc((void **)&d->ct_alt, d->mplane * sizeof(double)));
+    SW_CUDA(cudaMemset(d->ct_alt, 0, d->mplane * sizeof(double)));
+  }
+  sx %= d->Lx;
+  if (sx < 0) sx += d->Lx;
+  // ordered on the caller's stream: after the previous time loop (its end event was awaited on this stream) and after
+  // the ghost exchange of the last set/shift
+  const size_t n = (size_t)d->Lx * d->Ly_loc;
+  k_shift_slab<<<(unsigned)((n + 255) / 256), 256, 0, user>>>(d->ct_alt, d->ct, sx, sy, d->Lx, d->Ly_loc);
+  SW_LAUNCH_CHECK();
+  double *t = d->ct; d->ct = d->ct_alt; d->ct_alt = t;
+  d->prm.cospi_theta_field = d->ct;
+  SW_CUDA(cudaEventRecord(d->ev_user, user));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_user, 0));
+  if (d->nranks > 1) SW_NCCL(g_nccl.GroupStart());
+  if (int e = exchange_rows(d, d->ct, GH, d->Ly_loc + 2 * GH)) return e;
+  if (d->nranks > 1) SW_NCCL(g_nccl.GroupEnd());
+  SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+  SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_halo, 0));
+  SW_CUDA(cudaStreamWaitEvent(user, d->ev_halo, 0));
   return 0;
 }
 

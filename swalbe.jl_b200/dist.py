@@ -108,6 +108,10 @@ class DistSim:
         _lib.call("swalbe_dist_set_theta", self.handle, cospi_theta_slab.ptr if cospi_theta_slab is not None else None,
                   self._stream())
 
+    def shift_theta(self, sx: int, sy: int):
+        """move_substrate! across the slabs: θ[i, j] <- θ[i - sx, j - sy] on the global lattice (|sy| <= 3); collective."""
+        _lib.call("swalbe_dist_shift_theta", self.handle, int(sx), int(sy), self._stream())
+
     def height_stats(self, thresh=0.055):
         """(min, max, sum, count(h > thresh)) of this rank's rows; combine across ranks with min/max/+/+."""
         import torch

@@ -16,7 +16,7 @@ def main():
     from swalbe_b200.dist import DistSim, broadcast_unique_id_torch, slab_of
 
     out, mode = sys.argv[1], sys.argv[2]
-    thermal = mode == "thermal"
+    thermal = mode in ("thermal", "moving_theta_thermal")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl")
@@ -29,10 +29,12 @@ def main():
     h, z1, z2 = sw.Field(Lx, n).set(slab_of(hg, sim.decomp, rank)), sw.Field(Lx, n), sw.Field(Lx, n)
     sim.set_state(h, z1, z2)
     theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))  # same draw order as the single-GPU reference run
-    if mode == "theta_field":
+    if mode in ("theta_field", "moving_theta_thermal"):
         ct = sw.cospi_field(sw.Field(Lx, Ly).set(theta)).numpy()  # same device cospi.(θ) as the single-GPU run
         sim.set_theta(sw.Field(Lx, n).set(slab_of(ct, sim.decomp, rank)))
     sim.time_loop(5)
+    if mode == "moving_theta_thermal":
+        sim.shift_theta(1, 1)
     sim.time_loop(4, step0=5)
     sim.get_state(h)
     parts = [torch.empty_like(h.t) for _ in range(world)]

@@ -67,11 +67,23 @@ def test_single_rank_slab_theta_field_and_stats():
     assert np.array_equal(h.numpy(), ref.height)
     assert mn == ref.height.min() and mx == ref.height.max() and cnt == int((ref.height > 1.0).sum())
     assert abs(sm - ref.height.sum()) < 1e-10 * ref.height.sum()
+    # move_substrate! on the slab runtime: periodic shifts of the field, rows crossing the slab edge via the ghost rows
+    for shift in [(1, 1), (0, -3), (-5, 2), (Lx + 2, 0)]:
+        sim.shift_theta(*shift)
+        ct = onp.circshift(ct, shift)
+        sim.time_loop(2)
+        oc.time_loop(ref, p, nsteps=2, cospi_theta=ct)
+        sim.get_state(h)
+        assert np.array_equal(h.numpy(), ref.height), shift
+    with pytest.raises(ValueError):
+        sim.shift_theta(0, 4)  # deeper than the ghost rows
     sim.set_theta(None)  # back to the scalar theta of the params
     sim.time_loop(3)
     sim.get_state(h)
     oc.time_loop(ref, p, nsteps=3)
     assert np.array_equal(h.numpy(), ref.height)
+    with pytest.raises(ValueError):
+        sim.shift_theta(1, 1)  # no field to move
     sim.close()
 
 
@@ -111,7 +123,7 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("mode", ["plain", "thermal", "theta_field"])
+@pytest.mark.parametrize("mode", ["plain", "thermal", "theta_field", "moving_theta_thermal"])
 def test_two_rank_nccl_matches_single_gpu(tmp_path, mode):
     """2 ranks over NCCL == 1 GPU, bit for bit -- including the thermal noise (counter-based on the global cell) and a
     contact-angle field whose ghost rows travel through the same exchange."""
@@ -125,7 +137,7 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path, mode):
     import swalbe_b200 as sw
 
     Lx, Ly = 520, 96
-    thermal = mode == "thermal"
+    thermal = mode in ("thermal", "moving_theta_thermal")
     sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(kbt=1e-6 if thermal else 0.0, g=-0.001))
     st = sw.Sys(sysc, "GPU", kind="thermal" if thermal else "simple")
     rng = np.random.default_rng(5)
@@ -133,6 +145,12 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path, mode):
     theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))
     from swalbe_b200 import _lib
 
-    sw.fused_steps(st, sysc, 9, thermal_seed=77 if thermal else None, pressure_variant=_lib.PRESSURE_POWER_BROAD,
-                   θ=sw.Field(Lx, Ly).set(theta) if mode == "theta_field" else None)
+    kw = dict(thermal_seed=77 if thermal else None, pressure_variant=_lib.PRESSURE_POWER_BROAD)
+    if mode == "moving_theta_thermal":  # C4: noise + a contact-angle pattern that moves by (1,1) between the two loops
+        th, inp = sw.Field(Lx, Ly).set(theta), sw.Field(Lx, Ly).set(theta)
+        sw.fused_steps(st, sysc, 5, θ=th, **kw)
+        sw.move_substrate(th, inp, 98, 98)
+        sw.fused_steps(st, sysc, 4, θ=th, step0=5, **kw)
+    else:
+        sw.fused_steps(st, sysc, 9, θ=sw.Field(Lx, Ly).set(theta) if mode == "theta_field" else None, **kw)
     assert np.array_equal(got, st.height.numpy())
