@@ -37,4 +37,7 @@ namespace swalbe {
 int fill_consts(FusedArgs &a, const swalbe_params &p);
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean);
 bool bulk_eligible(int Lx, size_t ncells);
+// small-lattice tile flavour of the strict lean step (tile.cu)
+bool tile_eligible(const KernelKey &key, const FusedArgs &a);
+int launch_tile(const FusedArgs &a, const KernelKey &key, cudaStream_t stream);
 }

@@ -310,6 +310,46 @@ def test_wide_slab_32768_tiling_equivariance(sw):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("prm_kw,tau_pops,nsteps", [(dict(g=-0.001), False, 10), (dict(), False, 9),
+                                                     (dict(τ=0.8), True, 8), (dict(τ=0.8, n=3, m=2, hmin=0.07), True, 11)])
+def test_repeated_loops_replay_a_cuda_graph_bitwise(sw, prm_kw, tau_pops, nsteps):
+    """The chunks of a driver repeat the same call; from the second repetition on the library replays a captured CUDA
+    graph of the loop.  Four identical calls (plain launches, capture + launch, two replays) against the oracle, bit for
+    bit, with the launch counter advancing by nsteps every time; a changed parameter must not hit the stale graph."""
+    from swalbe_b200 import _lib
+
+    lib = _lib.load()
+    st, sysc, ref, p = _mk(sw, 70, 52, seed=11, prm_kw=prm_kw, tau_pops=tau_pops)
+    for rep in range(4):
+        c0 = lib.swalbe_launch_count()
+        sw.fused_steps(st, sysc, nsteps)
+        assert lib.swalbe_launch_count() - c0 == nsteps, rep
+        oc.time_loop(ref, p, nsteps=nsteps)
+        _compare(st, ref, what=f"repetition {rep}: ")
+    # same shapes, different surface tension: a new key -> plain launches again, no stale replay
+    kw2 = dict(prm_kw, γ=0.02)
+    sysc2 = sw.SysConst(Lx=70, Ly=52, param=sw.Taumucs(**kw2))
+    p2 = onp.Params(**{{"τ": "tau", "γ": "gamma"}.get(k, k): v for k, v in kw2.items()})
+    for rep in range(3):
+        sw.fused_steps(st, sysc2, nsteps)
+        oc.time_loop(ref, p2, nsteps=nsteps)
+        _compare(st, ref, what=f"second parameter set, repetition {rep}: ")
+    # skip_aux / lazy chunks (what time_loop issues between mass prints) replay as well
+    for rep in range(3):
+        sw.fused_steps(st, sysc2, nsteps, skip_aux=True)
+        oc.time_loop(ref, p2, nsteps=nsteps)
+        _compare(st, ref, fields=("height", "velx", "vely", "fout", "ftemp"), what=f"skip_aux repetition {rep}: ")
+
+
+def test_graph_replay_can_be_switched_off(sw, monkeypatch):
+    monkeypatch.setenv("SWALBE_GRAPH", "0")
+    st, sysc, ref, p = _mk(sw, 64, 40, seed=3, prm_kw=dict(g=-0.001))
+    for _ in range(3):
+        sw.fused_steps(st, sysc, 8)
+        oc.time_loop(ref, p, nsteps=8)
+    _compare(st, ref)
+
+
 def test_skip_aux_keeps_moments_and_populations_current(sw):
     """SWALBE_LOOP_SKIP_AUX: intermediate chunks of a driver skip the materialisation of feq/pressure/h∇p/slip/F; the
     moments and fout == ftemp are still exactly the reference's, and a later default call materialises everything."""
