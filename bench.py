@@ -280,8 +280,9 @@ def main():
             if not moving:
                 return sw.fused_steps(st, sysc, n, thermal_seed=thermal_seed, step0=s0,
                                       pressure_variant=_lib.PRESSURE_POWER_BROAD, **kw)
-            for t0, cnt, move in segments(s0, n):
-                sw.fused_steps(st, sysc, cnt, thermal_seed=thermal_seed, step0=t0, θ=th,
+            segs = segments(s0, n)
+            for q, (t0, cnt, move) in enumerate(segs):  # like the drivers' chunks: intermediate fields on the last one only
+                sw.fused_steps(st, sysc, cnt, thermal_seed=thermal_seed, step0=t0, θ=th, skip_aux=q < len(segs) - 1,
                                pressure_variant=_lib.PRESSURE_POWER_BROAD, **kw)
                 if move:
                     sw.move_substrate(th, inp, t0 + cnt, TMOVE)
