@@ -40,6 +40,15 @@ def _mk(sw, Lx, Ly, seed, prm_kw, tau_pops=False):
     return st, sysc, ref, onp.Params(**okw)
 
 
+@pytest.fixture(params=["tile", "march"])
+def small_lattice_flavour(request, monkeypatch):
+    """Lean steps of lattices <= 512^2 run through the tile kernel by default; "march" forces the marching kernel so
+    that both flavours see every small parity case."""
+    if request.param == "march":
+        monkeypatch.setenv("SWALBE_TILE_MAX", "0")
+    return request.param
+
+
 def _compare(st, ref, fields=STATE_FIELDS, what=""):
     for name in fields:
         got, want = getattr(st, name).numpy(), getattr(ref, name)
@@ -49,7 +58,7 @@ def _compare(st, ref, fields=STATE_FIELDS, what=""):
 
 @pytest.mark.parametrize("Lx,Ly", [(5, 5), (25, 26), (150, 200), (100, 96), (257, 19), (600, 40), (7, 300)])
 @pytest.mark.parametrize("nsteps", [1, 2, 7])
-def test_fused_loop_bitwise_default_params(sw, Lx, Ly, nsteps):
+def test_fused_loop_bitwise_default_params(sw, Lx, Ly, nsteps, small_lattice_flavour):
     st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx * 1000 + Ly, prm_kw=dict(g=-0.001, γ=0.0005))
     sw.fused_steps(st, sysc, nsteps)
     oc.time_loop(ref, p, nsteps=nsteps)
@@ -57,7 +66,7 @@ def test_fused_loop_bitwise_default_params(sw, Lx, Ly, nsteps):
 
 
 @pytest.mark.parametrize("Lx,Ly", [(1, 1), (2, 3), (3, 1), (1, 40), (9, 2)])
-def test_fused_loop_tiny_extents(sw, Lx, Ly):
+def test_fused_loop_tiny_extents(sw, Lx, Ly, small_lattice_flavour):
     """Degenerate periodic lattices: every neighbour is a wrapped copy of the few sites there are."""
     for kw, pops in ((dict(g=-0.001), False), (dict(τ=0.9), True)):
         st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx * 10 + Ly, prm_kw=kw, tau_pops=pops)
@@ -74,7 +83,7 @@ def test_fused_loop_tiny_extents(sw, Lx, Ly):
     dict(μ=1 / 12, δ=0.25, θ=1 / 6),
 ], ids=lambda d: ",".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in d.items()))
 @pytest.mark.parametrize("nsteps", [1, 4, 5])
-def test_fused_loop_bitwise_param_sets(sw, prm_kw, nsteps):
+def test_fused_loop_bitwise_param_sets(sw, prm_kw, nsteps, small_lattice_flavour):
     st, sysc, ref, p = _mk(sw, 70, 45, seed=11, prm_kw=prm_kw, tau_pops="τ" in prm_kw)
     sw.fused_steps(st, sysc, nsteps)
     oc.time_loop(ref, p, nsteps=nsteps)
@@ -119,7 +128,7 @@ def test_fused_equals_operator_by_operator_on_gpu(sw):
         assert np.array_equal(getattr(st, name).numpy(), getattr(st2, name).numpy()), name
 
 
-def test_lazy_populations_same_result(sw):
+def test_lazy_populations_same_result(sw, small_lattice_flavour):
     st, sysc, ref, p = _mk(sw, 90, 70, seed=5, prm_kw=dict())
     sw.fused_steps(st, sysc, 9, lazy_populations=True)
     oc.time_loop(ref, p, nsteps=9)
@@ -312,7 +321,7 @@ def test_wide_slab_32768_tiling_equivariance(sw):
 
 @pytest.mark.parametrize("prm_kw,tau_pops,nsteps", [(dict(g=-0.001), False, 10), (dict(), False, 9),
                                                      (dict(τ=0.8), True, 8), (dict(τ=0.8, n=3, m=2, hmin=0.07), True, 11)])
-def test_repeated_loops_replay_a_cuda_graph_bitwise(sw, prm_kw, tau_pops, nsteps):
+def test_repeated_loops_replay_a_cuda_graph_bitwise(sw, prm_kw, tau_pops, nsteps, small_lattice_flavour):
     """The chunks of a driver repeat the same call; from the second repetition on the library replays a captured CUDA
     graph of the loop.  Four identical calls (plain launches, capture + launch, two replays) against the oracle, bit for
     bit, with the launch counter advancing by nsteps every time; a changed parameter must not hit the stale graph."""
@@ -418,7 +427,7 @@ def test_special_values_propagate_like_the_reference(sw):
             assert np.isfinite(want).sum() > 0.3 * want.size  # a good part of the lattice is still healthy
 
 
-def test_spinodal_dewetting_long_run_bitwise(sw):
+def test_spinodal_dewetting_long_run_bitwise(sw, small_lattice_flavour):
     """A physically UNSTABLE configuration (thin random film, disjoining pressure n=3, m=2: spinodal dewetting, C3-style)
     amplifies any rounding difference exponentially: the perturbation first decays, then grows 6x within 3000 steps.
     The whole max-min history and the final fields must still equal the oracle bit for bit."""

@@ -19,6 +19,18 @@ for (Lx, Ly, kw) in [(25, 26, {}), (300, 40, dict(n=3, m=2, hmin=0.07)), (130, 3
     th = sw.Field(Lx, Ly).set(np.full((Lx, Ly), 1 / 9))
     sw.fused_steps(st, sysc, 2, θ=th, slip_variant=2, incl=([1e-4, 0.0], 1.0))
     print("ok", Lx, Ly, kw, float(st.height.t.sum()))
+# small-lattice flavours: marching lean kernels forced, then the tile kernel with CUDA-graph capture + replay
+os.environ["SWALBE_TILE_MAX"] = "0"
+sysc = sw.SysConst(Lx=70, Ly=44, param=sw.Taumucs())
+st = sw.Sys(sysc, "GPU")
+st.height.set(np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((70, 44))) + 0.06))
+for _ in range(3):
+    sw.fused_steps(st, sysc, 9)
+del os.environ["SWALBE_TILE_MAX"]
+for _ in range(4):
+    sw.fused_steps(st, sysc, 9)
+    sw.fused_steps(st, sysc, 9)
+print("ok small-lattice flavours", float(st.height.t.sum()))
 sysc = sw.SysConst(Lx=200, Ly=24, param=sw.Taumucs(kbt=1e-6))
 st = sw.Sys(sysc, "GPU", kind="thermal")
 sw.fused_steps(st, sysc, 3, thermal_seed=5)
