@@ -282,7 +282,7 @@ static GraphKey make_graph_key(const swalbe_state *st, const swalbe_params *p, i
 // Not for thermal loops (the step counter is baked into the nodes) or per-step logs (their slots move).
 static bool graph_candidate(const swalbe_plan *plan, const swalbe_params *prm, int nsteps, const swalbe_loop_logs *logs,
                             cudaStream_t stream) {
-  if (!env_int("SWALBE_GRAPH", 1) || nsteps < 8 || prm->use_thermal) return false;
+  if (!env_int("SWALBE_GRAPH", 1) || nsteps < 8 || nsteps > 16384 || prm->use_thermal) return false;  // (graph size bound)
   if (logs && (logs->hmin || logs->hmax || logs->wetted)) return false;
   if ((size_t)plan->Lx * plan->Ly > (size_t)std::max(0, env_int("SWALBE_GRAPH_MAX", 1024 * 1024))) return false;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
