@@ -23,7 +23,6 @@ static const Variant *const g_variants[] = {&g_variant_128, &g_variant_160, &g_v
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
-  if (k.lean_pm > 0 && k.tf) return var.tf[k.thermal ? 1 : 0][k.lean_pm][k.bulk ? 1 : 0];
   if (k.lean_pm > 0 && k.opts) return var.opts[k.thermal ? 1 : 0][k.lean_pm];
   if (k.lean_pm > 0 && k.bulk) return var.bulk[k.lean_pm][k.gz ? 1 : 0];
   if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm][k.gz ? 1 : 0];
@@ -173,15 +172,8 @@ KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   k.gz = p.g == 0.0;
   k.lazy = false;
   k.opts = p.cospi_theta_field != nullptr || p.slip_variant != SWALBE_SLIP_STANDARD || p.use_inclination != 0;
-  k.tf = false;
   if (want_lean && k.tau1 && pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
-  // a theta field and nothing else (the moving-wettability scripts): the strict flavour compiled for it
-  if (k.lean_pm > 0 && k.gz && p.cospi_theta_field != nullptr && p.slip_variant == SWALBE_SLIP_STANDARD &&
-      p.use_inclination == 0 && env_int("SWALBE_TF", 1)) {
-    k.tf = true;
-    k.opts = false;
-  }
   return k;
 }
 
@@ -225,15 +217,15 @@ struct swalbe_plan {
   GraphKey graph_key, seen_key;
   bool have_graph, have_seen;
   int graph_nsteps;
-  LaunchGeom geom[2][2][5][2][2][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy][opts][tf]
-  bool geom_ok[2][2][5][2][2][2][2][2];
+  LaunchGeom geom[2][2][5][2][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy][opts]
+  bool geom_ok[2][2][5][2][2][2][2];
 };
 
 static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
-  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts][k.tf];
-  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts][k.tf]) {
+  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts];
+  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts]) {
     if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
-    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts][k.tf] = true;
+    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts] = true;
   }
   *g = &gg;
   return 0;
@@ -362,7 +354,7 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   if (int e = fill_consts(a, *prm)) return e;
   const KernelKey key_full = make_key(*prm, a.pc.pmode, false);
   KernelKey key_mid = make_key(*prm, a.pc.pmode, true);  // lean kernel for the steps before the last
-  if (logs && (logs->hmin || logs->wetted)) { key_mid.opts = true; key_mid.tf = false; }
+  if (logs && (logs->hmin || logs->wetted)) key_mid.opts = true;
   // bulk-copy (TMA unit) row prefetch: needs 16-byte aligned row segments, i.e. even Lx and 16-B aligned planes
   auto aligned16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
   // Measured on B200: +3 % where the step is HBM-bound (8192^2: 43.2 vs 41.9 GLUPS), -2..3 % where it is latency- or

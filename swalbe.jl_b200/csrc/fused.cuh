@@ -172,7 +172,7 @@ constexpr int FUSED_LINES = FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES + 4 * RU
 constexpr int FUSED_PAD = 2;
 constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2 * FUSED_PAD); }
 
-template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS, bool TF = false>
+template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(16) double smem[];
   constexpr bool LEAN = PM >= 0;
@@ -249,8 +249,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   unsigned int d_wet = 0;
   // OPTS kernels take the uncommon options at run time; the strict lean kernels (OPTS == false) have them compiled out
   const bool logging = OPTS && (a.log_min != nullptr || a.log_wet != nullptr);
-  // TF: strict lean kernel compiled FOR a contact-angle field (the moving-wettability scripts), nothing else at run time
-  const bool theta_field = TF || (OPTS && a.ct_field != nullptr);
+  const bool theta_field = OPTS && a.ct_field != nullptr;
   const bool aux = !LEAN && a.pressure != nullptr;
   const int pmode = LEAN ? PM : a.pc.pmode;
   const int slipv = OPTS ? a.sc.variant : SWALBE_SLIP_STANDARD;

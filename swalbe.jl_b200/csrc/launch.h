@@ -25,7 +25,6 @@ struct KernelKey {
   bool gz;    // gravity == 0: lean kernels with the (+-0)*h terms of the equilibrium folded away
   bool lazy;  // populations are not written by this launch (geometry only: lower HBM floor)
   bool opts;  // lean kernel that takes theta field / slip variant / inclination / logs at run time
-  bool tf;    // strict lean kernel compiled for a theta field (g == 0, standard slip, no inclination, no logs)
 };
 
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);

@@ -12,7 +12,6 @@ struct Variant {
   fused_fn lean[2][5][2];  // [thermal][pmode][g==0] tau == 1 only, pmode in PM_BROAD_93..PM_FAST_32 (index 0 unused)
   fused_fn opts[2][5];     // [thermal][pmode]       lean + theta field / slip variant / inclination / logs at run time
   fused_fn bulk[5][2];     // [pmode][g==0]          lean, non-thermal, rows prefetched with cp.async.bulk (TMA unit)
-  fused_fn tf[2][5][2];    // [thermal][pmode][bulk] strict lean compiled for a theta FIELD, g == 0 (bulk: non-thermal only)
 };
 
 extern const Variant g_variant_128, g_variant_160, g_variant_192, g_variant_224, g_variant_256;
@@ -25,18 +24,12 @@ extern const Variant g_variant_128, g_variant_160, g_variant_192, g_variant_224,
   k_fused_step<NT, MB1, true, false, PM_BROAD_93, true, GZ, false>, k_fused_step<NT, MB1, true, false, PM_BROAD_32, true, GZ, false>, \
       k_fused_step<NT, MB1, true, false, PM_FAST_93, true, GZ, false>, k_fused_step<NT, MB1, true, false, PM_FAST_32, true, GZ, false>
 
-#define SW_TF_ROW(NT, MB1, TH, BULK)                                                                           \
-  k_fused_step<NT, MB1, true, TH, PM_BROAD_93, BULK, true, false, true>, k_fused_step<NT, MB1, true, TH, PM_BROAD_32, BULK, true, false, true>, \
-      k_fused_step<NT, MB1, true, TH, PM_FAST_93, BULK, true, false, true>, k_fused_step<NT, MB1, true, TH, PM_FAST_32, BULK, true, false, true>
-
 #define SW_DEFINE_VARIANT(NT, MB1, MB0)                                                                       \
   namespace {                                                                                                 \
   const fused_fn lean_##NT[2][2][4] = {{{SW_LEAN_ROW(NT, MB1, false, false, false)}, {SW_LEAN_ROW(NT, MB1, false, true, false)}}, \
                                        {{SW_LEAN_ROW(NT, MB1, true, false, false)}, {SW_LEAN_ROW(NT, MB1, true, true, false)}}};  \
   const fused_fn opts_##NT[2][4] = {{SW_LEAN_ROW(NT, MB1, false, false, true)}, {SW_LEAN_ROW(NT, MB1, true, false, true)}}; \
   const fused_fn bulk_##NT[2][4] = {{SW_BULK_ROW(NT, MB1, false)}, {SW_BULK_ROW(NT, MB1, true)}};              \
-  const fused_fn tf_##NT[3][4] = {{SW_TF_ROW(NT, MB1, false, false)}, {SW_TF_ROW(NT, MB1, false, true)},       \
-                                  {SW_TF_ROW(NT, MB1, true, false)}};                                          \
   Variant make_##NT() {                                                                                       \
     Variant v = {};                                                                                           \
     v.nt = NT;                                                                                                \
@@ -51,9 +44,6 @@ extern const Variant g_variant_128, g_variant_160, g_variant_192, g_variant_224,
       for (int pm = 1; pm <= 4; ++pm) v.opts[th][pm] = opts_##NT[th][pm - 1];                                 \
     for (int gz = 0; gz < 2; ++gz)                                                                            \
       for (int pm = 1; pm <= 4; ++pm) v.bulk[pm][gz] = bulk_##NT[gz][pm - 1];                                 \
-    for (int pm = 1; pm <= 4; ++pm) {                                                                         \
-      v.tf[0][pm][0] = tf_##NT[0][pm - 1]; v.tf[0][pm][1] = tf_##NT[1][pm - 1]; v.tf[1][pm][0] = tf_##NT[2][pm - 1]; \
-    }                                                                                                         \
     return v;                                                                                                 \
   }                                                                                                           \
   }                                                                                                           \
