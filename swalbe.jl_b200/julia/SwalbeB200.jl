@@ -231,6 +231,23 @@ function Swalbe.time_loop(sys::SysConst, state::CuState, Δh::Vector; verbose = 
 end
 
 
+# time_loop(sys, state, f, measure): the callback slot (src/simulate.jl:69-96) for the two callbacks the reference's
+# drivers pass -- wetted! (run_dropletrelax; counted on the device every step) and inclination! (run_dropletforced; with
+# the keyword defaults of src/forcing.jl:363 the ramp 0.5 + 0.5 tanh((t - tstart)/tsmooth) is the constant 1)
+function Swalbe.time_loop(sys::SysConst, state::CuState, f::Function, measure::Vector; verbose = false)
+    Tmax = sys.param.Tmax
+    if f === Swalbe.wetted!
+        wet = CUDA.zeros(UInt64, Tmax)
+        fused_steps!(state, sys, Tmax; logs = CLogs(CuPtr{Float64}(0), CuPtr{Float64}(0), pointer(wet), 0.055))
+        append!(measure, Int.(Array(wet)))
+    elseif f === Swalbe.inclination!
+        fused_steps!(state, sys, Tmax; incl = (measure, 0.5 + 0.5 * tanh(1000.0)))
+    else
+        error("time_loop on CuState: only Swalbe.wetted! and Swalbe.inclination! callbacks are fused on the device")
+    end
+    return state, measure
+end
+
 # ---- on-device initial conditions and substrate motion (include/swalbe_b200.h, "initial conditions") ----------
 # Methods on CuArray heights: `Swalbe.singledroplet(state.height, r, θ, c)` fills the device array without the host
 # loop + upload of src/initialvalues.jl:203-224.  `j_begin` places a row slab in the global lattice (multi-GPU).
