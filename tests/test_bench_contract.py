@@ -43,3 +43,25 @@ def test_b200_arm_line():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     assert d["mass_drift_rel"] < 1e-12
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+
+
+def test_c4_workload_helpers():
+    """Host logic of the complete C4 workload: the step ranges between two substrate moves and the slab-wise pattern."""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.segments(10, 200) == [(10, 88, True), (98, 98, True), (196, 14, False)]
+    assert bench.segments(0, 98) == [(0, 98, True)] and bench.segments(97, 2) == [(97, 1, True), (98, 1, False)]
+    for s0, n in [(0, 1), (5, 400), (98, 98), (195, 3)]:
+        segs = bench.segments(s0, n)
+        assert sum(c for _, c, _ in segs) == n and segs[0][0] == s0
+        assert all(t0 + c == nxt[0] for (t0, c, _), nxt in zip(segs, segs[1:]))
+        assert all(move == ((t0 + c) % bench.TMOVE == 0) for t0, c, move in segs)
+    full = bench.theta_pattern(64, 48)
+    parts = [bench.theta_pattern(64, 12, j0, 48) for j0 in (0, 12, 24, 36)]
+    assert np.array_equal(np.concatenate(parts, axis=1), full)
+    assert abs(full.mean() - 1 / 9) < 1e-12 and full.max() <= 1 / 9 + 1 / 36 + 1e-15
+    h = bench.initial_height(32, workload="thermal_moving")
+    assert abs(h.max() - 1.1) < 0.01 and abs(h.mean() - 1.0) < 1e-12
