@@ -54,6 +54,20 @@ class SlabDecomposition:
         return [("send", up, (n - d, n)), ("send", down, (0, d)), ("recv", down, (-d, 0)), ("recv", up, (n, n + d))]
 
 
+def shift_padded_slab(padded: np.ndarray, sx: int, sy: int, depth: int = HALO_DEPTH) -> np.ndarray:
+    """Index logic of swalbe_dist_shift_theta on the host: `padded` is a slab (Lx, n + 2*depth) whose ghost rows are
+    current; returns the slab after the GLOBAL periodic shift field[i, j] <- field[i - sx, j - sy] with the owned rows
+    filled (rows that cross the slab edge come out of the ghost rows, so |sy| <= depth) and stale ghost rows, which the
+    caller exchanges again."""
+    if abs(sy) > depth:
+        raise ValueError(f"|sy| = {abs(sy)} exceeds the ghost depth {depth}")
+    Lx, rows = padded.shape
+    n = rows - 2 * depth
+    out = padded.copy()
+    out[:, depth:depth + n] = np.roll(padded, sx, axis=0)[:, depth - sy:depth - sy + n]
+    return out
+
+
 def nccl_unique_id() -> bytes:
     raw = (C.c_ubyte * _lib.NCCL_UNIQUE_ID_BYTES)()
     _lib.call("swalbe_dist_unique_id", raw)

@@ -72,6 +72,66 @@ def _worker(rank, world, port, Lx, Ly, nsteps, tau, out_dir):
     dist.destroy_process_group()
 
 
+def _shift_worker(rank, world, port, Lx, Ly, shifts, out_dir):
+    """move_substrate! across slabs (swalbe_dist_shift_theta): shift with the ghost rows, exchange, repeat"""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from swalbe_b200.dist import HALO_DEPTH, SlabDecomposition, shift_padded_slab, slab_of
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dec = SlabDecomposition(Ly, world)
+    j0, n = dec.rows(rank)
+    d = HALO_DEPTH
+    theta = np.asfortranarray(np.random.default_rng(7).random((Lx, Ly)))
+    pad = np.zeros((Lx, n + 2 * d))
+    pad[:, d:d + n] = slab_of(theta, dec, rank)
+
+    def exchange(arr):
+        reqs, recvs = [], []
+        for kind, peer, (a, b) in dec.messages(rank):
+            view = arr[:, a + d:b + d]
+            if kind == "send":
+                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(view)), peer))
+            else:
+                buf = torch.empty(view.shape, dtype=torch.float64)
+                reqs.append(dist.irecv(buf, peer))
+                recvs.append((view, buf))
+        for r in reqs:
+            r.wait()
+        for view, buf in recvs:
+            view[...] = buf.numpy()
+
+    exchange(pad)
+    for q, (sx, sy) in enumerate(shifts):
+        pad = shift_padded_slab(pad, sx, sy)
+        exchange(pad)
+        np.save(os.path.join(out_dir, f"t{q}_{rank}.npy"), pad[:, d:d + n])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_theta_shift_matches_global_circshift(tmp_path):
+    import torch.multiprocessing as mp
+
+    from oracle import oracle_np as onp
+    from swalbe_b200.dist import shift_padded_slab
+
+    Lx, Ly, world = 17, 16, 2
+    shifts = [(1, 1), (0, -3), (-5, 2), (Lx + 2, 0), (3, 3)]
+    mp.spawn(_shift_worker, args=(world, _free_port(), Lx, Ly, shifts, str(tmp_path)), nprocs=world, join=True)
+    want = np.asfortranarray(np.random.default_rng(7).random((Lx, Ly)))
+    for q, sh in enumerate(shifts):
+        want = onp.circshift(want, sh)
+        got = np.concatenate([np.load(tmp_path / f"t{q}_{r}.npy") for r in range(world)], axis=1)
+        assert np.array_equal(got, want), (q, sh)
+    with pytest.raises(ValueError):
+        shift_padded_slab(np.zeros((4, 10)), 0, 4)
+
+
 @pytest.mark.parametrize("tau", [1.0, 0.8])
 def test_two_rank_slabs_match_global_oracle(tmp_path, tau):
     import torch.multiprocessing as mp
