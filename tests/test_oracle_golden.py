@@ -163,6 +163,24 @@ def test_relaxing_droplet():  # test/simulate.jl:44-60
     assert abs(st.height.sum() - mass0) / mass0 < 1e-12  # mass conserved to round-off
 
 
+def test_patterned_droplet():  # test/simulate.jl:96-112 (run_dropletpatterned: θₛ = fill(1/9) as a FIELD)
+    p = onp.Params(Tmax=10000, delta=3.0)
+    st = onp.State(150, 150)
+    st.height[...] = onp.singledroplet(150, 150, 35, 1 / 6, (75, 75))
+    onp.equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, p.g)
+    ct = np.asfortranarray(np.full((150, 150), onp.cospi(1 / 9)))
+    oc.time_loop(st, p, cospi_theta=ct, threads=oc.max_threads())
+    _droplet_checks(st.height)
+    # a constant field must give exactly what the scalar gives (same arithmetic, site by site)
+    st2 = onp.State(150, 150)
+    st2.height[...] = onp.singledroplet(150, 150, 35, 1 / 6, (75, 75))
+    oc.time_loop(st2, onp.Params(Tmax=300, delta=3.0), threads=oc.max_threads())
+    st3 = onp.State(150, 150)
+    st3.height[...] = onp.singledroplet(150, 150, 35, 1 / 6, (75, 75))
+    oc.time_loop(st3, onp.Params(Tmax=300, delta=3.0), cospi_theta=ct, threads=oc.max_threads())
+    assert np.array_equal(st2.height, st3.height)
+
+
 def test_sliding_droplet():  # test/simulate.jl:147-155 (inclination! in the callback slot, factor(t=1000)=1)
     import math
 
