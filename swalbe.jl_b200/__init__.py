@@ -407,9 +407,23 @@ def field_stats(f: Field, thresh=0.055):
     return mn, mx, sm, int(cnt)
 
 
-def wetted(area_size: list, st: CuState, hthresh=0.055):
-    """wetted!(area_size, state; hthresh)   src/measures.jl:13-17"""
-    area_size.append(field_stats(st.height, hthresh)[3])
+def wetted(area_size, *args, hthresh=0.055):
+    """wetted!(area_size, state; hthresh)                 src/measures.jl:13-17  (push! the wetted-site count)
+    wetted!(area_size, maxheight, height, t; hthresh)   src/measures.jl:6-11   (slot t, Julia's 1-based step index)
+
+    Both reductions run on the device (swalbe_field_stats); only the two numbers cross the bus."""
+    if len(args) == 1 or (len(args) == 2 and not isinstance(args[1], Field) and isinstance(args[0], CuState)):
+        st = args[0]
+        if len(args) == 2:  # positional hthresh, as the first version of this mirror took it
+            hthresh = args[1]
+        area_size.append(field_stats(st.height, hthresh)[3])
+        return
+    if len(args) != 3:
+        raise TypeError("MethodError: no method matching wetted! with these arguments")
+    maxheight, height, t = args
+    _, mx, _, cnt = field_stats(height, hthresh)
+    area_size[t - 1] = cnt
+    maxheight[t - 1] = mx
 
 
 def snapshot(snap: np.ndarray, field: Field, t: int, dumping=1000):

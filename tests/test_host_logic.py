@@ -101,3 +101,16 @@ def test_cospi_matches_reference_points():
     assert sw.cospi(0) == 1.0 and sw.cospi(0.5) == 0.0 and sw.cospi(1) == -1.0 and sw.cospi(1.5) == 0.0
     assert sw.cospi(-1 / 9) == sw.cospi(1 / 9) and sw.cospi(2.25) == sw.cospi(0.25) == sw.cospi(-1.75)
     assert abs(sw.cospi(1 / 6) - math.sqrt(3) / 2) < 2e-16
+
+
+def test_wetted_call_shapes(fake):  # src/measures.jl:6-17; known answers of test/measures.jl:2-24 need the device
+    area = []
+    sw.wetted(area, _State())
+    sw.wetted(area, _State(), hthresh=0.1)
+    assert area == [3, 3]
+    area_size, maxheight = [1.0] * 5, [0.0] * 5
+    sw.wetted(area_size, maxheight, sw.Field.__new__(sw.Field), 2)
+    assert area_size == [1.0, 3, 1.0, 1.0, 1.0] and maxheight == [0.0, 1.0, 0.0, 0.0, 0.0]
+    with pytest.raises(TypeError):
+        sw.wetted(area_size, maxheight, 2)
+
