@@ -110,3 +110,82 @@ def test_header_is_plain_c99(tmp_path):
                    "  return (int)sizeof(swalbe_state) - 17 * (int)sizeof(void *) + SWALBE_LOOP_SKIP_AUX - 2; }\n")
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
                            "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def _classify_c(param: str) -> str:
+    p = param.strip()
+    if "*" in p or "[" in p:
+        return "ptr"
+    if "double" in p:
+        return "f64"
+    if "unsigned long long" in p:
+        return "u64"
+    if "size_t" in p:
+        return "u64"  # (LP64: size_t and unsigned long long are both 8-byte unsigned; ctypes aliases them)
+    if re.search(r"\bint\b", p):
+        return "i32"
+    raise AssertionError(f"unclassified C parameter: {param!r}")
+
+
+def _header_prototypes():
+    src = open(os.path.join(ROOT, "include", "swalbe_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for name, params in re.findall(r"\b(swalbe_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        params = params.strip()
+        protos[name] = [] if params in ("", "void") else [_classify_c(p) for p in params.split(",")]
+    return protos
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Argument by argument: every ctypes argtypes list agrees with the C prototype it binds."""
+    from swalbe_b200 import _lib
+
+    def classify(t):
+        if t is C.c_double:
+            return "f64"
+        if t is C.c_int:
+            return "i32"
+        if t is C.c_ulonglong:
+            return "u64"
+        if t is C.c_void_p or t is C.c_char_p or hasattr(t, "contents"):
+            return "ptr"
+        raise AssertionError(f"unclassified ctypes type {t}")
+
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert [classify(t) for t in argtypes] == protos[name], name
+
+
+def test_julia_glue_binds_existing_symbols_with_matching_types():
+    """The Julia glue cannot run here (no Julia in the image), but every ccall in it must name a symbol the header
+    declares, with an argument-type tuple that matches the C prototype position by position, and its blocks must
+    balance."""
+    src = open(os.path.join(ROOT, "swalbe.jl_b200", "julia", "SwalbeB200.jl"), encoding="utf-8").read()
+    protos = _header_prototypes()
+    jl = {"Cdouble": "f64", "Cint": "i32", "Culonglong": "u64", "Csize_t": "u64"}
+
+    def classify(t):
+        t = t.strip()
+        if t.startswith(("CuPtr{", "Ptr{")) or t == "Cstring":
+            return "ptr"
+        return jl[t]
+
+    calls = re.findall(r"ccall\(\(:(swalbe_\w+), lib\),\s*(\w+),\s*\(([^)]*)\)", src, flags=re.S)
+    assert len(calls) >= 20
+    for name, ret, types in calls:
+        assert name in protos, f"ccall to undeclared symbol {name}"
+        got = [classify(t) for t in types.split(",") if t.strip()]
+        assert got == protos[name], f"{name}: Julia {got} vs C {protos[name]}"
+        assert ret in ("Cint", "Cstring", "Culonglong"), (name, ret)
+    bound = {c[0] for c in calls}
+    for must in ("swalbe_equilibrium_d2q9", "swalbe_bgk_stream_d2q9", "swalbe_moments_d2q9", "swalbe_filmpressure",
+                 "swalbe_hgradp", "swalbe_slippage", "swalbe_time_loop", "swalbe_plan_create", "swalbe_last_error"):
+        assert must in bound, must
+    # block balance (function/struct/if/while/do/module ... end), comments and strings stripped
+    body = "\n".join(re.sub(r"#.*$", "", re.sub(r'"(?:\\.|[^"\\])*"', '""', ln)) for ln in
+                     re.sub(r'"""(?:.|\n)*?"""', '""', src).splitlines())
+    openers = re.findall(r"(?<![\w!.])(?:function|struct|if|for|while|do|module|begin|let|try|macro|quote)(?![\w!])", body)
+    ends = re.findall(r"(?<![\w!.:\[])end(?![\w!])", body)
+    assert len(openers) == len(ends), (len(openers), len(ends))
