@@ -189,3 +189,46 @@ def test_julia_glue_binds_existing_symbols_with_matching_types():
     openers = re.findall(r"(?<![\w!.])(?:function|struct|if|for|while|do|module|begin|let|try|macro|quote)(?![\w!])", body)
     ends = re.findall(r"(?<![\w!.:\[])end(?![\w!])", body)
     assert len(openers) == len(ends), (len(openers), len(ends))
+
+
+def _header_struct_fields(name):
+    """[(field, kind)] of `typedef struct <name> {...}` in declaration order (kind: ptr / f64 / i32 / u64)."""
+    src = open(os.path.join(ROOT, "include", "swalbe_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"((?:const\s+)?(?:unsigned long long|double|int))\s+(.*)", decl)
+        base, names = m.group(1), m.group(2)
+        for nm in names.split(","):
+            nm = nm.strip()
+            kind = "ptr" if nm.startswith("*") else {"double": "f64", "int": "i32", "unsigned long long": "u64"}[base.replace("const ", "")]
+            out.append((nm.lstrip("*").strip(), kind))
+    return out
+
+
+def test_struct_fields_match_in_ctypes_and_julia():
+    """Field by field, in order: the C structs, their ctypes mirrors and the Julia structs of the glue."""
+    from swalbe_b200 import _lib
+
+    def ckind(t):
+        return {C.c_double: "f64", C.c_int: "i32", C.c_ulonglong: "u64", C.c_void_p: "ptr"}[t]
+
+    jsrc = open(os.path.join(ROOT, "swalbe.jl_b200", "julia", "SwalbeB200.jl"), encoding="utf-8").read()
+
+    def julia_fields(name):
+        body = re.search(r"struct %s\b.*?\n(.*?)\nend" % name, jsrc, flags=re.S).group(1)
+        body = re.sub(r"#.*", "", body)
+        out = []
+        for f, t in re.findall(r"(\w+)::([\w{}]+)", body):
+            out.append((f, "ptr" if t.startswith(("CuPtr{", "Ptr{")) else {"Cdouble": "f64", "Cint": "i32", "Culonglong": "u64"}[t]))
+        return out
+
+    for cname, cty, jname in (("swalbe_state", _lib.CState, "CState"), ("swalbe_params", _lib.CParams, "CParams"),
+                              ("swalbe_loop_logs", _lib.CLogs, "CLogs")):
+        want = _header_struct_fields(cname)
+        assert [(n, ckind(t)) for n, t in cty._fields_] == want, cname
+        assert julia_fields(jname) == want, jname
