@@ -40,3 +40,20 @@ def test_reference_citations_resolve():
                 bad.append(f"{os.path.relpath(f, ROOT)}: {m.group(0)} (file has {lengths[rel]} lines)")
     assert n > 100, n  # the citations are there at all
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_julia_glue_extends_functions_the_reference_defines():
+    """Every `Swalbe.f` the Julia glue adds methods to (or the INTEGRATION examples call) is a function of the reference."""
+    src = open(os.path.join(ROOT, "swalbe.jl_b200", "julia", "SwalbeB200.jl"), encoding="utf-8").read()
+    names = set(re.findall(r"(?:function\s+|^)Swalbe\.([\w!∇²]+)\s*\(", src, flags=re.M))
+    assert len(names) >= 12, names
+    ref_src = "\n".join(open(f, encoding="utf-8").read() for f in glob.glob(os.path.join(REF, "src", "*.jl")))
+    missing = [n for n in sorted(names) if not re.search(r"(?:function\s+|^)%s\s*\(" % re.escape(n), ref_src, flags=re.M)]
+    assert not missing, missing
+    # the state types and fields the glue touches exist upstream
+    for field in ("fout", "ftemp", "feq", "height", "velx", "vely", "vsq", "pressure", "dgrad", "Fx", "Fy", "slipx", "slipy",
+                  "h∇px", "h∇py", "kbtx", "kbty"):
+        assert re.search(r"\b%s\s*::" % re.escape(field), ref_src), field
+    for ty in ("CuState", "CuState_thermal", "SysConst"):
+        assert re.search(r"struct\s+%s\b" % ty, ref_src), ty
