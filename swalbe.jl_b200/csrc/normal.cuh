@@ -12,9 +12,11 @@
 #define SW_HD __host__ __device__ __forceinline__
 #else
 #define SW_HD inline
+#ifndef __VECTOR_TYPES_H__  // (plain C++ without the CUDA headers: tools/normal_host_test.cpp)
 struct double2 {
   double x, y;
 };
+#endif
 #endif
 
 namespace swalbe {
