@@ -94,6 +94,7 @@ __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
   }
 }
 
+#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these eight helpers)
 // 8-byte asynchronous global -> shared copy (LDGSTS); completion is tracked per thread by commit/wait groups,
 // not by the register scoreboard.
 __device__ __forceinline__ void cp_async8(double *smem_dst, const void *gsrc) {
@@ -135,6 +136,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     if (spin > (1u << 24)) __trap();  // a lost copy must fail loudly instead of hanging the device
   }
 }
+#endif  // SW_HOST_EMULATION
 
 // A row cursor: BYTE offset of (row, own column) inside a plane, advanced one row per iteration with the periodic
 // wrap folded in (no integer division and no index->byte scaling inside the loop).
@@ -174,7 +176,11 @@ constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT +
 
 template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
+#ifdef SW_HOST_EMULATION
+  double *const smem = emul_dynamic_smem();
+#else
   extern __shared__ __align__(16) double smem[];
+#endif
   constexpr bool LEAN = PM >= 0;
   constexpr int LW = NT + 2 * FUSED_PAD;
   constexpr int D = FUSED_D;
@@ -196,7 +202,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   double *const su = s2 + 2 * R2S;                 // own column, u ring slot 0, line 0
 
   // Programmatic dependent launch: let the next step's grid start filling SMs as ours drains ...
+#ifndef SW_HOST_EMULATION
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   if (tid < 2 * FUSED_PAD) {  // the pad cells of every line are never written by the pipeline; keep them finite
     const int e = tid < FUSED_PAD ? tid : NT + tid;
     for (int q = 0; q < FUSED_LINES; ++q) smem[q * LW + e] = 0.0;
@@ -434,7 +442,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   };
 
   // ... and do not touch global memory before the previous step's grid has completed and flushed its writes.
+#ifndef SW_HOST_EMULATION
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 
   // pipeline fill (predicated), steady state (predicate-free), drain (predicated)
   const int t_end = R + 8;

@@ -1,0 +1,171 @@
+// Host SIMT emulation of the step KERNELS themselves (swalbe.jl_b200/csrc/fused.cuh, tile.cuh) for
+// tests/test_simt_emulation.py -- test infrastructure only, nothing in the product links this.
+//   g++ -O1 -ffp-contract=off -DSW_HOST_EMULATION -w -I/usr/local/cuda/include -shared -fPIC -pthread tests/simt_emulation.cpp
+// Every CUDA thread of a CTA runs as one OS thread, __syncthreads() is a pthread barrier, __shared__ is static storage,
+// CTAs run one after the other; cp.async / cp.async.bulk / mbarrier become immediate copies and no-ops (legal: the
+// kernels never read a ring slot in the iteration that prefetches into it).  What is exercised on the CPU is therefore
+// the kernels' own index logic -- strips, halo columns, row cursors with periodic wrap or ghost rows, the software
+// pipeline and its ring slots, fill/steady/drain instantiations, the tile phases -- against the oracle, bit for bit.
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+// ---- the CUDA execution model, on the host --------------------------------------------------------------------------
+struct Emu3 {
+  unsigned x = 0, y = 0, z = 0;
+};
+static thread_local Emu3 threadIdx, blockIdx;
+static pthread_barrier_t g_cta_barrier;
+static double *g_dynamic_smem = nullptr;
+static inline void __syncthreads() { pthread_barrier_wait(&g_cta_barrier); }
+static inline double *emul_dynamic_smem() { return g_dynamic_smem; }
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __noinline__ __attribute__((noinline))
+
+// ---- intrinsics -----------------------------------------------------------------------------------------------------
+static inline int __double2hiint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+  const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+  double d; memcpy(&d, &u, 8); return d;
+}
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline void sincospi(double a, double *s, double *c) { *s = sin(a * 3.141592653589793); *c = cos(a * 3.141592653589793); }
+static inline long long __double_as_longlong(double x) { long long u; memcpy(&u, &x, 8); return u; }
+static inline double __longlong_as_double(long long u) { double x; memcpy(&x, &u, 8); return x; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }  // (per-step logs are not emulated)
+static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) {
+  return __sync_val_compare_and_swap(p, cmp, v);
+}
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
+static inline void __trap() { abort(); }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+
+// ---- the eight asynchronous-copy helpers of fused.cuh, as immediate copies -----------------------------------------
+static inline void cp_async8(double *smem_dst, const void *gsrc) { *smem_dst = *(const double *)gsrc; }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+static inline void mbar_init(unsigned long long *, unsigned) {}
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
+static inline void bulk_g2s(double *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *) { memcpy(smem_dst, gsrc, bytes); }
+static inline void mbar_wait(unsigned long long *, unsigned) {}
+
+#include "../swalbe.jl_b200/csrc/tile.cuh"  // (includes fused.cuh and common.cuh)
+
+using namespace swalbe;
+namespace swalbe {
+int set_error(int code, const char *, ...) { return code; }
+void count_launch(unsigned) {}
+}  // namespace swalbe
+
+typedef void (*kernel_fn)(const FusedArgs);
+
+static void launch(kernel_fn k, unsigned gx, unsigned gy, unsigned nthreads, size_t dyn_doubles, const FusedArgs &a) {
+  std::vector<double> smem(dyn_doubles + 2, 0.0);
+  g_dynamic_smem = (double *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+  for (unsigned by = 0; by < gy; ++by)
+    for (unsigned bx = 0; bx < gx; ++bx) {
+      pthread_barrier_init(&g_cta_barrier, nullptr, nthreads);
+      std::vector<std::thread> cta;
+      cta.reserve(nthreads);
+      for (unsigned t = 0; t < nthreads; ++t)
+        cta.emplace_back([=]() {
+          threadIdx.x = t; blockIdx.x = bx; blockIdx.y = by;
+          k(a);
+        });
+      for (auto &th : cta) th.join();
+      pthread_barrier_destroy(&g_cta_barrier);
+    }
+}
+
+constexpr int ENT = 128;  // CTA width of the emulated marching kernels
+
+template <bool GZ, bool OPTS, bool BULK>
+static kernel_fn lean_kernel(int pm) {
+  switch (pm) {
+    case PM_BROAD_93: return k_fused_step<ENT, 5, true, false, PM_BROAD_93, BULK, GZ, OPTS>;
+    case PM_BROAD_32: return k_fused_step<ENT, 5, true, false, PM_BROAD_32, BULK, GZ, OPTS>;
+    case PM_FAST_93: return k_fused_step<ENT, 5, true, false, PM_FAST_93, BULK, GZ, OPTS>;
+    case PM_FAST_32: return k_fused_step<ENT, 5, true, false, PM_FAST_32, BULK, GZ, OPTS>;
+    default: return nullptr;
+  }
+}
+template <bool GZ>
+static kernel_fn tile_kernel(int pm) {
+  switch (pm) {
+    case PM_BROAD_93: return k_tile_step<PM_BROAD_93, GZ>;
+    case PM_BROAD_32: return k_tile_step<PM_BROAD_32, GZ>;
+    case PM_FAST_93: return k_tile_step<PM_FAST_93, GZ>;
+    case PM_FAST_32: return k_tile_step<PM_FAST_32, GZ>;
+    default: return nullptr;
+  }
+}
+
+extern "C" {
+
+struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop put into FusedArgs
+  int flavour;     // 0 strict lean, 1 OPTS lean, 2 FULL, 3 strict lean with bulk row prefetch, 4 tile kernel
+  int Lx, Ly, jbeg, jend, W, rows_per_cta, wrap_y;
+  double tau, mu, delta, gamma, hmin, hcrit, g, cospi_theta;
+  int n, m, pressure_variant, slip_variant, use_incl;
+  double incl_ax, incl_ay, incl_factor;
+  const double *h_in, *ux_in, *uy_in, *f_in, *ct_field;
+  double *h_out, *ux_out, *uy_out, *f_out, *f_out2;
+  double *pressure, *hgx, *hgy, *slipx, *slipy, *Fx, *Fy, *feq, *vsq;
+  size_t fstride;
+};
+
+int simt_step(const SimtStep *s) {
+  FusedArgs a = {};
+  if (int e = resolve_pmode(s->pressure_variant, s->n, s->m, &a.pc.pmode)) return e;
+  a.pc.gamma = s->gamma; a.pc.kappa = host_kappa(s->cospi_theta, s->n, s->m, s->hmin);
+  a.pc.nm1 = (double)(s->n - 1); a.pc.mm1 = (double)(s->m - 1); a.pc.kden = (double)(s->n - s->m) * s->hmin;
+  a.pc.hmin = s->hmin; a.pc.hcrit = s->hcrit; a.pc.n = s->n; a.pc.m = s->m;
+  a.sc = make_slip(s->delta, s->mu, s->hcrit, s->slip_variant);
+  a.ec = make_eq(s->g);
+  volatile double it = 1.0 / s->tau;
+  volatile double om = 1.0 - it;
+  a.invtau = it; a.omega = om;
+  a.use_incl = s->use_incl; a.incl_ax = s->incl_ax; a.incl_ay = s->incl_ay; a.incl_factor = s->incl_factor;
+  a.Lx = s->Lx; a.Ly = s->Ly; a.jbeg = s->jbeg; a.jend = s->jend; a.W = s->W; a.rows_per_cta = s->rows_per_cta;
+  a.wrap_y = s->wrap_y; a.jglobal0 = 0; a.Ly_global = s->Ly;
+  a.fstride_in = a.fstride_out = a.fstride_out2 = s->fstride;
+  a.h_in = s->h_in; a.ux_in = s->ux_in; a.uy_in = s->uy_in; a.f_in = s->f_in; a.ct_field = s->ct_field;
+  a.h_out = s->h_out; a.ux_out = s->ux_out; a.uy_out = s->uy_out; a.f_out = s->f_out; a.f_out2 = s->f_out2;
+  a.pressure = s->pressure; a.hgx = s->hgx; a.hgy = s->hgy; a.slipx = s->slipx; a.slipy = s->slipy;
+  a.Fx = s->Fx; a.Fy = s->Fy; a.feq = s->feq; a.vsq = s->vsq;
+  const bool gz = s->g == 0.0, tau1 = s->tau == 1.0;
+  const int pm = a.pc.pmode;
+  kernel_fn k = nullptr;
+  if (s->flavour == 4) {
+    k = gz ? tile_kernel<true>(pm) : tile_kernel<false>(pm);
+    if (!k) return -1;
+    launch(k, (s->Lx + 31) / 32, (s->Ly + 7) / 8, 256, 0, a);
+    return 0;
+  }
+  if (s->flavour == 0) k = gz ? lean_kernel<true, false, false>(pm) : lean_kernel<false, false, false>(pm);
+  else if (s->flavour == 1) k = lean_kernel<false, true, false>(pm);
+  else if (s->flavour == 3) k = gz ? lean_kernel<true, false, true>(pm) : lean_kernel<false, false, true>(pm);
+  else if (s->flavour == 2) k = tau1 ? (kernel_fn)k_fused_step<ENT, 5, true, false, -1, false, false, true>
+                                     : (kernel_fn)k_fused_step<ENT, 3, false, false, -1, false, false, true>;
+  if (!k) return -1;
+  if (s->W < 1 || s->W > ENT - 8 || s->rows_per_cta < 1) return -2;
+  const int nrows = s->jend - s->jbeg;
+  launch(k, (s->Lx + s->W - 1) / s->W, (nrows + s->rows_per_cta - 1) / s->rows_per_cta, ENT, fused_smem_doubles(ENT), a);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+"""The step KERNELS themselves (csrc/fused.cuh marching kernel in its strict-lean, run-time-option, full and bulk-prefetch
+flavours; csrc/tile.cuh) executed on the CPU by a small SIMT emulation (tests/simt_emulation.cpp: one OS thread per
+CUDA thread, pthread barrier for __syncthreads, static storage for __shared__) and compared with the oracle bit for bit.
+This exercises, without a GPU, the kernels' index logic: strips and halo columns, row cursors with the periodic wrap,
+the software pipeline and its ring slots, the fill / steady / drain instantiations, chunk seams, the tile phases."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_c as oc
+from oracle import oracle_np as onp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+_d, _i, _p = C.c_double, C.c_int, C.c_void_p
+STRICT, OPTS, FULL, BULK, TILE = range(5)
+
+
+class SimtStep(C.Structure):
+    _fields_ = ([("flavour", _i)] + [(n, _i) for n in ("Lx", "Ly", "jbeg", "jend", "W", "rows_per_cta", "wrap_y")] +
+                [(n, _d) for n in ("tau", "mu", "delta", "gamma", "hmin", "hcrit", "g", "cospi_theta")] +
+                [(n, _i) for n in ("n", "m", "pressure_variant", "slip_variant", "use_incl")] +
+                [(n, _d) for n in ("incl_ax", "incl_ay", "incl_factor")] +
+                [(n, _p) for n in ("h_in", "ux_in", "uy_in", "f_in", "ct_field", "h_out", "ux_out", "uy_out", "f_out", "f_out2",
+                                   "pressure", "hgx", "hgy", "slipx", "slipy", "Fx", "Fy", "feq", "vsq")] +
+                [("fstride", C.c_size_t)])
+
+
+@pytest.fixture(scope="module")
+def simt(tmp_path_factory):
+    if not os.path.isfile(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not installed")
+    so = str(tmp_path_factory.mktemp("simt") / "libsimt.so")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-DSW_HOST_EMULATION", "-w", "-I", CUDA_INC, "-shared", "-fPIC",
+                    "-pthread", os.path.join(ROOT, "tests", "simt_emulation.cpp"), "-o", so, "-lm"], check=True)
+    lib = C.CDLL(so)
+    lib.simt_step.argtypes = [C.POINTER(SimtStep)]
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _state(Lx, Ly, seed, pops=False):
+    rng = np.random.default_rng(seed)
+    st = onp.State(Lx, Ly)
+    st.height[...] = np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06
+    st.velx[...] = 0.01 * rng.standard_normal((Lx, Ly))
+    st.vely[...] = 0.01 * rng.standard_normal((Lx, Ly))
+    if pops:
+        st.ftemp[...] = 0.1 + 0.01 * rng.random((Lx, Ly, 9))
+    return st
+
+
+def _run(simt, st, p, nsteps, flavour, W, rows, ct=None, pvariant=0, slip_variant=0, incl=None, last_full=False):
+    """nsteps launches with the moment ping-pong of swalbe_time_loop; the last one optionally through the FULL kernel,
+    which also materialises pressure / h∇p / slip / F / feq / vsq and writes ftemp."""
+    Lx, Ly = st.Lx, st.Ly
+    N = Lx * Ly
+    cur = [st.height, st.velx, st.vely]
+    alt = [np.zeros_like(a) for a in cur]
+    fsrc, fdst = st.ftemp, st.fout
+    for s in range(nsteps):
+        last = s == nsteps - 1
+        q = SimtStep()
+        q.flavour = FULL if (last and last_full) else flavour
+        q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = Lx, Ly, 0, Ly, W, rows, 1
+        q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+        q.cospi_theta, q.n, q.m, q.pressure_variant, q.slip_variant = onp.cospi(p.theta), p.n, p.m, pvariant, slip_variant
+        if incl is not None:
+            q.use_incl, q.incl_ax, q.incl_ay, q.incl_factor = 1, incl[0][0], incl[0][1], incl[1]
+        q.h_in, q.ux_in, q.uy_in = (_ptr(a) for a in cur)
+        q.h_out, q.ux_out, q.uy_out = (_ptr(a) for a in alt)
+        q.ct_field, q.fstride = _ptr(ct), N
+        if p.tau == 1.0:
+            q.f_in, q.f_out = None, _ptr(st.fout)
+            q.f_out2 = _ptr(st.ftemp) if (last and last_full) else None
+        else:
+            q.f_in, q.f_out = _ptr(fsrc), _ptr(fdst)
+        if last and last_full:
+            for name, fld in (("pressure", st.pressure), ("hgx", st.hgradpx), ("hgy", st.hgradpy), ("slipx", st.slipx),
+                              ("slipy", st.slipy), ("Fx", st.Fx), ("Fy", st.Fy), ("feq", st.feq), ("vsq", st.vsq)):
+                setattr(q, name, _ptr(fld))
+        assert simt.simt_step(C.byref(q)) == 0
+        cur, alt = alt, cur
+        fsrc, fdst = fdst, fsrc
+    for dst, src in zip((st.height, st.velx, st.vely), cur):
+        if dst is not src:
+            dst[...] = src
+    if p.tau != 1.0 and fsrc is not st.fout:  # newest populations are in the array written last
+        st.fout[...] = fsrc
+
+
+FIELDS = ("height", "velx", "vely", "fout")
+AUX = ("pressure", "hgradpx", "hgradpy", "slipx", "slipy", "Fx", "Fy", "feq", "vsq", "ftemp")
+
+
+def _same(a, b, names):
+    for name in names:
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+
+
+@pytest.mark.parametrize("Lx,Ly,W,rows", [(25, 26, 120, 26), (25, 26, 9, 5), (150, 40, 120, 13), (130, 9, 64, 64), (5, 5, 4, 2),
+                                          (3, 30, 120, 7)])
+def test_marching_kernel_strict_lean_on_cpu(simt, Lx, Ly, W, rows):
+    for kw in (dict(g=-0.001, gamma=0.0005), dict(n=3, m=2, hmin=0.07)):  # GZ = false / true instantiations
+        p = onp.Params(**kw)
+        a, b = _state(Lx, Ly, 7), _state(Lx, Ly, 7)
+        _run(simt, a, p, 3, STRICT, W, rows)
+        oc.time_loop(b, p, nsteps=3)
+        _same(a, b, FIELDS)
+
+
+def test_marching_kernel_full_flavour_materialises_every_field(simt):
+    for kw, pops in ((dict(g=-0.001), False), (dict(tau=0.8, n=3, m=2, hmin=0.07), True), (dict(n=4, m=2), False)):
+        p = onp.Params(**kw)
+        a, b = _state(70, 23, 5, pops), _state(70, 23, 5, pops)
+        _run(simt, a, p, 3, FULL if (p.tau != 1.0 or kw.get("n") == 4) else STRICT, 62, 8, last_full=True)
+        oc.time_loop(b, p, nsteps=3)
+        _same(a, b, FIELDS + (AUX if p.tau == 1.0 else AUX[:-1]))
+
+
+def test_marching_kernel_runtime_options_on_cpu(simt):
+    """OPTS flavour: contact-angle field, slip variants, inclination, array-form pressure"""
+    Lx, Ly = 40, 31
+    rng = np.random.default_rng(3)
+    ct = np.asfortranarray(np.cos(np.pi * (1 / 9 + rng.random((Lx, Ly)) / 36)))
+    cases = [(dict(), 0, 0, ct, None), (dict(n=3, m=2, hmin=0.07), 1, 2, None, None),
+             (dict(), 1, 1, ct, ([1e-4, -2e-4], 0.75)), (dict(g=-0.002), 0, 0, None, ([3e-4, 0.0], 1.0))]
+    for kw, pv, sv, field, incl in cases:
+        p = onp.Params(**kw)
+        a, b = _state(Lx, Ly, 11), _state(Lx, Ly, 11)
+        _run(simt, a, p, 3, OPTS, 36, 11, ct=field, pvariant=pv, slip_variant=sv, incl=incl)
+        oc.time_loop(b, p, nsteps=3, cospi_theta=field, pvariant="fast" if pv else "power_broad", slip_variant=sv, incl=incl)
+        _same(a, b, FIELDS)
+
+
+def test_marching_kernel_bulk_prefetch_flavour_on_cpu(simt):
+    """cp.async.bulk row segments (thread 0 copies whole rows, split where a strip crosses the periodic x boundary)"""
+    p = onp.Params(n=3, m=2, hmin=0.07)
+    for Lx, Ly, W, rows in ((128, 12, 120, 12), (200, 10, 100, 4)):
+        a, b = _state(Lx, Ly, 2), _state(Lx, Ly, 2)
+        _run(simt, a, p, 2, BULK, W, rows)
+        oc.time_loop(b, p, nsteps=2)
+        _same(a, b, FIELDS)
+
+
+@pytest.mark.parametrize("Lx,Ly", [(5, 5), (33, 9), (70, 20), (1, 3), (32, 8), (64, 16)])
+def test_tile_kernel_on_cpu(simt, Lx, Ly):
+    for kw in (dict(g=-0.001), dict(n=3, m=2, hmin=0.07)):
+        p = onp.Params(**kw)
+        a, b = _state(Lx, Ly, 13), _state(Lx, Ly, 13)
+        _run(simt, a, p, 3, TILE, 0, 0)
+        oc.time_loop(b, p, nsteps=3)
+        _same(a, b, FIELDS)
