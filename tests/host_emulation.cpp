@@ -39,7 +39,8 @@ extern "C" {
 // one time step (tau == 1 or general tau) over the whole periodic lattice, composed like csrc/tile.cu
 int emul_step(double *h, double *ux, double *uy, double *fout, const double *ftemp, double *pressure, int Lx, int Ly,
               double tau, double mu, double delta, double gamma, double hmin, double hcrit, double g, int n, int m,
-              double cospi_theta, const double *ct_field, int pressure_variant, int slip_variant, double *scratch /* 10*N */) {
+              double cospi_theta, const double *ct_field, int pressure_variant, int slip_variant, double *scratch /* 10*N */,
+              double kbt, unsigned long long seed, unsigned long long step) {
   const size_t N = (size_t)Lx * Ly;
   PressureConsts pc;
   if (int e = resolve_pmode(pressure_variant, n, m, &pc.pmode)) return e;
@@ -51,6 +52,10 @@ int emul_step(double *h, double *ux, double *uy, double *fout, const double *fte
   volatile double it = 1.0 / tau;
   volatile double om = 1.0 - it;
   double *p = scratch, *fs = scratch + N;  // pressure, 9 post-collision planes
+  static NormalTables T;
+  normal_tables_fill(T, 0, 1);
+  const ThermalConsts tc = make_thermal(kbt, mu, delta);
+  const PhiloxKey K = make_philox_key(seed);
   for (int j = 0; j < Ly; ++j)
     for (int i = 0; i < Lx; ++i) {
       const double hc = h[at(i, j, Lx, Ly)];
@@ -71,7 +76,13 @@ int emul_step(double *h, double *ux, double *uy, double *fout, const double *fte
       const double hgx = hc * gx, hgy = hc * gy;
       double sx, sy;
       slip_terms(hc, ux[c], uy[c], sc, slip_variant, sx, sy);
-      const double Fx = (-hgx) - sx, Fy = (-hgy) - sy;
+      double Fx = (-hgx) - sx, Fy = (-hgy) - sy;
+      if (kbt > 0.0) {  // thermal!: in-kernel noise keyed on (seed, step, global cell)
+        double kx, ky;
+        thermal_pair(hc, tc, K, step, (unsigned long long)c, T, kx, ky);
+        Fx = Fx - kx;
+        Fy = Fy - ky;
+      }
       double fe[9], vsq, f[9];
       equilibrium_site<false>(hc, ux[c], uy[c], ec, fe, vsq);
       if (tau == 1.0) collide_site_tau1(fe, Fx, Fy, f);

@@ -104,6 +104,16 @@ static kernel_fn lean_kernel(int pm) {
   }
 }
 template <bool GZ>
+static kernel_fn thermal_kernel(int pm) {
+  switch (pm) {
+    case PM_BROAD_93: return k_fused_step<ENT, 5, true, true, PM_BROAD_93, false, GZ, false>;
+    case PM_BROAD_32: return k_fused_step<ENT, 5, true, true, PM_BROAD_32, false, GZ, false>;
+    case PM_FAST_93: return k_fused_step<ENT, 5, true, true, PM_FAST_93, false, GZ, false>;
+    case PM_FAST_32: return k_fused_step<ENT, 5, true, true, PM_FAST_32, false, GZ, false>;
+    default: return nullptr;
+  }
+}
+template <bool GZ>
 static kernel_fn tile_kernel(int pm) {
   switch (pm) {
     case PM_BROAD_93: return k_tile_step<PM_BROAD_93, GZ>;
@@ -117,7 +127,8 @@ static kernel_fn tile_kernel(int pm) {
 extern "C" {
 
 struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop put into FusedArgs
-  int flavour;     // 0 strict lean, 1 OPTS lean, 2 FULL, 3 strict lean with bulk row prefetch, 4 tile kernel
+  int flavour;     // 0 strict lean, 1 OPTS lean, 2 FULL, 3 strict lean with bulk row prefetch, 4 tile kernel,
+                   // 5 strict lean with in-kernel thermal noise
   int Lx, Ly, jbeg, jend, W, rows_per_cta, wrap_y;
   double tau, mu, delta, gamma, hmin, hcrit, g, cospi_theta;
   int n, m, pressure_variant, slip_variant, use_incl;
@@ -126,6 +137,9 @@ struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop 
   double *h_out, *ux_out, *uy_out, *f_out, *f_out2;
   double *pressure, *hgx, *hgy, *slipx, *slipy, *Fx, *Fy, *feq, *vsq;
   size_t fstride;
+  double kbt;                      // thermal flavour
+  unsigned long long seed, step;
+  long long jglobal0, Ly_global;   // slab runs: global index of local row 0, global extent (noise counter)
 };
 
 int simt_step(const SimtStep *s) {
@@ -141,7 +155,8 @@ int simt_step(const SimtStep *s) {
   a.invtau = it; a.omega = om;
   a.use_incl = s->use_incl; a.incl_ax = s->incl_ax; a.incl_ay = s->incl_ay; a.incl_factor = s->incl_factor;
   a.Lx = s->Lx; a.Ly = s->Ly; a.jbeg = s->jbeg; a.jend = s->jend; a.W = s->W; a.rows_per_cta = s->rows_per_cta;
-  a.wrap_y = s->wrap_y; a.jglobal0 = 0; a.Ly_global = s->Ly;
+  a.wrap_y = s->wrap_y; a.jglobal0 = s->jglobal0; a.Ly_global = s->Ly_global > 0 ? s->Ly_global : s->Ly;
+  a.tc = make_thermal(s->kbt, s->mu, s->delta); a.pk = make_philox_key(s->seed); a.step = s->step;
   a.fstride_in = a.fstride_out = a.fstride_out2 = s->fstride;
   a.h_in = s->h_in; a.ux_in = s->ux_in; a.uy_in = s->uy_in; a.f_in = s->f_in; a.ct_field = s->ct_field;
   a.h_out = s->h_out; a.ux_out = s->ux_out; a.uy_out = s->uy_out; a.f_out = s->f_out; a.f_out2 = s->f_out2;
@@ -159,6 +174,7 @@ int simt_step(const SimtStep *s) {
   if (s->flavour == 0) k = gz ? lean_kernel<true, false, false>(pm) : lean_kernel<false, false, false>(pm);
   else if (s->flavour == 1) k = lean_kernel<false, true, false>(pm);
   else if (s->flavour == 3) k = gz ? lean_kernel<true, false, true>(pm) : lean_kernel<false, false, true>(pm);
+  else if (s->flavour == 5) k = gz ? thermal_kernel<true>(pm) : thermal_kernel<false>(pm);
   else if (s->flavour == 2) k = tau1 ? (kernel_fn)k_fused_step<ENT, 5, true, false, -1, false, false, true>
                                      : (kernel_fn)k_fused_step<ENT, 3, false, false, -1, false, false, true>;
   if (!k) return -1;

@@ -24,7 +24,7 @@ def emul(tmp_path_factory):
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-DSW_HOST_EMULATION", "-w", "-I", CUDA_INC, "-shared", "-fPIC",
                     os.path.join(ROOT, "tests", "host_emulation.cpp"), "-o", so, "-lm"], check=True)
     lib = C.CDLL(so)
-    lib.emul_step.argtypes = [_p] * 6 + [_i, _i] + [_d] * 7 + [_i, _i, _d, _p, _i, _i, _p]
+    lib.emul_step.argtypes = [_p] * 6 + [_i, _i] + [_d] * 7 + [_i, _i, _d, _p, _i, _i, _p, _d, C.c_ulonglong, C.c_ulonglong]
     lib.emul_division_mismatches.argtypes = [_p, _p, C.c_long]
     lib.emul_division_mismatches.restype = C.c_long
     lib.emul_philox.argtypes = [_p, _p, _p]
@@ -42,7 +42,7 @@ def _emul_steps(lib, st, p, nsteps, ct=None, pvariant=0, slip_variant=0):
     for _ in range(nsteps):
         rc = lib.emul_step(_ptr(st.height), _ptr(st.velx), _ptr(st.vely), _ptr(st.fout), _ptr(st.ftemp), _ptr(st.pressure),
                            Lx, Ly, p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g, p.n, p.m, onp.cospi(p.theta),
-                           _ptr(ct), pvariant, slip_variant, _ptr(scratch))
+                           _ptr(ct), pvariant, slip_variant, _ptr(scratch), 0.0, 0, 0)
         assert rc == 0
         st.ftemp[...] = st.fout  # fout == ftemp after every step (src/collide.jl:103)
 

@@ -16,7 +16,7 @@ from oracle import oracle_np as onp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INC = "/usr/local/cuda/include"
 _d, _i, _p = C.c_double, C.c_int, C.c_void_p
-STRICT, OPTS, FULL, BULK, TILE = range(5)
+STRICT, OPTS, FULL, BULK, TILE, THERMAL = range(6)
 
 
 class SimtStep(C.Structure):
@@ -26,7 +26,8 @@ class SimtStep(C.Structure):
                 [(n, _d) for n in ("incl_ax", "incl_ay", "incl_factor")] +
                 [(n, _p) for n in ("h_in", "ux_in", "uy_in", "f_in", "ct_field", "h_out", "ux_out", "uy_out", "f_out", "f_out2",
                                    "pressure", "hgx", "hgy", "slipx", "slipy", "Fx", "Fy", "feq", "vsq")] +
-                [("fstride", C.c_size_t)])
+                [("fstride", C.c_size_t), ("kbt", _d), ("seed", C.c_ulonglong), ("step", C.c_ulonglong),
+                 ("jglobal0", C.c_longlong), ("Ly_global", C.c_longlong)])
 
 
 @pytest.fixture(scope="module")
@@ -157,3 +158,84 @@ def test_tile_kernel_on_cpu(simt, Lx, Ly):
         _run(simt, a, p, 3, TILE, 0, 0)
         oc.time_loop(b, p, nsteps=3)
         _same(a, b, FIELDS)
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    """the device arithmetic source composed on the host (tests/host_emulation.cpp): the reference for the noise path"""
+    so = str(tmp_path_factory.mktemp("emul2") / "libemul.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-DSW_HOST_EMULATION", "-w", "-I", CUDA_INC, "-shared", "-fPIC",
+                    os.path.join(ROOT, "tests", "host_emulation.cpp"), "-o", so, "-lm"], check=True)
+    lib = C.CDLL(so)
+    lib.emul_step.argtypes = [_p] * 6 + [_i, _i] + [_d] * 7 + [_i, _i, _d, _p, _i, _i, _p, _d, C.c_ulonglong, C.c_ulonglong]
+    return lib
+
+
+def test_thermal_kernel_noise_plumbing_on_cpu(simt, emul):
+    """The marching kernel with in-kernel noise against the same device source composed site by site: seed, step counter
+    and the running global-cell cursor (strip offsets, chunk seams, periodic wrap) must select the same Philox block
+    for every site."""
+    Lx, Ly, kbt, seed = 50, 23, 1e-5, 77
+    p = onp.Params(kbt=kbt, n=3, m=2, hmin=0.07)
+    a, b = _state(Lx, Ly, 21), _state(Lx, Ly, 21)
+    N = Lx * Ly
+    cur = [a.height, a.velx, a.vely]
+    alt = [np.zeros_like(x) for x in cur]
+    scratch = np.zeros(10 * N)
+    for s in range(3):
+        q = SimtStep()
+        q.flavour, q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = THERMAL, Lx, Ly, 0, Ly, 21, 6, 1
+        q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+        q.cospi_theta, q.n, q.m, q.pressure_variant, q.slip_variant = onp.cospi(p.theta), p.n, p.m, 1, 0
+        q.h_in, q.ux_in, q.uy_in = (_ptr(x) for x in cur)
+        q.h_out, q.ux_out, q.uy_out = (_ptr(x) for x in alt)
+        q.f_out, q.fstride, q.kbt, q.seed, q.step = _ptr(a.fout), N, kbt, seed, 5 + s
+        assert simt.simt_step(C.byref(q)) == 0
+        cur, alt = alt, cur
+        assert emul.emul_step(_ptr(b.height), _ptr(b.velx), _ptr(b.vely), _ptr(b.fout), _ptr(b.ftemp), _ptr(b.pressure), Lx, Ly,
+                              p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g, p.n, p.m, onp.cospi(p.theta), None, 1, 0,
+                              _ptr(scratch), kbt, seed, 5 + s) == 0
+    assert np.array_equal(cur[0], b.height) and np.array_equal(cur[1], b.velx) and np.array_equal(a.fout, b.fout)
+    quiet = _state(Lx, Ly, 21)
+    oc.time_loop(quiet, onp.Params(n=3, m=2, hmin=0.07), nsteps=3, pvariant="fast")
+    assert not np.array_equal(cur[0], quiet.height)  # (the noise is really there)
+
+
+def test_slab_launches_with_ghost_rows_on_cpu(simt):
+    """What swalbe_dist_time_loop launches on one rank: planes with 3 ghost rows per side handed over at logical row 0
+    (wrap_y = 0), two 3-row edge strips and the interior as separate launches; two emulated ranks with the ghost rows
+    exchanged in NumPy must reproduce the global oracle bit for bit."""
+    Lx, Ly, ranks, GH = 45, 24, 2, 3
+    n = Ly // ranks
+    p = onp.Params(g=-0.001)
+    ref = _state(Lx, Ly, 31)
+    h0, ux0, uy0 = ref.height.copy(), ref.velx.copy(), ref.vely.copy()
+
+    def padded(a, r):  # rows [r*n - GH, (r+1)*n + GH) of the periodic global field
+        return np.asfortranarray(np.take(a, np.arange(r * n - GH, (r + 1) * n + GH), axis=1, mode="wrap"))
+
+    cur = [[padded(a, r) for a in (h0, ux0, uy0)] for r in range(ranks)]
+    fout = [np.zeros((Lx, n, 9), order="F") for _ in range(ranks)]
+    for s in range(3):
+        nxt = [[np.zeros_like(a) for a in cur[r]] for r in range(ranks)]
+        for r in range(ranks):
+            off = GH * Lx * 8  # pointers at logical row 0
+            for jbeg, jend, rows in ((0, GH, GH), (n - GH, n, GH), (GH, n - GH, 4)):  # edge strips, then the interior
+                q = SimtStep()
+                q.flavour, q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = STRICT, Lx, n, jbeg, jend, 40, rows, 0
+                q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+                q.cospi_theta, q.n, q.m = onp.cospi(p.theta), p.n, p.m
+                q.h_in, q.ux_in, q.uy_in = (C.c_void_p(a.ctypes.data + off) for a in cur[r])
+                q.h_out, q.ux_out, q.uy_out = (C.c_void_p(a.ctypes.data + off) for a in nxt[r])
+                q.f_out, q.fstride = _ptr(fout[r]), Lx * n
+                assert simt.simt_step(C.byref(q)) == 0
+        for r in range(ranks):  # halo exchange: ghost rows from the ring neighbours' owned rows
+            lo, hi = (r - 1) % ranks, (r + 1) % ranks
+            for k in range(3):
+                nxt[r][k][:, :GH] = nxt[lo][k][:, n:n + GH]
+                nxt[r][k][:, n + GH:] = nxt[hi][k][:, GH:2 * GH]
+        cur = nxt
+    oc.time_loop(ref, p, nsteps=3)
+    got_h = np.concatenate([cur[r][0][:, GH:GH + n] for r in range(ranks)], axis=1)
+    got_f = np.concatenate(fout, axis=1)
+    assert np.array_equal(got_h, ref.height) and np.array_equal(got_f, ref.fout)
