@@ -93,13 +93,13 @@ static void launch(kernel_fn k, unsigned gx, unsigned gy, unsigned nthreads, siz
 
 constexpr int ENT = 128;  // CTA width of the emulated marching kernels
 
-template <bool GZ, bool OPTS, bool BULK>
+template <bool GZ, bool OPTS, bool BULK, int NT = ENT>
 static kernel_fn lean_kernel(int pm) {
   switch (pm) {
-    case PM_BROAD_93: return k_fused_step<ENT, 5, true, false, PM_BROAD_93, BULK, GZ, OPTS>;
-    case PM_BROAD_32: return k_fused_step<ENT, 5, true, false, PM_BROAD_32, BULK, GZ, OPTS>;
-    case PM_FAST_93: return k_fused_step<ENT, 5, true, false, PM_FAST_93, BULK, GZ, OPTS>;
-    case PM_FAST_32: return k_fused_step<ENT, 5, true, false, PM_FAST_32, BULK, GZ, OPTS>;
+    case PM_BROAD_93: return k_fused_step<NT, 3, true, false, PM_BROAD_93, BULK, GZ, OPTS>;
+    case PM_BROAD_32: return k_fused_step<NT, 3, true, false, PM_BROAD_32, BULK, GZ, OPTS>;
+    case PM_FAST_93: return k_fused_step<NT, 3, true, false, PM_FAST_93, BULK, GZ, OPTS>;
+    case PM_FAST_32: return k_fused_step<NT, 3, true, false, PM_FAST_32, BULK, GZ, OPTS>;
     default: return nullptr;
   }
 }
@@ -128,7 +128,7 @@ extern "C" {
 
 struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop put into FusedArgs
   int flavour;     // 0 strict lean, 1 OPTS lean, 2 FULL, 3 strict lean with bulk row prefetch, 4 tile kernel,
-                   // 5 strict lean with in-kernel thermal noise
+                   // 5 strict lean with in-kernel thermal noise, 6 strict lean with CTAs of 224 threads
   int Lx, Ly, jbeg, jend, W, rows_per_cta, wrap_y;
   double tau, mu, delta, gamma, hmin, hcrit, g, cospi_theta;
   int n, m, pressure_variant, slip_variant, use_incl;
@@ -175,6 +175,12 @@ int simt_step(const SimtStep *s) {
   else if (s->flavour == 1) k = lean_kernel<false, true, false>(pm);
   else if (s->flavour == 3) k = gz ? lean_kernel<true, false, true>(pm) : lean_kernel<false, false, true>(pm);
   else if (s->flavour == 5) k = gz ? thermal_kernel<true>(pm) : thermal_kernel<false>(pm);
+  else if (s->flavour == 6) {
+    k = gz ? lean_kernel<true, false, false, 224>(pm) : lean_kernel<false, false, false, 224>(pm);
+    if (!k || s->W < 1 || s->W > 224 - 8 || s->rows_per_cta < 1) return -2;
+    launch(k, (s->Lx + s->W - 1) / s->W, (s->jend - s->jbeg + s->rows_per_cta - 1) / s->rows_per_cta, 224, fused_smem_doubles(224), a);
+    return 0;
+  }
   else if (s->flavour == 2) k = tau1 ? (kernel_fn)k_fused_step<ENT, 5, true, false, -1, false, false, true>
                                      : (kernel_fn)k_fused_step<ENT, 3, false, false, -1, false, false, true>;
   if (!k) return -1;

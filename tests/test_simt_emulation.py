@@ -16,7 +16,7 @@ from oracle import oracle_np as onp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INC = "/usr/local/cuda/include"
 _d, _i, _p = C.c_double, C.c_int, C.c_void_p
-STRICT, OPTS, FULL, BULK, TILE, THERMAL = range(6)
+STRICT, OPTS, FULL, BULK, TILE, THERMAL, STRICT224 = range(7)
 
 
 class SimtStep(C.Structure):
@@ -239,3 +239,69 @@ def test_slab_launches_with_ghost_rows_on_cpu(simt):
     got_h = np.concatenate([cur[r][0][:, GH:GH + n] for r in range(ranks)], axis=1)
     got_f = np.concatenate(fout, axis=1)
     assert np.array_equal(got_h, ref.height) and np.array_equal(got_f, ref.fout)
+
+
+def test_wider_cta_and_moments_only_steps_on_cpu(simt):
+    """CTAs of 224 threads (the width the 8192^2 film step runs with) and steps that do not write the populations"""
+    p = onp.Params(n=3, m=2, hmin=0.07)
+    a, b = _state(230, 12, 17), _state(230, 12, 17)
+    _run(simt, a, p, 2, STRICT224, 216, 5)
+    oc.time_loop(b, p, nsteps=2)
+    _same(a, b, FIELDS)
+    # lazy populations: f_out == NULL on all but the last step
+    a, b = _state(40, 17, 19), _state(40, 17, 19)
+    N = 40 * 17
+    cur, alt = [a.height, a.velx, a.vely], [np.zeros((40, 17), order="F") for _ in range(3)]
+    for s in range(4):
+        q = SimtStep()
+        q.flavour, q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = STRICT, 40, 17, 0, 17, 33, 6, 1
+        q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+        q.cospi_theta, q.n, q.m = onp.cospi(p.theta), p.n, p.m
+        q.h_in, q.ux_in, q.uy_in = (_ptr(x) for x in cur)
+        q.h_out, q.ux_out, q.uy_out = (_ptr(x) for x in alt)
+        q.f_out, q.fstride = (_ptr(a.fout) if s == 3 else None), N
+        assert simt.simt_step(C.byref(q)) == 0
+        cur, alt = alt, cur
+    oc.time_loop(b, p, nsteps=4)
+    assert np.array_equal(cur[0], b.height) and np.array_equal(cur[2], b.vely) and np.array_equal(a.fout, b.fout)
+
+
+def test_general_tau_slab_with_population_ghost_rows_on_cpu(simt):
+    """tau != 1 on a slab: the old populations are read through pointers at logical row 0 of planes with ONE ghost row
+    per side (the moments have three), plane stride including the ghosts -- the layout of swalbe_dist_* at tau != 1."""
+    Lx, Ly, ranks, GH = 37, 20, 2, 3
+    n = Ly // ranks
+    p = onp.Params(tau=0.8)
+    ref = _state(Lx, Ly, 41, pops=True)
+    h0, ux0, uy0, f0 = ref.height.copy(), ref.velx.copy(), ref.vely.copy(), ref.ftemp.copy()
+    rows_m = lambda r: np.arange(r * n - GH, (r + 1) * n + GH)  # noqa: E731
+    rows_f = lambda r: np.arange(r * n - 1, (r + 1) * n + 1)    # noqa: E731
+    mom = [[np.asfortranarray(np.take(a, rows_m(r), axis=1, mode="wrap")) for a in (h0, ux0, uy0)] for r in range(ranks)]
+    pop = [np.asfortranarray(np.take(f0, rows_f(r), axis=1, mode="wrap")) for r in range(ranks)]  # (Lx, n+2, 9)
+    for s in range(3):
+        mom2 = [[np.zeros_like(a) for a in mom[r]] for r in range(ranks)]
+        pop2 = [np.zeros_like(a) for a in pop]
+        for r in range(ranks):
+            mo, fo = GH * Lx * 8, 1 * Lx * 8
+            for jbeg, jend, rows in ((0, GH, GH), (n - GH, n, GH), (GH, n - GH, 3)):
+                q = SimtStep()
+                q.flavour, q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = FULL, Lx, n, jbeg, jend, 30, rows, 0
+                q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+                q.cospi_theta, q.n, q.m = onp.cospi(p.theta), p.n, p.m
+                q.h_in, q.ux_in, q.uy_in = (C.c_void_p(a.ctypes.data + mo) for a in mom[r])
+                q.h_out, q.ux_out, q.uy_out = (C.c_void_p(a.ctypes.data + mo) for a in mom2[r])
+                q.f_in, q.f_out = C.c_void_p(pop[r].ctypes.data + fo), C.c_void_p(pop2[r].ctypes.data + fo)
+                q.fstride = Lx * (n + 2)
+                assert simt.simt_step(C.byref(q)) == 0
+        for r in range(ranks):
+            lo, hi = (r - 1) % ranks, (r + 1) % ranks
+            for k in range(3):
+                mom2[r][k][:, :GH] = mom2[lo][k][:, n:n + GH]
+                mom2[r][k][:, n + GH:] = mom2[hi][k][:, GH:2 * GH]
+            pop2[r][:, 0, :] = pop2[lo][:, n, :]
+            pop2[r][:, n + 1, :] = pop2[hi][:, 1, :]
+        mom, pop = mom2, pop2
+    oc.time_loop(ref, p, nsteps=3)
+    assert np.array_equal(np.concatenate([mom[r][0][:, GH:GH + n] for r in range(ranks)], axis=1), ref.height)
+    assert np.array_equal(np.concatenate([pop[r][:, 1:n + 1, :] for r in range(ranks)], axis=1), ref.fout)
+
