@@ -44,11 +44,28 @@ static inline void sincospi(double a, double *s, double *c) { *s = sin(a * 3.141
 static inline long long __double_as_longlong(double x) { long long u; memcpy(&u, &x, 8); return u; }
 static inline double __longlong_as_double(long long u) { double x; memcpy(&x, &u, 8); return x; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
-template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }  // (per-step logs are not emulated)
+// warp shuffles: the 32 OS threads of a warp meet at a per-warp barrier around a shared slot array
+static pthread_barrier_t g_warp_barrier[8];
+static unsigned long long g_shfl_slot[8][32];
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int delta);
 static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) {
   return __sync_val_compare_and_swap(p, cmp, v);
 }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int delta) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  g_shfl_slot[w][lane] = bits;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  const unsigned src = lane + (unsigned)delta;
+  const unsigned long long got = src < 32u ? g_shfl_slot[w][src] : bits;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  T out;
+  memcpy(&out, &got, sizeof(T));
+  return out;
+}
 static inline void __trap() { abort(); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
@@ -79,6 +96,7 @@ static void launch(kernel_fn k, unsigned gx, unsigned gy, unsigned nthreads, siz
   for (unsigned by = 0; by < gy; ++by)
     for (unsigned bx = 0; bx < gx; ++bx) {
       pthread_barrier_init(&g_cta_barrier, nullptr, nthreads);
+      for (unsigned w = 0; w < nthreads / 32; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);
       std::vector<std::thread> cta;
       cta.reserve(nthreads);
       for (unsigned t = 0; t < nthreads; ++t)
@@ -88,6 +106,7 @@ static void launch(kernel_fn k, unsigned gx, unsigned gy, unsigned nthreads, siz
         });
       for (auto &th : cta) th.join();
       pthread_barrier_destroy(&g_cta_barrier);
+      for (unsigned w = 0; w < nthreads / 32; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
     }
 }
 
@@ -140,6 +159,9 @@ struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop 
   double kbt;                      // thermal flavour
   unsigned long long seed, step;
   long long jglobal0, Ly_global;   // slab runs: global index of local row 0, global extent (noise counter)
+  double *log_min, *log_max;       // per-step logs (OPTS / FULL flavours): slots of THIS step, pre-set to +-inf / 0
+  unsigned long long *log_wet;
+  double hthresh;
 };
 
 int simt_step(const SimtStep *s) {
@@ -162,6 +184,7 @@ int simt_step(const SimtStep *s) {
   a.h_out = s->h_out; a.ux_out = s->ux_out; a.uy_out = s->uy_out; a.f_out = s->f_out; a.f_out2 = s->f_out2;
   a.pressure = s->pressure; a.hgx = s->hgx; a.hgy = s->hgy; a.slipx = s->slipx; a.slipy = s->slipy;
   a.Fx = s->Fx; a.Fy = s->Fy; a.feq = s->feq; a.vsq = s->vsq;
+  a.log_min = s->log_min; a.log_max = s->log_max; a.log_wet = s->log_wet; a.hthresh = s->hthresh;
   const bool gz = s->g == 0.0, tau1 = s->tau == 1.0;
   const int pm = a.pc.pmode;
   kernel_fn k = nullptr;

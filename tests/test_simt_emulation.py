@@ -27,7 +27,8 @@ class SimtStep(C.Structure):
                 [(n, _p) for n in ("h_in", "ux_in", "uy_in", "f_in", "ct_field", "h_out", "ux_out", "uy_out", "f_out", "f_out2",
                                    "pressure", "hgx", "hgy", "slipx", "slipy", "Fx", "Fy", "feq", "vsq")] +
                 [("fstride", C.c_size_t), ("kbt", _d), ("seed", C.c_ulonglong), ("step", C.c_ulonglong),
-                 ("jglobal0", C.c_longlong), ("Ly_global", C.c_longlong)])
+                 ("jglobal0", C.c_longlong), ("Ly_global", C.c_longlong), ("log_min", _p), ("log_max", _p), ("log_wet", _p),
+                 ("hthresh", _d)])
 
 
 @pytest.fixture(scope="module")
@@ -304,4 +305,30 @@ def test_general_tau_slab_with_population_ghost_rows_on_cpu(simt):
     oc.time_loop(ref, p, nsteps=3)
     assert np.array_equal(np.concatenate([mom[r][0][:, GH:GH + n] for r in range(ranks)], axis=1), ref.height)
     assert np.array_equal(np.concatenate([pop[r][:, 1:n + 1, :] for r in range(ranks)], axis=1), ref.fout)
+
+
+def test_per_step_logs_on_cpu(simt):
+    """time_loop(sys, state, Δh) / the wetted! callback: min, max and count(h > thresh) of the height BEFORE each step,
+    reduced per thread, per warp (shuffles), per CTA (shared memory) and across CTAs (atomics)"""
+    Lx, Ly, nsteps = 70, 19, 4
+    p = onp.Params(g=-0.001, gamma=0.0005)
+    a, b = _state(Lx, Ly, 23), _state(Lx, Ly, 23)
+    mn, mx = np.full(nsteps, np.inf), np.full(nsteps, -np.inf)
+    wet = np.zeros(nsteps, dtype=np.uint64)
+    cur, alt = [a.height, a.velx, a.vely], [np.zeros((Lx, Ly), order="F") for _ in range(3)]
+    for s in range(nsteps):
+        q = SimtStep()
+        q.flavour, q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = OPTS, Lx, Ly, 0, Ly, 50, 7, 1
+        q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+        q.cospi_theta, q.n, q.m = onp.cospi(p.theta), p.n, p.m
+        q.h_in, q.ux_in, q.uy_in = (_ptr(x) for x in cur)
+        q.h_out, q.ux_out, q.uy_out = (_ptr(x) for x in alt)
+        q.f_out, q.fstride = _ptr(a.fout), Lx * Ly
+        q.log_min, q.log_max = C.c_void_p(mn.ctypes.data + 8 * s), C.c_void_p(mx.ctypes.data + 8 * s)
+        q.log_wet, q.hthresh = C.c_void_p(wet.ctypes.data + 8 * s), 1.0
+        assert simt.simt_step(C.byref(q)) == 0
+        cur, alt = alt, cur
+    dh, w = oc.time_loop(b, p, nsteps=nsteps, log_dh=True, log_wetted=True, hthresh=1.0)
+    assert np.array_equal(cur[0], b.height)
+    assert np.array_equal(mx - mn, np.asarray(dh)) and [int(v) for v in wet] == [int(v) for v in w]
 
