@@ -19,12 +19,14 @@ __device__ __forceinline__ int wrapm(int v, int L) {
   return v < 0 ? v + L : v;
 }
 
-template <int PM, bool GZ>
+// TF: compiled for a contact-angle FIELD (a.ct_field != NULL): cospi(theta) is staged on the tile + 2 next to h
+template <int PM, bool GZ, bool TF = false>
 __global__ void __launch_bounds__(TT) k_tile_step(const __grid_constant__ FusedArgs a) {
   __shared__ double sh[TY + 6][TX + 6];
   __shared__ double sux[TY + 2][TX + 2], suy[TY + 2][TX + 2];
   __shared__ double sp[TY + 4][TX + 4];
   __shared__ double sf[9][TY + 2][TX + 2];
+  __shared__ double sct[TF ? TY + 4 : 1][TF ? TX + 4 : 1];
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int Lx = a.Lx, Ly = a.Ly;
@@ -40,6 +42,12 @@ __global__ void __launch_bounds__(TT) k_tile_step(const __grid_constant__ FusedA
     sux[ly][lx] = a.ux_in[g];
     suy[ly][lx] = a.uy_in[g];
   }
+  if (TF) {
+    for (int idx = tid; idx < (TY + 4) * (TX + 4); idx += TT) {
+      const int ly = idx / (TX + 4), lx = idx - ly * (TX + 4);
+      sct[ly][lx] = a.ct_field[(size_t)wrapm(y0 - 2 + ly, Ly) * Lx + wrapm(x0 - 2 + lx, Lx)];
+    }
+  }
   __syncthreads();
 
   // phase 2: film pressure on the tile + 2   (src/pressure.jl:141-153; same expression as fused.cuh stage B)
@@ -50,7 +58,8 @@ __global__ void __launch_bounds__(TT) k_tile_step(const __grid_constant__ FusedA
                                     sh[ly][lx + 2], sh[ly + 2][lx + 2], sh[ly + 2][lx]);
     const double x = div_exact(a.pc.hmin, hc + a.pc.hcrit);
     const double pw = disjoining_powers(x, PM, a.pc.n, a.pc.m);
-    sp[ly][lx] = (-a.pc.gamma * (a.pc.kappa * pw)) - a.pc.gamma * lap;
+    const double kappa = TF ? kappa_from_field(sct[ly][lx], a.pc) : a.pc.kappa;
+    sp[ly][lx] = (-a.pc.gamma * (kappa * pw)) - a.pc.gamma * lap;
   }
   __syncthreads();
 

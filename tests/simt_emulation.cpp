@@ -132,13 +132,13 @@ static kernel_fn thermal_kernel(int pm) {
     default: return nullptr;
   }
 }
-template <bool GZ>
+template <bool GZ, bool TF = false>
 static kernel_fn tile_kernel(int pm) {
   switch (pm) {
-    case PM_BROAD_93: return k_tile_step<PM_BROAD_93, GZ>;
-    case PM_BROAD_32: return k_tile_step<PM_BROAD_32, GZ>;
-    case PM_FAST_93: return k_tile_step<PM_FAST_93, GZ>;
-    case PM_FAST_32: return k_tile_step<PM_FAST_32, GZ>;
+    case PM_BROAD_93: return k_tile_step<PM_BROAD_93, GZ, TF>;
+    case PM_BROAD_32: return k_tile_step<PM_BROAD_32, GZ, TF>;
+    case PM_FAST_93: return k_tile_step<PM_FAST_93, GZ, TF>;
+    case PM_FAST_32: return k_tile_step<PM_FAST_32, GZ, TF>;
     default: return nullptr;
   }
 }
@@ -189,7 +189,8 @@ int simt_step(const SimtStep *s) {
   const int pm = a.pc.pmode;
   kernel_fn k = nullptr;
   if (s->flavour == 4) {
-    k = gz ? tile_kernel<true>(pm) : tile_kernel<false>(pm);
+    if (s->ct_field) k = gz ? tile_kernel<true, true>(pm) : tile_kernel<false, true>(pm);
+    else k = gz ? tile_kernel<true>(pm) : tile_kernel<false>(pm);
     if (!k) return -1;
     launch(k, (s->Lx + 31) / 32, (s->Ly + 7) / 8, 256, 0, a);
     return 0;

@@ -332,3 +332,16 @@ def test_per_step_logs_on_cpu(simt):
     assert np.array_equal(cur[0], b.height)
     assert np.array_equal(mx - mn, np.asarray(dh)) and [int(v) for v in wet] == [int(v) for v in w]
 
+
+@pytest.mark.parametrize("Lx,Ly", [(33, 9), (70, 20), (5, 3)])
+def test_tile_kernel_with_theta_field_on_cpu(simt, Lx, Ly):
+    """the opt-in (SWALBE_TILE_THETA=1) tile instantiations compiled for a contact-angle field"""
+    rng = np.random.default_rng(5)
+    ct = np.asfortranarray(np.cos(np.pi * (1 / 9 + rng.random((Lx, Ly)) / 36)))
+    for kw, pv in ((dict(n=3, m=2, hmin=0.07), 0), (dict(g=-0.001), 1)):
+        p = onp.Params(**kw)
+        a, b = _state(Lx, Ly, 29), _state(Lx, Ly, 29)
+        _run(simt, a, p, 3, TILE, 0, 0, ct=ct, pvariant=pv)
+        oc.time_loop(b, p, nsteps=3, cospi_theta=ct, pvariant="fast" if pv else "power_broad")
+        _same(a, b, FIELDS)
+
