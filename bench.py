@@ -8,7 +8,13 @@ One "step" = one pass of the hot path (src/simulate.jl:15-22) over the whole lat
 SURVEY.md 8d C5/C4 geometry); at N > 1 every rank owns an L x L slab (weak scaling, global lattice L x N*L) and the
 ranks exchange halo rows over NCCL.  Prints ONE JSON line (rank 0).
 
-  value     MLUPS with the state resident in HBM, CUDA-event timed, max over ranks
+  value     MLUPS with the state resident in HBM, CUDA-event timed, max over ranks.  The timed steps are the same at every
+            N: one fused step kernel per step, no materialisation of the reference's intermediate fields (the last
+            step of a user-level call also stores feq/pressure/h∇p/slip/F: that launch is timed separately, as
+            `materialise_step_ms`)
+  parity_vs_1gpu   after the timed region: a 2048 x (256 N) lattice stepped 8 times by the N-rank slab runtime and by the
+            single-GPU loop on rank 0 -- film, thermal (seeded) and thermal + moving contact-angle pattern -- gathered
+            and compared BITWISE (height, velocities, populations)
   e2e       MLUPS of a whole user-level job through the public API: pinned-host initial height -> H2D ->
             time_loop (K steps, fused kernels, per-tdump mass read-back) -> D2H of the final height
   roofline  144 B/LU (9 populations read + 9 written) x L^2 per launch / mean kernel time, against
@@ -93,6 +99,81 @@ def workload_params(args, K):
     return kw
 
 
+class NvmlSampler:
+    """SM clock, power and throttle reasons of ONE GPU, sampled every 20 ms from a thread of this process through NVML
+    (nvidia_ml_py) -- on a busy 8-GPU box the nvidia-smi process of round 1 did not deliver a single line in time.
+    summary() keeps the samples that fall inside the timed window.  Same interface as ClockSampler (the fallback)."""
+
+    def __init__(self, index=0, enabled=True):
+        self.rows, self.t0, self.t1, self.ok, self._stop = [], None, None, False, threading.Event()
+        if not enabled:
+            return
+        try:
+            import pynvml as nv
+            import torch
+
+            nv.nvmlInit()
+            h = None
+            try:  # CUDA ordinal -> NVML handle through the UUID (CUDA_VISIBLE_DEVICES may renumber the devices)
+                h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.nv, self.h = nv, h
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._sample()
+            self.ok = True
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.ok = False
+
+    def _sample(self):
+        nv, h = self.nv, self.h
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                          nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons)))
+
+    def _pump(self):
+        while not self._stop.wait(0.02):
+            try:
+                self._sample()
+            except Exception:
+                break
+
+    def __enter__(self):
+        self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *exc):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        self.stop()
+        if not self.ok or not self.rows:
+            return None
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= self.t1 + 0.03]
+        window = "timed region"
+        if not inside:
+            mid = 0.5 * (self.t0 + self.t1)
+            inside, window = [min(self.rows, key=lambda r: abs(r[0] - mid))], "nearest sample"
+        sm = sorted(r[1] for r in inside)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        reasons = [n for n, b in bits.items() if any(r[3] & b for r in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "power_w_max": max(r[2] for r in inside), "samples": len(sm), "window": window, "source": "nvml"}
+
+
+def make_sampler(index, enabled):
+    s = NvmlSampler(index, enabled)
+    return s if (s.ok or not enabled) else ClockSampler(index, enabled)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons, sampled every 50 ms by a background process that is started BEFORE the
     warm-up (nvidia-smi takes a while to come up); summary() keeps the samples that fall inside the timed window."""
@@ -147,7 +228,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in inside)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in inside), "samples": len(sm), "window": window}
+                "power_w_max": max(float(r[2]) for r in inside), "samples": len(sm), "window": window, "source": "nvidia-smi"}
+
+
+def host_threads():
+    """Threads the CPU legs use: every core this process may run on.  Passed EXPLICITLY to the oracle's OpenMP loops --
+    torch.distributed.run exports OMP_NUM_THREADS=1, which made the N > 1 reference arm of round 1 a 1-core number."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def cpu_baseline_run(L, steps, threads, warmup=1, workload="film"):
@@ -181,7 +271,7 @@ def run_reference(args, rank):
         return
     from oracle import oracle_c as oc
 
-    threads = oc.max_threads()
+    threads = host_threads()
     Ls = 2048
     mlups, dt = cpu_baseline_run(Ls, args.steps, threads, warmup=max(1, min(args.warmup, 3)), workload=args.workload)
     m1, _ = cpu_baseline_run(1024, 3, 1, workload=args.workload)
@@ -206,12 +296,91 @@ def workload_config(args):
                               "by (1,1) every 98 steps on the device, n=3,m=2,hmin=0.07,gamma=0.01,mu=1/12, h=1+0.1 sin sin",
             "droplet": "n=3,m=2,hmin=0.07,theta=1/9, spherical-cap droplet radius min(L/4,256) on a 0.05 precursor (C2)",
             "spinodal": "n=3,m=2,hmin=0.07,gamma=0.01, randomly perturbed film h=1+0.01 N(0,1) (C3)"}[args.workload]
-    weak = args.gpus == 1 or getattr(args, "scaling", "weak") == "weak"
-    rows = args.L if weak else args.L // args.gpus
-    return {"workload": f"thin-film D2Q9 LBM step, {args.L}x{rows} per GPU, tau=1, {what}",
+    rows = rows_per_rank(args)
+    tau = getattr(args, "tau", 1.0)
+    return {"workload": f"thin-film D2Q9 LBM step, {args.L}x{rows} per GPU, tau={tau:g}, {what}",
             "grid": [args.L, rows * args.gpus], "per_gpu_grid": [args.L, rows], "bytes_per_update_alg": B_ALG,
             "decomposition": "row slabs along y, NCCL send/recv halos" if args.gpus > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (>= 1.5 GB touched per step vs 126 MB L2)"}
+
+
+def rows_per_rank(args):
+    """rows of the lattice one rank owns: --rows if given, else L (weak scaling / single GPU) or L / N (strong)"""
+    if getattr(args, "rows", 0):
+        return args.rows
+    weak = args.gpus == 1 or getattr(args, "scaling", "weak") == "weak"
+    return args.L if weak else args.L // args.gpus
+
+
+PARITY_L, PARITY_ROWS, PARITY_STEPS, PARITY_STEP0 = 2048, 256, 8, 94  # (steps 94..101 straddle a substrate move at 98)
+
+
+def parity_vs_single_gpu(sw, _lib, rank, world):
+    """N ranks == 1 GPU, bit for bit (north_star: "1/2/4/8 GPUs must give identical fields").  A 2048 x (256 N) lattice
+    is stepped 8 times by the slab runtime on all ranks and by the single-GPU fused loop on rank 0, for the film, the
+    thermal (seeded Philox noise) and the thermal + moving contact-angle configurations; height, velocities and the
+    nine populations are gathered on rank 0 and compared with torch.equal semantics (number of differing values)."""
+    import argparse as ap
+
+    import torch
+
+    from swalbe_b200.dist import DistSim, broadcast_unique_id_torch
+
+    L, rows, Ly = PARITY_L, PARITY_ROWS, PARITY_ROWS * world
+    out = {}
+    for wl in ("film", "thermal", "thermal_moving"):
+        a = ap.Namespace(workload=wl)
+        prm = sw.Taumucs(**workload_params(a, PARITY_STEPS))
+        sysc = sw.SysConst(Lx=L, Ly=Ly, param=prm)
+        seed = 1234 if wl != "film" else None
+        moving = wl == "thermal_moving"
+        # (a fresh NCCL communicator per case: a DistSim owns its communicator and destroys it on close)
+        sim = DistSim(sysc, rank, world, broadcast_unique_id_torch() if world > 1 else None, thermal_seed=seed)
+        h = sw.Field(L, rows).set(initial_height(L, rows, rank * rows, Ly, workload=wl))
+        ux, uy, f = sw.Field(L, rows), sw.Field(L, rows), sw.Field(L, rows, 9)
+        sim.set_state(h, ux, uy)
+        if moving:
+            sim.set_theta(sw.cospi_field(sw.Field(L, rows).set(theta_pattern(L, rows, rank * rows, Ly))))
+        for t0, cnt, move in (segments(PARITY_STEP0, PARITY_STEPS) if moving else [(PARITY_STEP0, PARITY_STEPS, False)]):
+            sim.time_loop(cnt, t0)
+            if move:
+                sim.shift_theta(1, 1)
+        sim.get_state(h, ux, uy, f)
+        mine = torch.cat([h.t[None], ux.t[None], uy.t[None], f.t], dim=0).contiguous()  # (12, rows, L)
+        if world > 1:
+            import torch.distributed as dist
+
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+        else:
+            parts = [mine]
+        sim.close()
+        if rank == 0:
+            got = torch.cat(parts, dim=1)  # (12, Ly, L)
+            st = sw.Sys(sysc, "GPU", kind="thermal" if seed is not None else "simple")
+            st.height.set(initial_height(L, Ly, 0, Ly, workload=wl))
+            kw = dict(thermal_seed=seed, pressure_variant=_lib.PRESSURE_POWER_BROAD, skip_aux=True)
+            if moving:
+                th, inp = sw.Field(L, Ly).set(theta_pattern(L, Ly, 0, Ly)), sw.Field(L, Ly)
+                inp.set(th)
+                for t0, cnt, move in segments(PARITY_STEP0, PARITY_STEPS):
+                    sw.fused_steps(st, sysc, cnt, step0=t0, θ=th, **kw)
+                    if move:
+                        sw.move_substrate(th, inp, t0 + cnt, TMOVE)
+            else:
+                sw.fused_steps(st, sysc, PARITY_STEPS, step0=PARITY_STEP0, **kw)
+            want = torch.cat([st.height.t[None], st.velx.t[None], st.vely.t[None], st.fout.t], dim=0)
+            ndiff = int((got != want).sum().item())
+            moved = int((want[0] != torch.from_numpy(initial_height(L, Ly, 0, Ly, workload=wl).transpose().copy()).cuda()).sum().item())
+            out[wl] = "bitwise" if (ndiff == 0 and moved > 0) else f"{ndiff} values differ" if ndiff else "fields did not change"
+            del st, got, want
+        del parts, mine
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    verdict = "bitwise" if all(v == "bitwise" for v in out.values()) else "; ".join(f"{k}: {v}" for k, v in out.items())
+    return {"verdict": verdict, "cases": out, "grid": [L, Ly], "steps": PARITY_STEPS, "ranks": world,
+            "fields": "height, velx, vely, fout (9 planes)"}
 
 
 def main():
@@ -221,6 +390,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--L", type=int, default=8192)
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: L; e.g. --L 32768 --rows 4096: C5 weak slabs)")
+    ap.add_argument("--tau", type=float, default=1.0, help="relaxation time (every BASELINE config has tau = 1; tau != 1 runs "
+                                                            "the general kernels that read the old populations)")
     ap.add_argument("--workload", default="film", choices=["film", "thermal", "thermal_moving", "droplet", "spinodal"],
                     help="film: C5 flat film + sine (default); thermal: film + Philox noise; thermal_moving: the complete C4 "
                          "(noise + contact-angle pattern moved by (1,1) every 98 steps, n=3,m=2,hmin=0.07,mu=1/12); droplet: C2 spherical cap, "
@@ -229,6 +401,7 @@ def main():
                     help="N>1: weak = L x L per rank (default, the contract), strong = L x L in total (L/N rows per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank-vs-1-GPU bitwise leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,8 +418,6 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback on the b200 arm)")
     torch.cuda.set_device(local_rank)
-    # nvidia-smi needs seconds to come up on a busy 8-GPU box: start the clock sampler now, on rank 0 only
-    early_sampler = ClockSampler(local_rank, enabled=rank == 0)
     if rank == 0:
         ge.build()
     if world > 1:
@@ -258,35 +429,39 @@ def main():
     from swalbe_b200 import _lib
 
     lib = _lib.load()
+    sampler = make_sampler(local_rank, enabled=rank == 0)  # clocks of rank 0's GPU, sampled during the timed region
     L, K, W = args.L, args.steps, args.warmup
-    prm = sw.Taumucs(**workload_params(args, K))
-    sysc = sw.SysConst(Lx=L, Ly=L, param=prm)
-    rows = L if (world == 1 or args.scaling == "weak") else L // world   # rows per rank
+    wkw = workload_params(args, K)
+    if args.tau != 1.0:
+        wkw.update(τ=args.tau)
+    prm = sw.Taumucs(**wkw)
+    rows = rows_per_rank(args)   # rows per rank
     Ly_glob = rows * world
+    sysc = sw.SysConst(Lx=L, Ly=rows, param=prm)
     thermal_seed = 1234 if args.workload in ("thermal", "thermal_moving") else None
     moving = args.workload == "thermal_moving"
     e2e = None
+    extra = {}
 
     if world == 1:
         st = sw.Sys(sysc, "GPU", kind="thermal" if thermal_seed is not None else "simple")
-        h0 = initial_height(L, workload=args.workload)
+        h0 = initial_height(L, rows, workload=args.workload)
         st.height.set(h0)
         th = inp = None
         if moving:
-            th, inp = sw.Field(L, L).set(theta_pattern(L)), sw.Field(L, L)
+            th, inp = sw.Field(L, rows).set(theta_pattern(L, rows)), sw.Field(L, rows)
             inp.set(th)
+        state = {"started": False}
 
-        def run(n, s0=0, **kw):
-            if not moving:
-                return sw.fused_steps(st, sysc, n, thermal_seed=thermal_seed, step0=s0,
-                                      pressure_variant=_lib.PRESSURE_POWER_BROAD, **kw)
-            segs = segments(s0, n)
-            for q, (t0, cnt, move) in enumerate(segs):  # like the drivers' chunks: intermediate fields on the last one only
-                sw.fused_steps(st, sysc, cnt, thermal_seed=thermal_seed, step0=t0, θ=th, skip_aux=q < len(segs) - 1,
-                               pressure_variant=_lib.PRESSURE_POWER_BROAD, **kw)
+        def run(n, s0=0, aux=False, **kw):
+            """n steps; `aux`: the last launch also materialises the reference's intermediate fields (user-level call)"""
+            segs = segments(s0, n) if moving else [(s0, n, False)]
+            for q, (t0, cnt, move) in enumerate(segs):
+                sw.fused_steps(st, sysc, cnt, thermal_seed=thermal_seed, step0=t0, θ=th, skip_aux=not (aux and q == len(segs) - 1),
+                               pressure_variant=_lib.PRESSURE_POWER_BROAD, moments_consistent=state["started"], **kw)
+                state["started"] = True
                 if move:
                     sw.move_substrate(th, inp, t0 + cnt, TMOVE)
-        sampler = early_sampler
         run(W)
         torch.cuda.synchronize()
         l0 = lib.swalbe_launch_count()
@@ -300,82 +475,84 @@ def main():
         sampler.stop()
         ms = e0.elapsed_time(e1)
         mass_drift = abs(st.height.t.sum().item() - h0.sum()) / h0.sum()
-        lu = L * L * K
-        # moments-only row (populations materialised on the last step only), reported separately
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        run(W, lazy_populations=True)
-        e2.record()
-        run(K, W, lazy_populations=True)
-        e3.record()
+        lu = L * rows * K
+        # the launch that ends a user-level call: the same step + feq/vsq/pressure/h∇p/slip/F and the second population
+        # copy written out (38 planes instead of 12) -- timed on its own, never part of `value`
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        run(1, W + K, aux=True)
+        e4.record()
+        for q in range(3):
+            run(1, W + K + 1 + q, aux=True)
+        e5.record()
         torch.cuda.synchronize()
-        lazy_mlups = lu / (e2.elapsed_time(e3) * 1e-3) / 1e6
+        extra["materialise_step_ms"] = round(e4.elapsed_time(e5) / 3, 4)
+        lazy_mlups = None
+        if args.tau == 1.0:
+            # moments-only row (populations materialised on the last step only), reported separately
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            run(W, lazy_populations=True)
+            e2.record()
+            run(K, W, lazy_populations=True)
+            e3.record()
+            torch.cuda.synchronize()
+            lazy_mlups = lu / (e2.elapsed_time(e3) * 1e-3) / 1e6
         if not args.no_e2e:
             # e2e: the call a user makes -- host initial condition in, time_loop, host result out
             h_host = torch.from_numpy(np.ascontiguousarray(h0.transpose())).pin_memory()
             out_host = torch.empty_like(h_host).pin_memory()
 
-            def job():
+            def job(sc):
                 st.height.t.copy_(h_host, non_blocking=True)
                 st.velx.t.zero_(); st.vely.t.zero_()
-                sw.equilibrium(st, sysc)
+                sw.equilibrium(st, sc)
                 if thermal_seed is None:
-                    sw.time_loop(sysc, st)
+                    sw.time_loop(sc, st)
                 else:
-                    run(sysc.param.Tmax)
+                    state["started"] = False
+                    run(sc.param.Tmax, aux=True)
                 out_host.copy_(st.height.t, non_blocking=True)
                 torch.cuda.synchronize()
 
-            wkw = workload_params(args, K)
-            wkw.update(Tmax=min(K, 4), tdump=2)
-            sysc_warm = sw.SysConst(Lx=L, Ly=L, param=sw.Taumucs(**wkw))
-            sysc, sysc_keep = sysc_warm, sysc
-            job()  # untimed warm-up of the e2e path (first-use costs: module load of the operator kernels, async pool)
-            sysc = sysc_keep
+            wk2 = dict(wkw)
+            wk2.update(Tmax=min(K, 4), tdump=2)
+            job(sw.SysConst(Lx=L, Ly=rows, param=sw.Taumucs(**wk2)))  # untimed warm-up of the e2e path (first-use costs)
             dt = float("inf")
-            for _ in range(3):  # best of three whole jobs (host-side jitter: allocator, Python GC, nvidia-smi teardown)
+            for _ in range(3):  # best of three whole jobs (host-side jitter: allocator, Python GC)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                job()
+                job(sysc)
                 dt = min(dt, time.perf_counter() - t0)
-            plane = L * L * 8
+            plane = L * rows * 8
             e2e = {"value": round(lu / dt / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": plane // K,
                    "d2h_bytes_per_step": (plane + 16 * 4) // K,
-                   "what": f"pinned-host height -> H2D -> equilibrium! + time_loop({K} steps, mass read-back every tdump) -> D2H height; "
-                           "copies amortised over the steps of the job; best of 3 jobs after one warm-up job"}
+                   "what": f"pinned-host height -> H2D -> equilibrium! + time_loop({K} steps, mass read-back every tdump, every field of "
+                           "the state materialised on return) -> D2H height; copies amortised over the steps of the job; best of 3 "
+                           "jobs after one warm-up job"}
+        del st
+        torch.cuda.empty_cache()
     else:
-        import ctypes as C
         import torch.distributed as dist
 
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            raw = (C.c_ubyte * 128)()
-            _lib.call("swalbe_dist_unique_id", raw)
-            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
-        idbuf = idbuf.cuda()
-        dist.broadcast(idbuf, 0)
-        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
-        q = sw._c_params(prm, thermal_seed=thermal_seed)
-        handle = C.c_void_p()
-        _lib.call("swalbe_dist_create", C.byref(handle), raw, rank, world, L, Ly_glob, C.byref(q))
+        from swalbe_b200.dist import DistSim, broadcast_unique_id_torch
+
+        sysg = sw.SysConst(Lx=L, Ly=Ly_glob, param=prm)
+        sim = DistSim(sysg, rank, world, broadcast_unique_id_torch(), thermal_seed=thermal_seed)
         h0 = initial_height(L, rows, rank * rows, Ly_glob, workload=args.workload)
         hd = sw.Field(L, rows).set(h0)
         zero = sw.Field(L, rows)
-        stream = sw._stream()
-        _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
+        sim.set_state(hd, zero, zero)
 
         def set_theta():
             if moving:  # this rank's rows of the pattern; cospi.(θ) on the device
-                ct = sw.cospi_field(sw.Field(L, rows).set(theta_pattern(L, rows, rank * rows, Ly_glob)))
-                _lib.call("swalbe_dist_set_theta", handle, ct.ptr, stream)
+                sim.set_theta(sw.cospi_field(sw.Field(L, rows).set(theta_pattern(L, rows, rank * rows, Ly_glob))))
 
         def dist_run(n, s0):
             for t0, cnt, move in (segments(s0, n) if moving else [(s0, n, False)]):
-                _lib.call("swalbe_dist_time_loop", handle, cnt, t0, stream)
+                sim.time_loop(cnt, t0)
                 if move:
-                    _lib.call("swalbe_dist_shift_theta", handle, 1, 1, stream)
+                    sim.shift_theta(1, 1)
 
         set_theta()
-        sampler = early_sampler
         dist_run(W, 0)
         torch.cuda.synchronize()
         dist.barrier()
@@ -392,7 +569,7 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
-        _lib.call("swalbe_dist_get_state", handle, hd.ptr, None, None, None, stream)
+        sim.get_state(hd)
         msum = torch.tensor([hd.t.sum().item(), float(h0.sum())], device="cuda", dtype=torch.float64)
         dist.all_reduce(msum)
         mass_drift = abs(msum[0].item() - msum[1].item()) / msum[1].item()
@@ -405,10 +582,10 @@ def main():
             torch.cuda.synchronize(); dist.barrier()
             t0 = time.perf_counter()
             hd.t.copy_(h_host, non_blocking=True)
-            _lib.call("swalbe_dist_set_state", handle, hd.ptr, zero.ptr, zero.ptr, None, stream)
+            sim.set_state(hd, zero, zero)
             set_theta()
             dist_run(K, 0)
-            _lib.call("swalbe_dist_get_state", handle, hd.ptr, None, None, None, stream)
+            sim.get_state(hd)
             out_host.copy_(hd.t, non_blocking=True)
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
@@ -417,7 +594,11 @@ def main():
             e2e = {"value": round(lu / dt.item() / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": plane * world // K,
                    "d2h_bytes_per_step": plane * world // K,
                    "what": f"per-rank pinned-host slab -> H2D -> {K} fused steps with NCCL halos -> D2H slab; max over ranks"}
-        _lib.call("swalbe_dist_destroy", handle)
+        sim.close()
+        del hd, zero
+        torch.cuda.empty_cache()
+
+    parity = None if args.no_parity else parity_vs_single_gpu(sw, _lib, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -436,9 +617,11 @@ def main():
     achieved = B_ALG * L * rows / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}_{L}")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(f"{args.workload}_{L}" + (f"_tau{args.tau:g}" if args.tau != 1.0 else "")) if rows == L else None
     except Exception:
         pass
+    clk = clocks.summary() or {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
     line = {
         "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
@@ -453,15 +636,17 @@ def main():
                      # tau = 1 kernel never reads the old populations, so it moves ~120 B/LU against the 144 B convention
                      "dram_gbs": round(traffic / (kernel_ms * 1e-3) / 1e9, 1) if traffic and world == 1 else None,
                      "dram_frac": round(traffic / (kernel_ms * 1e-3) / 1e9 / peak, 4) if traffic and world == 1 else None},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "mass_drift_rel": mass_drift,
     }
+    line.update(extra)
+    if parity is not None:
+        line["parity_vs_1gpu"] = parity["verdict"]
+        line["parity_detail"] = parity
     if lazy_mlups is not None:
         line["moments_only_mlups"] = round(lazy_mlups, 1)  # separate row: populations written on the last step only
-    if not args.no_cpu_baseline:
-        from oracle import oracle_c as oc
-
-        threads = oc.max_threads()
+    if not args.no_cpu_baseline and world == 1:  # (rank 0 at N = 1 only: the tier's contract)
+        threads = host_threads()
         m, dt = cpu_baseline_run(1024, 4, threads, workload=args.workload)
         nst = max(4, min(400, int(12.0 / (dt / 4) / 4)))
         mN, dtN = cpu_baseline_run(2048, nst, threads, workload=args.workload)

@@ -208,6 +208,11 @@ typedef struct swalbe_params {
  * height/velx/vely and fout == ftemp are always current on return.  For drivers that call the loop in chunks (mass
  * print every tdump steps, moving substrates) and only need the intermediate fields at the very end. */
 #define SWALBE_LOOP_SKIP_AUX 2
+/* tau != 1 only: the caller promises that height/velx/vely ARE the moments of ftemp (src/moments.jl:47-50) -- true on
+ * return of every swalbe_time_loop call, false after an initial condition was written into height.  The first step of
+ * the call can then derive h and u from the populations like every later step does (144 B per lattice update instead
+ * of 192).  Drivers set it on every chunk after their first. */
+#define SWALBE_LOOP_MOMENTS_CONSISTENT 4
 /* per-step device logs (see swalbe_time_loop) */
 typedef struct swalbe_loop_logs {
   double *hmin, *hmax;        /* device, nsteps each: min/max of height BEFORE each step (src/simulate.jl:56); NULL = off */

@@ -48,6 +48,7 @@ def lib():
         _lib.oracle_step.restype = C.c_int
         _lib.oracle_time_loop.restype = C.c_int
         _lib.oracle_max_threads.restype = C.c_int
+        _lib.oracle_time_loop_lowmem.restype = C.c_int
     return _lib
 
 
@@ -172,3 +173,26 @@ def time_loop(st, p, nsteps=None, cospi_theta=None, pvariant="power_broad", slip
     if rc:
         raise ValueError("DomainError")
     return dh, wet
+
+
+class _LowmemState(C.Structure):
+    _fields_ = [(n, _dp) for n in ("height", "velx", "vely", "pressure", "f", "g")]
+
+
+def time_loop_lowmem(height, velx, vely, f, p, nsteps, cospi_theta=None, pvariant="power_broad", slip_variant=0, incl=None,
+                     threads=None):
+    """The low-memory fused restatement (22 planes; see swalbe_oracle.c): nsteps iterations of src/simulate.jl:15-22 on
+    height/velx/vely (Lx, Ly) and the populations f (Lx, Ly, 9; the reference's ftemp == fout), all updated IN PLACE.
+    Returns the pressure field of the last step.  Pinned bit for bit to time_loop() by tests/test_oracle_golden.py."""
+    q, _keep = _mk_params(p, cospi_theta, pvariant, slip_variant, incl)
+    Lx, Ly = height.shape
+    pressure = np.zeros((Lx, Ly), order="F")
+    g = np.zeros((Lx, Ly, 9), order="F")
+    s = _LowmemState(_p(height), _p(velx), _p(vely), _p(pressure), _p(f), _p(g))
+    rc = lib().oracle_time_loop_lowmem(C.byref(s), C.byref(q), C.c_int(Lx), C.c_int(Ly), C.c_int(nsteps),
+                                       C.c_int(threads or THREADS))
+    if rc:
+        raise ValueError("DomainError")
+    if nsteps % 2:  # the two population buffers swap every step: the newest set is in g after an odd number of steps
+        f[...] = g
+    return pressure

@@ -319,6 +319,141 @@ int oracle_time_loop(oracle_state *s, const oracle_params *p, int Lx, int Ly, in
   return 0;
 }
 
+/* ---- low-memory fused restatement ------------------------------------------------------------------
+ * The same step with the same per-site expressions (copied from the sweeps above, same association), but
+ * organised as three passes over 22 planes instead of ~100 sweeps over 46: (1) film pressure from height,
+ * (2) per site: h∇p, slip, force, equilibrium, collision IN PLACE into f, (3) streaming f -> g plus
+ * moments.  It exists so that the BASELINE-size parity tests (4096^2, 8192^2) fit in host memory and finish in
+ * seconds; tests/test_oracle_golden.py pins it bit for bit to oracle_time_loop above on every variant.
+ * f holds the current populations (the reference's ftemp == fout), g is scratch of the same size; on return
+ * f holds the streamed populations of the last step and `pressure` the pressure that step computed. */
+typedef struct {
+  double *height, *velx, *vely, *pressure, *f, *g;
+} oracle_lowmem_state;
+
+int oracle_time_loop_lowmem(oracle_lowmem_state *s, const oracle_params *p, int Lx, int Ly, int nsteps, int threads) {
+  const size_t N = (size_t)Lx * Ly;
+  int mode;
+  if (p->pressure_variant == 1) {
+    if (p->n == 9 && p->m == 3) mode = 93;
+    else if (p->n == 3 && p->m == 2) mode = 32;
+    else return 1;
+  } else mode = 0;
+  const double gamma = p->gamma, hmin = p->hmin, hcrit = p->hcrit, delta = p->delta, mu = p->mu, g = p->g, tau = p->tau;
+  const int n = p->n, m = p->m, variant = p->slip_variant;
+  const double nm1 = (double)(n - 1), mm1 = (double)(m - 1), den = (double)(n - m) * hmin;
+  const double g0 = 1.5 * g, w1 = 1.0 / 9.0, w5 = 1.0 / 36.0;
+  const double omeg = 1 - 1 / tau, it = 1 / tau;
+  static const int cs[9][2] = {{0, 0}, {1, 0}, {0, 1}, {-1, 0}, {0, -1}, {1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+  for (int step = 0; step < nsteps; ++step) {
+    const double *h = s->height;
+    double *pr = s->pressure, *f = s->f, *gg = s->g;
+    /* (1) filmpressure!  src/pressure.jl:141-153 (:89-113 for the array form) */
+    PARFOR
+    for (int j = 0; j < Ly; ++j) {
+      const int jp = j ? j - 1 : Ly - 1, jm = j + 1 < Ly ? j + 1 : 0;
+      for (int i = 0; i < Lx; ++i) {
+        const int ip = i ? i - 1 : Lx - 1, im = i + 1 < Lx ? i + 1 : 0;
+        const size_t c = IDX(i, j);
+        const double hip = h[IDX(ip, j)], hjp = h[IDX(i, jp)], him = h[IDX(im, j)], hjm = h[IDX(i, jm)],
+                     hipjp = h[IDX(ip, jp)], himjp = h[IDX(im, jp)], himjm = h[IDX(im, jm)], hipjm = h[IDX(ip, jm)];
+        double x = hmin / (h[c] + hcrit);
+        double pw = mode == 93 ? fast_93(x) : mode == 32 ? fast_32(x) : power_broad(x, n) - power_broad(x, m);
+        double ct = p->cospi_theta_field ? p->cospi_theta_field[c] : p->cospi_theta;
+        double o = -gamma * ((1 - ct) * nm1 * mm1 / den * pw);
+        pr[c] = o - gamma * (2.0 / 3.0 * (hjp + hip + him + hjm) + 1.0 / 6.0 * (hipjp + himjp + himjm + hipjm) -
+                             10.0 / 3.0 * h[c]);
+      }
+    }
+    /* (2) h∇p! forcing.jl:181-184, slippage! :43-44 (+variants), force sum simulate.jl:18-19 (+inclination!
+     * forcing.jl:364), equilibrium! equilibrium.jl:67-114, collision collide.jl:76-89 -- in place into f */
+    PARFOR
+    for (int j = 0; j < Ly; ++j) {
+      const int jp = j ? j - 1 : Ly - 1, jm = j + 1 < Ly ? j + 1 : 0;
+      for (int i = 0; i < Lx; ++i) {
+        const int ip = i ? i - 1 : Lx - 1, im = i + 1 < Lx ? i + 1 : 0;
+        const size_t c = IDX(i, j);
+        const double fip = pr[IDX(ip, j)], fjp = pr[IDX(i, jp)], fim = pr[IDX(im, j)], fjm = pr[IDX(i, jm)],
+                     fipjp = pr[IDX(ip, jp)], fimjp = pr[IDX(im, jp)], fimjm = pr[IDX(im, jm)], fipjm = pr[IDX(ip, jm)];
+        const double hh = h[c], ux = s->velx[c], uy = s->vely[c];
+        double gx = -1.0 / 3.0 * (fip - fim) - 1.0 / 12.0 * (fipjp - fimjp - fimjm + fipjm);
+        double gy = -1.0 / 3.0 * (fjp - fjm) - 1.0 / 12.0 * (fipjp + fimjp - fimjm - fipjm);
+        double hgx = hh * gx, hgy = hh * gy;
+        double sx, sy;
+        if (variant == 0) {
+          sx = (6 * mu * hh * ux) / (2 * (hh * hh) + 6 * delta * hh + 3 * (delta * delta));
+          sy = (6 * mu * hh * uy) / (2 * (hh * hh) + 6 * delta * hh + 3 * (delta * delta));
+        } else if (variant == 1) {
+          double hc = hh + hcrit;
+          sx = (6 * mu * hc * ux) / (2 * (hc * hc) + 6 * delta * hc + 3 * (delta * delta));
+          sy = (6 * mu * hc * uy) / (2 * (hc * hc) + 6 * delta * hc + 3 * (delta * delta));
+        } else {
+          sx = (6 * mu * hh * ux) / (2 * (hh * hh) + 6 * delta * (hh + hcrit));
+          sy = (6 * mu * hh * uy) / (2 * (hh * hh) + 6 * delta * (hh + hcrit));
+        }
+        double Fx = -hgx - sx, Fy = -hgy - sy;
+        if (p->use_inclination) {
+          Fx = Fx + hh * p->incl_ax * p->incl_factor;
+          Fy = Fy + hh * p->incl_ay * p->incl_factor;
+        }
+        double vsq = ux * ux + uy * uy;
+        double fe[9];
+        fe[0] = hh * (1 - 5.0 / 6.0 * g * hh - 2.0 / 3.0 * vsq);
+        fe[1] = w1 * hh * (g0 * hh + 3 * ux + 4.5 * (ux * ux) - 1.5 * vsq);
+        fe[2] = w1 * hh * (g0 * hh + 3 * uy + 4.5 * (uy * uy) - 1.5 * vsq);
+        fe[3] = w1 * hh * (g0 * hh - 3 * ux + 4.5 * (ux * ux) - 1.5 * vsq);
+        fe[4] = w1 * hh * (g0 * hh - 3 * uy + 4.5 * (uy * uy) - 1.5 * vsq);
+        {
+          double sm = ux + uy;
+          fe[5] = w5 * hh * (g0 * hh + 3 * sm + 4.5 * (sm * sm) - 1.5 * vsq);
+          fe[7] = w5 * hh * (g0 * hh - 3 * sm + 4.5 * (sm * sm) - 1.5 * vsq);
+          double d = uy - ux;
+          fe[6] = w5 * hh * (g0 * hh + 3 * d + 4.5 * (d * d) - 1.5 * vsq);
+          double e = ux - uy;
+          fe[8] = w5 * hh * (g0 * hh + 3 * e + 4.5 * (e * e) - 1.5 * vsq);
+        }
+        for (int k = 0; k < 9; ++k) {
+          double b = omeg * f[c + k * N] + it * fe[k];
+          switch (k) {
+            case 0: break;
+            case 1: b = b + 1.0 / 3.0 * Fx; break;
+            case 2: b = b + 1.0 / 3.0 * Fy; break;
+            case 3: b = b - 1.0 / 3.0 * Fx; break;
+            case 4: b = b - 1.0 / 3.0 * Fy; break;
+            case 5: b = b + 1.0 / 24.0 * (Fx + Fy); break;
+            case 6: b = b + 1.0 / 24.0 * (Fy - Fx); break;
+            case 7: b = b - 1.0 / 24.0 * (Fx + Fy); break;
+            default: b = b + 1.0 / 24.0 * (Fx - Fy); break;
+          }
+          f[c + k * N] = b;
+        }
+      }
+    }
+    /* (3) streaming collide.jl:92-103 into g, moments! moments.jl:47-50 */
+    PARFOR
+    for (int j = 0; j < Ly; ++j) {
+      const int jn[3] = {j ? j - 1 : Ly - 1, j, j + 1 < Ly ? j + 1 : 0};  /* j - cy for cy = 1, 0, -1 */
+      for (int i = 0; i < Lx; ++i) {
+        const int in[3] = {i ? i - 1 : Lx - 1, i, i + 1 < Lx ? i + 1 : 0};
+        const size_t c = IDX(i, j);
+        double fk[9];
+        for (int k = 0; k < 9; ++k) {
+          fk[k] = f[IDX(in[1 - cs[k][0]], jn[1 - cs[k][1]]) + k * N];
+          gg[c + k * N] = fk[k];
+        }
+        double hn = 0.0;
+        for (int k = 0; k < 9; ++k) hn = hn + fk[k];
+        s->height[c] = hn;
+        s->velx[c] = (fk[1] - fk[3] + fk[5] - fk[6] - fk[7] + fk[8]) / hn;
+        s->vely[c] = (fk[2] - fk[4] + fk[5] + fk[6] - fk[7] - fk[8]) / hn;
+      }
+    }
+    s->f = gg;
+    s->g = f;
+  }
+  return 0;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -493,8 +493,12 @@ def _c_params(p: Taumucs, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None, t
 
 def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None,
                 thermal_seed=None, step0=0, lazy_populations=False, log_minmax=False, log_wetted=False, hthresh=0.055,
-                pressure_variant=None, skip_aux=False):
+                pressure_variant=None, skip_aux=False, moments_consistent=False):
     """nsteps iterations of the loop body src/simulate.jl:15-22 through swalbe_time_loop (one fused kernel/step).
+
+    ``moments_consistent`` (τ ≠ 1): the caller vouches that height/velx/vely are the moments of ftemp -- true after any
+    earlier fused_steps/time_loop/moments! call on this state, false after writing an initial condition into height --
+    so that the first step, too, derives them from the populations (SWALBE_LOOP_MOMENTS_CONSISTENT).
 
     Returns (hmin[nsteps], hmax[nsteps], wetted[nsteps]) device tensors for the requested logs (else None)."""
     torch = _torch()
@@ -512,13 +516,14 @@ def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_varia
         wet = torch.empty(nsteps, dtype=torch.int64, device="cuda")
         logs.wetted = wet.data_ptr()
     logs.hthresh = hthresh
-    flags = (_lib.LOOP_LAZY_POPULATIONS if lazy_populations else 0) | (_lib.LOOP_SKIP_AUX if skip_aux else 0)
+    flags = ((_lib.LOOP_LAZY_POPULATIONS if lazy_populations else 0) | (_lib.LOOP_SKIP_AUX if skip_aux else 0) |
+             (_lib.LOOP_MOMENTS_CONSISTENT if moments_consistent else 0))
     _lib.call("swalbe_time_loop", st.plan(), C.byref(cs), C.byref(q), int(nsteps), int(step0), flags,
               C.byref(logs) if (log_minmax or log_wetted) else None, _stream())
     return mn, mx, wet
 
 
-def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None):
+def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, lazy_populations=True):
     """The four 2-D time_loop methods  src/simulate.jl:6-96:
 
     time_loop(sys, state)                       plain                          :6-25
@@ -527,7 +532,11 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None):
     time_loop(sys, state, f, measure::list)     callback slot; f ∈ {wetted, inclination}  :69-96
 
     The loop body runs as fused kernels in chunks of `tdump` steps; the mass print happens at the same
-    steps as in the reference (t % tdump == 0, before that step's update)."""
+    steps as in the reference (t % tdump == 0, before that step's update).  On return every field of the state holds
+    what the reference's holds; in between, the loop moves as little as the arithmetic allows: at τ = 1 the populations
+    are only written by the last step of a chunk (`lazy_populations`: ω = 0, nothing reads them -- 48 instead of 120
+    bytes per lattice update, same bits on return), at τ ≠ 1 every chunk after the first vouches for its moments so that
+    all of its steps derive h and u from the populations (144 instead of 192 bytes)."""
     p = sys_.param
     θ, dh, cb, measure = None, None, None, None
     if len(extra) == 1 and isinstance(extra[0], list):
@@ -554,7 +563,8 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None):
         n = nxt - t
         # only the final chunk needs feq/pressure/h∇p/slip/F materialised (the state the reference returns)
         mn, mx, wet = fused_steps(st, sys_, n, θ=θ, incl=incl, log_minmax=dh is not None, log_wetted=cb is wetted,
-                                  skip_aux=nxt <= p.Tmax)
+                                  skip_aux=nxt <= p.Tmax, lazy_populations=bool(lazy_populations) and p.tau == 1.0,
+                                  moments_consistent=t > 1)
         if dh is not None:
             dh.extend((mx - mn).cpu().tolist())
         if cb is wetted:

@@ -15,7 +15,7 @@ OK, ERR_DOMAIN, ERR_EXTENT, ERR_CUDA, ERR_NCCL, ERR_ARG = range(6)
 
 PRESSURE_POWER_BROAD, PRESSURE_FAST = 0, 1
 SLIP_STANDARD, SLIP_HCRIT, SLIP_RING_RIV = 0, 1, 2
-LOOP_DEFAULT, LOOP_LAZY_POPULATIONS, LOOP_SKIP_AUX = 0, 1, 2
+LOOP_DEFAULT, LOOP_LAZY_POPULATIONS, LOOP_SKIP_AUX, LOOP_MOMENTS_CONSISTENT = 0, 1, 2, 4
 NCCL_UNIQUE_ID_BYTES = 128
 
 

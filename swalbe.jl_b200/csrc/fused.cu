@@ -23,6 +23,7 @@ static const Variant *const g_variants[] = {&g_variant_128, &g_variant_160, &g_v
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
+  if (k.fm) return k.lean_pm > 0 ? var.fm_lean[k.lean_pm][k.gz ? 1 : 0] : var.fm_full[k.thermal ? 1 : 0];
   if (k.lean_pm > 0 && k.opts) return var.opts[k.thermal ? 1 : 0][k.lean_pm];
   if (k.lean_pm > 0 && k.bulk) return var.bulk[k.lean_pm][k.gz ? 1 : 0];
   if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm][k.gz ? 1 : 0];
@@ -55,7 +56,10 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   auto t_iter = [&](int ctas_on_sm, int nt) {
     return std::max(0.87, ctas_on_sm * nt * (1.80 + 0.0018 * nt) * 1e-3 * flavour);
   };
-  const double hbm_floor = (double)Lx * (double)nrows * (key.lazy ? 48.0 : 120.0) / 5.5e6;  // us
+  // bytes really moved per lattice update: tau == 1 reads 3 planes and writes 12 (3 when the populations stay lazy);
+  // tau != 1 reads 12 and writes 12, or 9 and 9 when the moments are derived from the populations (FM)
+  const double bytes_lu = key.tau1 ? (key.lazy ? 48.0 : 120.0) : (key.fm ? 144.0 : 192.0);
+  const double hbm_floor = (double)Lx * (double)nrows * bytes_lu / 5.5e6;  // us
   double best_bound_eff = -1.0;  // best W/NT among HBM-bound candidates
   const int fill = 8 + FUSED_D;
   double best_cost = 1e300;
@@ -171,6 +175,7 @@ KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   k.bulk = false;
   k.gz = p.g == 0.0;
   k.lazy = false;
+  k.fm = false;
   k.opts = p.cospi_theta_field != nullptr || p.slip_variant != SWALBE_SLIP_STANDARD || p.use_inclination != 0;
   if (want_lean && k.tau1 && pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
@@ -217,15 +222,16 @@ struct swalbe_plan {
   GraphKey graph_key, seen_key;
   bool have_graph, have_seen;
   int graph_nsteps;
-  LaunchGeom geom[2][2][5][2][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy][opts]
-  bool geom_ok[2][2][5][2][2][2][2];
+  LaunchGeom geom[2][2][5][2][2][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy][opts][fm]
+  bool geom_ok[2][2][5][2][2][2][2][2];
 };
 
 static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
-  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts];
-  if (!plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts]) {
+  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts][k.fm];
+  bool &ok = plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts][k.fm];
+  if (!ok) {
     if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
-    plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts] = true;
+    ok = true;
   }
   *g = &gg;
   return 0;
@@ -352,9 +358,20 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
 
   FusedArgs a = {};
   if (int e = fill_consts(a, *prm)) return e;
-  const KernelKey key_full = make_key(*prm, a.pc.pmode, false);
+  KernelKey key_full = make_key(*prm, a.pc.pmode, false);
   KernelKey key_mid = make_key(*prm, a.pc.pmode, true);  // lean kernel for the steps before the last
   if (logs && (logs->hmin || logs->wetted)) key_mid.opts = true;
+  // tau != 1: every step after the first derives h and u from the populations the previous step streamed (FM kernels:
+  // 72 B read + 72 B written per lattice update); the first one reads the caller's planes unless the caller vouches
+  // for them (an initial condition written into `height` is NOT the zeroth moment of ftemp: src/simulate.jl:349-356).
+  const bool fm = !tau1 && env_int("SWALBE_FM", 1) != 0;
+  const bool fm_first = fm && (flags & SWALBE_LOOP_MOMENTS_CONSISTENT) != 0;
+  KernelKey key_first = key_mid, key_first_full = key_full;  // step 0 when it has to read the moment planes
+  if (fm) {
+    key_full.fm = key_mid.fm = true;
+    if (!key_mid.opts && !key_mid.thermal && a.pc.pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0)) key_mid.lean_pm = a.pc.pmode;
+    a.fm_prefetch = std::max(0, std::min(16, env_int("SWALBE_FM_PREFETCH", 3)));
+  }
   // bulk-copy (TMA unit) row prefetch: needs 16-byte aligned row segments, i.e. even Lx and 16-B aligned planes
   auto aligned16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
   // Measured on B200: +3 % where the step is HBM-bound (8192^2: 43.2 vs 41.9 GLUPS), -2..3 % where it is latency- or
@@ -362,9 +379,11 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   key_mid.bulk = key_mid.lean_pm > 0 && !key_mid.opts && !key_mid.thermal && !lazy && bulk_eligible(Lx, N) && aligned16(st->height) &&
                  aligned16(st->velx) && aligned16(st->vely) && aligned16(plan->scratch);
   key_mid.lazy = lazy;
-  LaunchGeom *g_full = nullptr, *g_mid = nullptr;
+  LaunchGeom *g_full = nullptr, *g_mid = nullptr, *g_first = nullptr, *g_first_full = nullptr;
   if (int e = plan_geometry(plan, key_full, &g_full)) return e;
   if (int e = plan_geometry(plan, key_mid, &g_mid)) return e;
+  if (int e = plan_geometry(plan, key_first, &g_first)) return e;
+  if (int e = plan_geometry(plan, key_first_full, &g_first_full)) return e;
   a.Lx = Lx; a.Ly = Ly; a.jbeg = 0; a.jend = Ly;
   a.wrap_y = 1; a.jglobal0 = 0; a.Ly_global = Ly;
   a.fstride_in = a.fstride_out = a.fstride_out2 = N;
@@ -389,7 +408,10 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   double *A[3] = {st->height, st->velx, st->vely};
   double *B[3] = {plan->scratch, plan->scratch + N, plan->scratch + 2 * N};
   bool src_is_A = true;
-  if (nsteps & 1) {
+  // FM: the moment planes are read by step 0 at most and written by the last step only -- no ping-pong, and no copy
+  // unless the same launch does both
+  const bool fm_pingpong_free = fm && (fm_first || nsteps > 1);
+  if (fm_pingpong_free ? false : (nsteps & 1)) {
     for (int q = 0; q < 3; ++q) SW_CUDA(cudaMemcpyAsync(B[q], A[q], sizeof(double) * N, cudaMemcpyDeviceToDevice, stream));
     src_is_A = false;
   }
@@ -401,6 +423,11 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
     double **src = src_is_A ? A : B, **dst = src_is_A ? B : A;
     a.h_in = src[0]; a.ux_in = src[1]; a.uy_in = src[2];
     a.h_out = dst[0]; a.ux_out = dst[1]; a.uy_out = dst[2];
+    const bool step_fm = fm && (s > 0 || fm_first);
+    if (fm_pingpong_free) {
+      a.h_in = A[0]; a.ux_in = A[1]; a.uy_in = A[2];  // (read by a non-FM step 0 only)
+      a.h_out = last ? A[0] : nullptr; a.ux_out = last ? A[1] : nullptr; a.uy_out = last ? A[2] : nullptr;
+    }
     if (tau1) {
       a.f_in = nullptr;
       a.f_out = (!lazy || last) ? st->fout : nullptr;
@@ -420,11 +447,12 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
     a.log_max = log_mm ? logs->hmax + s : nullptr;
     a.log_wet = log_wet ? logs->wetted + s : nullptr;
     const bool use_full = last && !skip_aux;
-    const LaunchGeom &g = use_full ? *g_full : *g_mid;
+    const KernelKey &key = (fm && !step_fm) ? (use_full ? key_first_full : key_first) : (use_full ? key_full : key_mid);
+    const LaunchGeom &g = (fm && !step_fm) ? (use_full ? *g_first_full : *g_first) : (use_full ? *g_full : *g_mid);
     a.rows_per_cta = g.rows_per_cta; a.W = g.W;
     if (!use_full && N <= tile_max && tile_eligible(key_mid, a)) {  // latency-bound lattices: three-phase tile kernel
       if (int e = launch_tile(a, key_mid, stream)) return e;
-    } else if (int e = launch_fused(g, a, use_full ? key_full : key_mid, stream)) return e;
+    } else if (int e = launch_fused(g, a, key, stream)) return e;
     src_is_A = !src_is_A;
     fsrc_is_ftemp = !fsrc_is_ftemp;
   }

@@ -32,6 +32,12 @@
 // every option decided at run time (used for the last step of a call, which materialises the reference's
 // intermediate fields, and for all uncommon options).  Instantiated per CTA width in fused_v*.cu (variants.h).
 //
+// FM flavour (tau != 1 only, "from moments"): the height and velocity of a site ARE the moments of the populations the
+// previous step streamed there (src/moments.jl:47-50), so a step in the middle of a swalbe_time_loop call does not read
+// the h / ux / uy planes at all and does not write them either: each iteration loads the nine old populations of row
+// N(t+1) (L2-prefetched a few rows ahead), folds them into h for the h ring, and stage C derives u from the populations
+// it needs for the collision anyway.  HBM traffic: 72 B read + 72 B written per lattice update -- the D2Q9 figure.
+//
 // All arithmetic comes from common.cuh (reference evaluation order, no FMA contraction).
 #pragma once
 #include <limits.h>
@@ -73,6 +79,7 @@ struct FusedArgs {
   double *log_min, *log_max;
   unsigned long long *log_wet;
   double hthresh;
+  int fm_prefetch;  // FM kernels: rows ahead of the population loads that are prefetched into L2 (0 = off)
 };
 
 __device__ __forceinline__ void atomic_min_double(double *addr, double v) {
@@ -94,7 +101,7 @@ __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
   }
 }
 
-#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these eight helpers)
+#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these nine helpers)
 // 8-byte asynchronous global -> shared copy (LDGSTS); completion is tracked per thread by commit/wait groups,
 // not by the register scoreboard.
 __device__ __forceinline__ void cp_async8(double *smem_dst, const void *gsrc) {
@@ -125,6 +132,7 @@ __device__ __forceinline__ void bulk_g2s(double *smem_dst, const void *gsrc, uns
                "l"(gsrc), "r"(bytes), "r"(b)
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *gsrc) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gsrc)); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
   unsigned done = 0;
@@ -174,8 +182,9 @@ constexpr int FUSED_LINES = FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES + 4 * RU
 constexpr int FUSED_PAD = 2;
 constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2 * FUSED_PAD); }
 
-template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS>
+template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS, bool FM = false>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
+  static_assert(!FM || (!TAU1 && !BULK), "the from-moments flavour exists for tau != 1 (at tau == 1 no population is read)");
 #ifdef SW_HOST_EMULATION
   double *const smem = emul_dynamic_smem();
 #else
@@ -230,8 +239,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     __syncthreads();
   }
 
-  RowCursor cN, cU, cO, cC, cT;
-  cN.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // h row N(0); prefetched D iterations ahead, starting at t = -D
+  RowCursor cN, cU, cO, cC, cT, cPf;
+  // h row N(0); prefetched D iterations ahead, starting at t = -D.  FM: old populations of row N(t+1) at iteration t
+  cN.init(FM ? j0 - 3 - D : j0 - 4, Lx, a.Ly, a.wrap_y, ci);
+  if (FM) cPf.init(j0 - 3 - D + a.fm_prefetch, Lx, a.Ly, a.wrap_y, ci);  // L2 prefetch runs fm_prefetch rows ahead of cN
   cU.init(j0 - 7, Lx, a.Ly, a.wrap_y, ci);  // u row F(0)
   cO.init(j0 - 9, Lx, a.Ly, a.wrap_y, ci);  // output row O(0)
   cC.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // cospi(theta) field: row P(1), loaded one iteration ahead
@@ -268,7 +279,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   auto iter = [&](const int t, auto steady) {
     constexpr bool S = decltype(steady)::value;
     // ---- asynchronous prefetch of the next row ----------------------------------------------------------
-    {
+    const long long offN = cN.off;  // FM: row N(t+1)
+    if (FM) {
+      if (a.fm_prefetch > 0) {  // (FM launches are periodic in y, wrap_y == 1: every row the cursor reaches exists)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) prefetch_l2(at(a.f_in, cPf.off + k * fs_in8));
+      }
+      cPf.advance(row_bytes, wrapLy, col_bytes);
+      cN.advance(row_bytes, wrapLy, col_bytes);
+    } else {
       const int tn = t + D;  // h row N(tn) = j0-4+tn is needed for tn in [1, R+6]; u rows F(tn) for tn in [6, R+7]
       const bool need_h = S || (tn >= 1 && tn <= R + 6), need_u = S || (tn >= 6 && tn <= R + 7);
       if (BULK) {
@@ -321,6 +340,12 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         if (S || (t >= 2 && t <= R + 5)) ct_n = __ldg(at(a.ct_field, cC.off));
         cC.advance(row_bytes, wrapLy, col_bytes);
       }
+      double fm_n[9];
+      const bool need_m = FM && (S || t <= R + 5);  // row N(t+1) = j0-3+t is needed for t+1 in [1, R+6]
+      if (need_m) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) fm_n[k] = __ldg(at(a.f_in, offN + k * fs_in8));
+      }
       double ft_n[9];
       if (!TAU1) {
         if (S || (t >= 5 && t <= R + 6)) {  // row F(t+1) = j0-6+t in [j0-1, j0+R]
@@ -350,7 +375,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         const double *q1 = a2 + R4_P * LW;  // p row F
         const double *q2 = a1 + R4_P * LW;  // p row F+1
         const double hc = sh[((t - 3) & 7) * LW];
-        const double ux_c = ur[RU_UX * LW], uy_c = ur[RU_UY * LW];
+        double ux_c, uy_c;
+        if (FM) velocity_site(ft_c, hc, ux_c, uy_c);  // moments! of the previous step (src/moments.jl:49-50), not stored
+        else { ux_c = ur[RU_UX * LW]; uy_c = ur[RU_UY * LW]; }
         const double pipjp = q0[-1], pimjp = q0[1], pimjm = q2[1], pipjm = q2[-1];
         const double gx = grad9_x(q1[-1], q1[1], pipjp, pimjp, pimjm, pipjm);
         const double gy = grad9_y(q0[0], q2[0], pipjp, pimjp, pimjm, pipjm);
@@ -407,10 +434,11 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         fn[0] = f0_b;  fn[1] = a2[R4_F1 * LW - 1];  fn[3] = a2[R4_F3 * LW + 1];  // row O   = F(t-2)
         fn[2] = f2_c;  fn[5] = a3[R4_F5 * LW - 1];  fn[6] = a3[R4_F6 * LW + 1];  // row O-1 = F(t-3), moving +y
         fn[4] = f4_a;  fn[7] = o2[R2_F7 * LW + 1];  fn[8] = o2[R2_F8 * LW - 1];  // row O+1 = F(t-1), moving -y
-        double hn, uxn, uyn;
-        moments_site(fn, hn, uxn, uyn);
+        const bool want_m = TAU1 || a.h_out != nullptr;  // tau != 1: only the last step of a call stores the moments
+        double hn = 0.0, uxn = 0.0, uyn = 0.0;
+        if (want_m) moments_site(fn, hn, uxn, uyn);
         if (col_out) {
-          *at(a.h_out, cO.off) = hn; *at(a.ux_out, cO.off) = uxn; *at(a.uy_out, cO.off) = uyn;
+          if (want_m) { *at(a.h_out, cO.off) = hn; *at(a.ux_out, cO.off) = uxn; *at(a.uy_out, cO.off) = uyn; }
           if (a.f_out != nullptr) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) *at(a.f_out, cO.off + k * fs_out8) = fn[k];
@@ -434,10 +462,11 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 9; ++k) ft_c[k] = ft_n[k];
       }
+      if (need_m) sh[((t + 1) & 7) * LW] = height_site(fm_n);  // h row N(t+1) into its ring slot (free since iteration t-3)
     }
     // the prefetch issued D-1 iterations ago (h row N(t+1), u rows F(t+1)) must have landed before the next iteration
     if (BULK) mbar_wait(&s_bar[(t + 1) & 3], (unsigned)((t + 1) >> 2) & 1u);
-    else cp_async_wait<D - 1>();
+    else if (!FM) cp_async_wait<D - 1>();
     __syncthreads();
   };
 

@@ -25,6 +25,7 @@ struct KernelKey {
   bool gz;    // gravity == 0: lean kernels with the (+-0)*h terms of the equilibrium folded away
   bool lazy;  // populations are not written by this launch (geometry only: lower HBM floor)
   bool opts;  // lean kernel that takes theta field / slip variant / inclination / logs at run time
+  bool fm;    // tau != 1: height / velocity derived from the streamed populations instead of read from their planes
 };
 
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);

@@ -12,6 +12,8 @@ struct Variant {
   fused_fn lean[2][5][2];  // [thermal][pmode][g==0] tau == 1 only, pmode in PM_BROAD_93..PM_FAST_32 (index 0 unused)
   fused_fn opts[2][5];     // [thermal][pmode]       lean + theta field / slip variant / inclination / logs at run time
   fused_fn bulk[5][2];     // [pmode][g==0]          lean, non-thermal, rows prefetched with cp.async.bulk (TMA unit)
+  fused_fn fm_full[2];     // [thermal]              tau != 1, moments derived from the streamed populations (FM), run-time options
+  fused_fn fm_lean[5][2];  // [pmode][g==0]          tau != 1, FM, strict lean
 };
 
 extern const Variant g_variant_128, g_variant_160, g_variant_192, g_variant_224, g_variant_256;
@@ -24,12 +26,17 @@ extern const Variant g_variant_128, g_variant_160, g_variant_192, g_variant_224,
   k_fused_step<NT, MB1, true, false, PM_BROAD_93, true, GZ, false>, k_fused_step<NT, MB1, true, false, PM_BROAD_32, true, GZ, false>, \
       k_fused_step<NT, MB1, true, false, PM_FAST_93, true, GZ, false>, k_fused_step<NT, MB1, true, false, PM_FAST_32, true, GZ, false>
 
+#define SW_FM_ROW(NT, MB0, GZ)                                                                                \
+  k_fused_step<NT, MB0, false, false, PM_BROAD_93, false, GZ, false, true>, k_fused_step<NT, MB0, false, false, PM_BROAD_32, false, GZ, false, true>, \
+      k_fused_step<NT, MB0, false, false, PM_FAST_93, false, GZ, false, true>, k_fused_step<NT, MB0, false, false, PM_FAST_32, false, GZ, false, true>
+
 #define SW_DEFINE_VARIANT(NT, MB1, MB0)                                                                       \
   namespace {                                                                                                 \
   const fused_fn lean_##NT[2][2][4] = {{{SW_LEAN_ROW(NT, MB1, false, false, false)}, {SW_LEAN_ROW(NT, MB1, false, true, false)}}, \
                                        {{SW_LEAN_ROW(NT, MB1, true, false, false)}, {SW_LEAN_ROW(NT, MB1, true, true, false)}}};  \
   const fused_fn opts_##NT[2][4] = {{SW_LEAN_ROW(NT, MB1, false, false, true)}, {SW_LEAN_ROW(NT, MB1, true, false, true)}}; \
   const fused_fn bulk_##NT[2][4] = {{SW_BULK_ROW(NT, MB1, false)}, {SW_BULK_ROW(NT, MB1, true)}};              \
+  const fused_fn fm_##NT[2][4] = {{SW_FM_ROW(NT, MB0, false)}, {SW_FM_ROW(NT, MB0, true)}};                   \
   Variant make_##NT() {                                                                                       \
     Variant v = {};                                                                                           \
     v.nt = NT;                                                                                                \
@@ -44,6 +51,10 @@ extern const Variant g_variant_128, g_variant_160, g_variant_192, g_variant_224,
       for (int pm = 1; pm <= 4; ++pm) v.opts[th][pm] = opts_##NT[th][pm - 1];                                 \
     for (int gz = 0; gz < 2; ++gz)                                                                            \
       for (int pm = 1; pm <= 4; ++pm) v.bulk[pm][gz] = bulk_##NT[gz][pm - 1];                                 \
+    v.fm_full[0] = k_fused_step<NT, MB0, false, false, -1, false, false, true, true>;                         \
+    v.fm_full[1] = k_fused_step<NT, MB0, false, true, -1, false, false, true, true>;                          \
+    for (int gz = 0; gz < 2; ++gz)                                                                            \
+      for (int pm = 1; pm <= 4; ++pm) v.fm_lean[pm][gz] = fm_##NT[gz][pm - 1];                                \
     return v;                                                                                                 \
   }                                                                                                           \
   }                                                                                                           \

@@ -70,7 +70,7 @@ static inline void __trap() { abort(); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 
-// ---- the eight asynchronous-copy helpers of fused.cuh, as immediate copies -----------------------------------------
+// ---- the nine asynchronous-copy helpers of fused.cuh, as immediate copies / no-ops -----------------------------------------
 static inline void cp_async8(double *smem_dst, const void *gsrc) { *smem_dst = *(const double *)gsrc; }
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
@@ -79,6 +79,7 @@ static inline void mbar_fence_init() {}
 static inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
 static inline void bulk_g2s(double *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *) { memcpy(smem_dst, gsrc, bytes); }
 static inline void mbar_wait(unsigned long long *, unsigned) {}
+static inline void prefetch_l2(const void *) {}
 
 #include "../swalbe.jl_b200/csrc/tile.cuh"  // (includes fused.cuh and common.cuh)
 
@@ -132,6 +133,16 @@ static kernel_fn thermal_kernel(int pm) {
     default: return nullptr;
   }
 }
+template <bool GZ>
+static kernel_fn fm_kernel(int pm) {  // tau != 1, moments derived from the streamed populations
+  switch (pm) {
+    case PM_BROAD_93: return k_fused_step<ENT, 3, false, false, PM_BROAD_93, false, GZ, false, true>;
+    case PM_BROAD_32: return k_fused_step<ENT, 3, false, false, PM_BROAD_32, false, GZ, false, true>;
+    case PM_FAST_93: return k_fused_step<ENT, 3, false, false, PM_FAST_93, false, GZ, false, true>;
+    case PM_FAST_32: return k_fused_step<ENT, 3, false, false, PM_FAST_32, false, GZ, false, true>;
+    default: return nullptr;
+  }
+}
 template <bool GZ, bool TF = false>
 static kernel_fn tile_kernel(int pm) {
   switch (pm) {
@@ -147,7 +158,8 @@ extern "C" {
 
 struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop put into FusedArgs
   int flavour;     // 0 strict lean, 1 OPTS lean, 2 FULL, 3 strict lean with bulk row prefetch, 4 tile kernel,
-                   // 5 strict lean with in-kernel thermal noise, 6 strict lean with CTAs of 224 threads
+                   // 5 strict lean with in-kernel thermal noise, 6 strict lean with CTAs of 224 threads,
+                   // 7 tau != 1 strict lean from-moments (FM), 8 tau != 1 FULL from-moments
   int Lx, Ly, jbeg, jend, W, rows_per_cta, wrap_y;
   double tau, mu, delta, gamma, hmin, hcrit, g, cospi_theta;
   int n, m, pressure_variant, slip_variant, use_incl;
@@ -162,6 +174,7 @@ struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop 
   double *log_min, *log_max;       // per-step logs (OPTS / FULL flavours): slots of THIS step, pre-set to +-inf / 0
   unsigned long long *log_wet;
   double hthresh;
+  int fm_prefetch;                 // FM flavours: L2 prefetch distance (a no-op here, but the cursor logic runs)
 };
 
 int simt_step(const SimtStep *s) {
@@ -185,6 +198,7 @@ int simt_step(const SimtStep *s) {
   a.pressure = s->pressure; a.hgx = s->hgx; a.hgy = s->hgy; a.slipx = s->slipx; a.slipy = s->slipy;
   a.Fx = s->Fx; a.Fy = s->Fy; a.feq = s->feq; a.vsq = s->vsq;
   a.log_min = s->log_min; a.log_max = s->log_max; a.log_wet = s->log_wet; a.hthresh = s->hthresh;
+  a.fm_prefetch = s->fm_prefetch;
   const bool gz = s->g == 0.0, tau1 = s->tau == 1.0;
   const int pm = a.pc.pmode;
   kernel_fn k = nullptr;
@@ -205,6 +219,8 @@ int simt_step(const SimtStep *s) {
     launch(k, (s->Lx + s->W - 1) / s->W, (s->jend - s->jbeg + s->rows_per_cta - 1) / s->rows_per_cta, 224, fused_smem_doubles(224), a);
     return 0;
   }
+  else if (s->flavour == 7) k = tau1 ? nullptr : gz ? fm_kernel<true>(pm) : fm_kernel<false>(pm);
+  else if (s->flavour == 8) k = tau1 ? nullptr : (kernel_fn)k_fused_step<ENT, 3, false, false, -1, false, false, true, true>;
   else if (s->flavour == 2) k = tau1 ? (kernel_fn)k_fused_step<ENT, 5, true, false, -1, false, false, true>
                                      : (kernel_fn)k_fused_step<ENT, 3, false, false, -1, false, false, true>;
   if (!k) return -1;

@@ -111,6 +111,40 @@ def test_fused_loop_variants_theta_field_slip_inclination(sw):
     _compare(st, ref, what="fast93:")
 
 
+@pytest.mark.parametrize("prm_kw", [dict(τ=0.9), dict(τ=0.75, n=3, m=2, hmin=0.07, g=0.001), dict(τ=1.4, n=4, m=2)],
+                         ids=["tau0.9", "tau0.75-32-g", "tau1.4-generic"])
+def test_general_tau_from_moments_kernels(sw, prm_kw, monkeypatch, small_lattice_flavour):
+    """tau != 1: after the first step the loop derives h and u from the populations (FM kernels, 144 B/LU).  Chunked
+    calls that vouch for their moments (SWALBE_LOOP_MOMENTS_CONSISTENT), one long call, the plane-reading kernels
+    (SWALBE_FM=0) and the oracle must all agree bit for bit, on every field of the state."""
+    Lx, Ly, chunks = 150, 61, (1, 3, 2, 1)
+    st, sysc, ref, p = _mk(sw, Lx, Ly, seed=77, prm_kw=prm_kw, tau_pops=True)
+    done = 0
+    for n in chunks:  # the first chunk starts from an initial condition: height is NOT the moment of ftemp
+        sw.fused_steps(st, sysc, n, moments_consistent=done > 0, skip_aux=done + n < sum(chunks))
+        done += n
+    oc.time_loop(ref, p, nsteps=sum(chunks))
+    _compare(st, ref, what="chunked:")
+    st1, _, _, _ = _mk(sw, Lx, Ly, seed=77, prm_kw=prm_kw, tau_pops=True)
+    sw.fused_steps(st1, sysc, sum(chunks))
+    _compare(st1, ref, what="one call:")
+    monkeypatch.setenv("SWALBE_FM", "0")
+    st0, _, _, _ = _mk(sw, Lx, Ly, seed=77, prm_kw=prm_kw, tau_pops=True)
+    sw.fused_steps(st0, sysc, sum(chunks))
+    _compare(st0, ref, what="FM off:")
+    monkeypatch.delenv("SWALBE_FM")
+    # options that send the FM steps through the run-time-option kernel: theta field, slip variant, per-step logs
+    rng = np.random.default_rng(5)
+    theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))
+    thf = sw.Field(Lx, Ly).set(theta)
+    ct = sw.cospi_field(thf).numpy()
+    st2, _, ref2, _ = _mk(sw, Lx, Ly, seed=78, prm_kw=prm_kw, tau_pops=True)
+    mn, mx, wet = sw.fused_steps(st2, sysc, 5, θ=thf, slip_variant=1, log_minmax=True, log_wetted=True, hthresh=1.0)
+    dh, w = oc.time_loop(ref2, p, nsteps=5, cospi_theta=ct, slip_variant=1, log_dh=True, log_wetted=True, hthresh=1.0)
+    _compare(st2, ref2, what="options:")
+    assert np.array_equal((mx - mn).cpu().numpy(), np.asarray(dh)) and wet.cpu().tolist() == [int(v) for v in w]
+
+
 def test_fused_equals_operator_by_operator_on_gpu(sw):
     """The fused kernel against the seven per-operator kernels run in the reference's order (both on the GPU)."""
     st, sysc, _, _ = _mk(sw, 130, 61, seed=21, prm_kw=dict(g=0.001))

@@ -214,3 +214,36 @@ def test_initial_conditions_known_answers():  # test/initialvalues.jl:16-76
     t = onp.torus(256, 256, 45, 80, 1 / 9, (128, 128))  # doctest src/initialvalues.jl:126-137
     assert np.isclose(t.max(), 45 * (1 - onp.cospi(1 / 9))) and _findmax_index(t) == (127, 47)
 
+
+
+@pytest.mark.parametrize("case", [
+    dict(prm=dict(g=-0.001, gamma=0.0005)),
+    dict(prm=dict(n=3, m=2, hmin=0.07, gamma=0.01)),
+    dict(prm=dict(tau=0.8, n=4, m=2), pops=True),
+    dict(prm=dict(n=3, m=2, hmin=0.07, mu=1 / 12), theta_field=True, slip_variant=1, incl=([1e-4, -2e-5], 0.75)),
+    dict(prm=dict(tau=1.3), pops=True, pvariant="fast", slip_variant=2),
+], ids=["rt", "c3", "tau0.8", "theta-slip2-incl", "tau1.3-fast-ring"])
+def test_lowmem_fused_restatement_equals_the_pass_structured_oracle(case):
+    """oracle_time_loop_lowmem (22 planes, three passes: what the 4096^2 / 8192^2 GPU parity tests run) against
+    oracle_time_loop (the reference's pass structure, 46 planes), bit for bit, on every variant; 1 vs 4 threads."""
+    Lx, Ly, nsteps = 37, 29, 5
+    rng = np.random.default_rng(99)
+    p = onp.Params(**case["prm"])
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06
+    ref.velx[...] = 0.01 * rng.standard_normal((Lx, Ly))
+    ref.vely[...] = 0.01 * rng.standard_normal((Lx, Ly))
+    if case.get("pops"):
+        ref.ftemp[...] = 0.1 + 0.01 * rng.random((Lx, Ly, 9))
+    ct = np.asfortranarray(np.cos(np.pi * (1 / 9 + rng.random((Lx, Ly)) / 36))) if case.get("theta_field") else None
+    kw = dict(cospi_theta=ct, pvariant=case.get("pvariant", "power_broad"), slip_variant=case.get("slip_variant", 0),
+              incl=case.get("incl"))
+    for threads, steps in ((1, nsteps), (4, nsteps - 1)):
+        h, ux, uy, f = (np.asfortranarray(a.copy()) for a in (ref.height, ref.velx, ref.vely, ref.ftemp))
+        full = onp.State(Lx, Ly)
+        for name in ("height", "velx", "vely", "ftemp"):
+            getattr(full, name)[...] = getattr(ref, name)
+        pr = oc.time_loop_lowmem(h, ux, uy, f, p, steps, threads=threads, **kw)
+        oc.time_loop(full, p, nsteps=steps, threads=threads, **kw)
+        assert np.array_equal(h, full.height) and np.array_equal(ux, full.velx) and np.array_equal(uy, full.vely)
+        assert np.array_equal(f, full.fout) and np.array_equal(pr, full.pressure)

@@ -16,7 +16,7 @@ from oracle import oracle_np as onp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INC = "/usr/local/cuda/include"
 _d, _i, _p = C.c_double, C.c_int, C.c_void_p
-STRICT, OPTS, FULL, BULK, TILE, THERMAL, STRICT224 = range(7)
+STRICT, OPTS, FULL, BULK, TILE, THERMAL, STRICT224, FM_LEAN, FM_FULL = range(9)
 
 
 class SimtStep(C.Structure):
@@ -28,7 +28,7 @@ class SimtStep(C.Structure):
                                    "pressure", "hgx", "hgy", "slipx", "slipy", "Fx", "Fy", "feq", "vsq")] +
                 [("fstride", C.c_size_t), ("kbt", _d), ("seed", C.c_ulonglong), ("step", C.c_ulonglong),
                  ("jglobal0", C.c_longlong), ("Ly_global", C.c_longlong), ("log_min", _p), ("log_max", _p), ("log_wet", _p),
-                 ("hthresh", _d)])
+                 ("hthresh", _d), ("fm_prefetch", _i)])
 
 
 @pytest.fixture(scope="module")
@@ -345,3 +345,37 @@ def test_tile_kernel_with_theta_field_on_cpu(simt, Lx, Ly):
         oc.time_loop(b, p, nsteps=3, cospi_theta=ct, pvariant="fast" if pv else "power_broad")
         _same(a, b, FIELDS)
 
+
+
+@pytest.mark.parametrize("Lx,Ly,W,rows", [(25, 26, 120, 26), (150, 40, 120, 13), (70, 23, 62, 8), (5, 5, 4, 2), (3, 30, 120, 7)])
+def test_general_tau_from_moments_flavour_on_cpu(simt, Lx, Ly, W, rows):
+    """tau != 1, FM kernels: the first step reads the caller's h / u planes (which are NOT the moments of ftemp -- an
+    initial condition), every later step derives h from the nine old populations it loads for the h ring and u from the
+    populations it collides; the moment planes are written by the last step only.  This is the launch sequence of
+    swalbe_time_loop at tau != 1 (csrc/fused.cu), compared with the oracle bit for bit, materialised fields included."""
+    for kw, last_full, pf in ((dict(tau=0.8, n=3, m=2, hmin=0.07), True, 3), (dict(tau=1.3, g=-0.001, gamma=0.0005), False, 0)):
+        p = onp.Params(**kw)
+        a, b = _state(Lx, Ly, 47, pops=True), _state(Lx, Ly, 47, pops=True)
+        nsteps, N = 4, Lx * Ly
+        fsrc, fdst = a.ftemp, a.fout
+        for s in range(nsteps):
+            last = s == nsteps - 1
+            q = SimtStep()
+            q.flavour = FULL if s == 0 else (FM_FULL if (last and last_full) else FM_LEAN)
+            q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = Lx, Ly, 0, Ly, W, rows, 1
+            q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+            q.cospi_theta, q.n, q.m, q.fm_prefetch = onp.cospi(p.theta), p.n, p.m, pf
+            q.h_in, q.ux_in, q.uy_in = _ptr(a.height), _ptr(a.velx), _ptr(a.vely)  # (read by step 0 only)
+            if last:
+                q.h_out, q.ux_out, q.uy_out = _ptr(a.height), _ptr(a.velx), _ptr(a.vely)
+            q.f_in, q.f_out, q.fstride = _ptr(fsrc), _ptr(fdst), N
+            if last and last_full:
+                for name, fld in (("pressure", a.pressure), ("hgx", a.hgradpx), ("hgy", a.hgradpy), ("slipx", a.slipx),
+                                  ("slipy", a.slipy), ("Fx", a.Fx), ("Fy", a.Fy), ("feq", a.feq), ("vsq", a.vsq)):
+                    setattr(q, name, _ptr(fld))
+            assert simt.simt_step(C.byref(q)) == 0
+            fsrc, fdst = fdst, fsrc
+        if fsrc is not a.fout:
+            a.fout[...] = fsrc
+        oc.time_loop(b, p, nsteps=nsteps)
+        _same(a, b, FIELDS + (AUX[:-1] if last_full else ()))
