@@ -16,7 +16,10 @@
  *  - Zero-copy: the library never frees or retains caller pointers beyond a call.
  *  - Every call is asynchronous on the caller's `stream` (a cudaStream_t passed as void*; NULL = the
  *    legacy default stream), so it is ordered with the caller's own device work.  No hidden
- *    cudaDeviceSynchronize.
+ *    cudaDeviceSynchronize.  The only host-blocking entry points are the ones that own memory:
+ *    swalbe_plan_create / swalbe_dist_create (cudaMalloc, NCCL communicator set-up), their destroy
+ *    counterparts (swalbe_dist_destroy waits for the handle's own three streams before freeing) and
+ *    swalbe_dist_last_loop_ms (waits for the loop's end event, by definition).
  *  - Every function returns 0 on success or a swalbe_status code; swalbe_last_error() gives the
  *    message (thread-local).  Nothing throws across the ABI.
  *  - Arithmetic is IEEE-754 double with NO fused multiply-add contraction and the reference's exact

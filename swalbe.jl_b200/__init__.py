@@ -31,7 +31,7 @@ __all__ = [
     "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES", "viewdists", "viewneighbors", "power_broad", "power_2",
     "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field", "torus", "rivulet", "sinewave2d",
     "randinterface", "circshift", "move_substrate", "restart_from_height", "save_heights", "dump_height_slab",
-    "load_height_slab",
+    "load_height_slab", "SnapshotBuffer",
 ]
 
 
@@ -336,6 +336,8 @@ def hgradp(st: CuState):
 def gradf(outx, outy, f, *rest):
     """∇f!(outx, outy, f) | ∇f!(outx, outy, f, a) | ∇f!(outx, outy, f, dgrad, a)   src/differences.jl:153-206"""
     a = rest[-1] if rest else None
+    if a is not None and not isinstance(a, Field):  # a scalar multiplier broadcasts like the reference's `a .* (...)`
+        a = Field(*_dims(f), fill=float(a))
     _lib.call("swalbe_grad9", _ptr(outx), _ptr(outy), _ptr(f), _ptr(a), *_dims(f), _stream())
 
 
@@ -371,9 +373,30 @@ def slippage_ring_riv(*args):
     _slip(_lib.SLIP_RING_RIV, args)
 
 
-def thermal(*args, seed=0, step=0):
+_noise = {"seed": None, "calls": 0}
+
+
+def _noise_seed() -> int:
+    """the process-wide default Philox key: drawn from the OS once, like Julia's unseeded default RNG"""
+    if _noise["seed"] is None:
+        import os
+
+        _noise["seed"] = int.from_bytes(os.urandom(8), "little")
+    return _noise["seed"]
+
+
+def thermal(*args, seed=None, step=None):
     """thermal!(kbtx, kbty, height, kbt, μ, δ) | thermal!(state, sys)   src/forcing.jl:297-320
-    (counter-based Philox normals keyed on (seed, step, cell) instead of Julia's randn! stream)."""
+    (counter-based Philox normals keyed on (seed, step, cell) instead of Julia's randn! stream).
+
+    Like `randn!`, every call draws FRESH noise: without `step` a process-wide call counter advances the Philox
+    stream, without `seed` the key is drawn from the OS once per process.  Pass both for a reproducible field (the
+    decomposition-independent noise of the fused loop uses step = time step)."""
+    if step is None:
+        step = _noise["calls"]
+        _noise["calls"] += 1
+    if seed is None:
+        seed = _noise_seed()
     if isinstance(args[0], CuState):
         st, sys_ = args
         p = sys_.param
@@ -426,10 +449,46 @@ def wetted(area_size, *args, hthresh=0.055):
     maxheight[t - 1] = mx
 
 
-def snapshot(snap: np.ndarray, field: Field, t: int, dumping=1000):
-    """snapshot!(snap, field, t; dumping)   src/measures.jl:99-105"""
+class SnapshotBuffer:
+    """The scripts' `snap = zeros(ndumps, Lx*Ly)` matrix in PINNED host memory, filled by asynchronous copies
+    (SURVEY.md 8f1): `snapshot!` copies the field into a device staging plane on the compute stream (the field itself is
+    overwritten by the very next step) and a side stream moves the staging plane to the host while the loop goes on.
+    `array()` waits for the copies in flight and returns the NumPy matrix (rows = dumps, Julia's `vec` order)."""
+
+    def __init__(self, ndumps: int, Lx: int, Ly: int):
+        torch = _torch()
+        self.host = torch.zeros((ndumps, Lx * Ly), dtype=torch.float64).pin_memory()
+        self.stage = torch.empty(Lx * Ly, dtype=torch.float64, device="cuda")
+        self.stream = torch.cuda.Stream()
+        self.done = None
+
+    def push(self, row: int, field: Field):
+        torch = _torch()
+        cur = torch.cuda.current_stream()
+        if self.done is not None:
+            cur.wait_event(self.done)  # the staging plane is free again once the previous dump has left the device
+        self.stage.copy_(field.t.reshape(-1))
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            self.host[row].copy_(self.stage, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record(self.stream)
+
+    def array(self) -> np.ndarray:
+        self.stream.synchronize()
+        return self.host.numpy()
+
+
+def snapshot(snap, field: Field, t: int, dumping=1000):
+    """snapshot!(snap, field, t; dumping)   src/measures.jl:99-105.  `snap`: a SnapshotBuffer (asynchronous pinned
+    copy, the loop is not stalled) or a plain NumPy matrix (synchronous, like the reference's `Array(field)`)."""
     if t % dumping == 0:
-        snap[t // dumping - 1, :] = field.numpy().reshape(-1, order="F")
+        if isinstance(snap, SnapshotBuffer):
+            snap.push(t // dumping - 1, field)
+        else:
+            snap[t // dumping - 1, :] = field.numpy().reshape(-1, order="F")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -659,8 +718,12 @@ def sinewave2d(field: "Field", h0=1.0, ϵ=0.001, kx=15, ky=18, j_begin=0, Ly=Non
     return field.touch()
 
 
-def randinterface(field: "Field", h0, ϵ, seed=0, j_begin=0):
-    """randinterface!(height, h₀, ϵ)  src/initialvalues.jl:23-33 with seeded counter-based normals on the device."""
+def randinterface(field: "Field", h0, ϵ, seed=None, j_begin=0):
+    """randinterface!(height, h₀, ϵ)  src/initialvalues.jl:23-33 with counter-based normals on the device.  Without
+    `seed` every call draws a new interface (like the reference's randn!); slabs of one lattice must share a seed."""
+    if seed is None:
+        seed = (_noise_seed() + 0x9E3779B97F4A7C15 * (1 + _noise["calls"])) & 0xFFFFFFFFFFFFFFFF
+        _noise["calls"] += 1
     Lx, Lyl, jb, _ = _slab(field, j_begin, None)
     _lib.call("swalbe_ic_randinterface", field.ptr, float(h0), float(ϵ), int(seed), Lx, Lyl, jb, _stream())
     return field.touch()

@@ -77,6 +77,8 @@ struct swalbe_dist {
   double *m[2][3];        // ping-pong sets of (h, ux, uy)
   double *f[2];           // population sets (tau == 1: only f[0], no ghosts)
   double *ct;             // cospi(theta) slab with GH ghost rows (NULL: scalar theta)
+  double *ct_spare;       // a slab released by swalbe_dist_set_theta(NULL), kept for the next field (no free in the loop)
+  bool looped;            // ev_t1 has been recorded (a time loop has run)
   double *ct_alt;         // second buffer of the same shape: target of swalbe_dist_shift_theta (allocated on first use)
   int cur;                // index of the set holding the current moments
   int fcur;               // index of the set holding the current populations (tau != 1)
@@ -219,7 +221,10 @@ static int dist_allocate(swalbe_dist *d, const void *id128, int rank, int nranks
 
 int swalbe_dist_destroy(swalbe_dist *d) {
   if (!d) return 0;
-  cudaDeviceSynchronize();
+  // the only blocking entry point besides create: the handle's own streams are drained before its memory goes away
+  if (d->s_comp) cudaStreamSynchronize(d->s_comp);
+  if (d->s_edge) cudaStreamSynchronize(d->s_edge);
+  if (d->s_comm) cudaStreamSynchronize(d->s_comm);
   if (d->comm) g_nccl.CommDestroy(d->comm);
   for (int s = 0; s < 2; ++s) {
     for (int q = 0; q < 3; ++q) cudaFree(d->m[s][q]);
@@ -227,6 +232,7 @@ int swalbe_dist_destroy(swalbe_dist *d) {
   }
   cudaFree(d->ct);
   cudaFree(d->ct_alt);
+  cudaFree(d->ct_spare);
   if (d->s_comp) cudaStreamDestroy(d->s_comp);
   if (d->s_comm) cudaStreamDestroy(d->s_comm);
   if (d->s_edge) cudaStreamDestroy(d->s_edge);
@@ -322,6 +328,7 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
   SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_edges, 0));
   SW_CUDA(cudaEventRecord(d->ev_t1, d->s_comp));
   SW_CUDA(cudaStreamWaitEvent(user, d->ev_t1, 0));
+  d->looped = true;
   return 0;
 }
 
@@ -345,14 +352,15 @@ int swalbe_dist_get_state(swalbe_dist *d, double *height, double *velx, double *
 int swalbe_dist_set_theta(swalbe_dist *d, const double *ct_slab, void *stream_) {
   if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
   cudaStream_t user = (cudaStream_t)stream_;
-  SW_CUDA(cudaStreamSynchronize(d->s_comp));  // geometry / kernel flavour may change: drain our own streams first
-  SW_CUDA(cudaStreamSynchronize(d->s_edge));
-  SW_CUDA(cudaStreamSynchronize(d->s_comm));
+  // No host synchronisation: launches already enqueued keep the kernel flavour and pointers they were given; the copy
+  // below is ordered after the last time loop by its end event (the loop's kernels read the slab this call overwrites).
+  if (d->looped) SW_CUDA(cudaStreamWaitEvent(user, d->ev_t1, 0));
   if (!ct_slab) {
-    cudaFree(d->ct);
+    if (d->ct) d->ct_spare = d->ct;  // (never both set: a spare slab is taken back before a new one is allocated)
     d->ct = nullptr;
     d->prm.cospi_theta_field = nullptr;
   } else {
+    if (!d->ct && d->ct_spare) { d->ct = d->ct_spare; d->ct_spare = nullptr; }
     if (!d->ct) SW_CUDA(cudaMalloc((void **)&d->ct, d->mplane * sizeof(double)));
     const size_t n = (size_t)d->Ly_loc * d->Lx;
     SW_CUDA(cudaMemcpyAsync(d->ct + (size_t)GH * d->Lx, ct_slab, n * sizeof(double), cudaMemcpyDeviceToDevice, user));

@@ -21,10 +21,30 @@ def _as_host(a) -> np.ndarray:
     return a.numpy() if hasattr(a, "numpy") and not isinstance(a, np.ndarray) else np.asarray(a, dtype=np.float64)
 
 
-def save_heights(path: str, columns: Mapping) -> None:
-    """Store {"h_<t>": matrix or vector} the way the scripts do: each entry flattened column-major (Julia's vec)."""
+def _npz_path(path) -> str:
+    """np.savez appends ".npz" to names that lack it; use the same name on the way in and on the way out"""
+    path = os.fspath(path)
+    return path if path.endswith(".npz") else path + ".npz"
+
+
+def save_heights(path: str, columns: Mapping) -> str:
+    """Store {"h_<t>": matrix or vector} the way the scripts do: each entry flattened column-major (Julia's vec).
+    Returns the file name written (".npz" appended when missing; restart_from_height accepts either spelling)."""
     out = {k: np.ravel(_as_host(v), order="F").astype(np.float64) for k, v in columns.items()}
-    np.savez(path, **out)
+    path = _npz_path(path)
+    with open(path, "wb") as f:
+        np.savez(f, **out)
+    return path
+
+
+def _last_column(cols) -> str:
+    """the reference's `df[:, end]`: the column of the highest time step (h_<t> by integer t; other names keep their
+    insertion order and come first)"""
+    def key(item):
+        idx, name = item
+        tail = name[2:] if name.startswith("h_") else ""
+        return (1, int(tail), idx) if tail.isdigit() else (0, 0, idx)
+    return max(enumerate(cols), key=key)[1]
 
 
 def restart_from_height(data, kind: str = "npz", timestep: int = 0, size=(512, 512)) -> np.ndarray:
@@ -36,13 +56,14 @@ def restart_from_height(data, kind: str = "npz", timestep: int = 0, size=(512, 5
     if kind not in ("npz", "dict"):
         raise ValueError(f"kind={kind!r}: only the NumPy container is available here (JLD2/BSON need Julia packages)")
     if isinstance(data, (str, os.PathLike)):
-        with np.load(data) as z:
+        data = os.fspath(data)
+        with np.load(data if os.path.exists(data) else _npz_path(data)) as z:
             cols = {k: z[k] for k in z.files}
     else:
         cols = dict(data)
     if not cols:
         raise ValueError("no stored heights")
-    key = list(cols)[-1] if timestep == 0 else f"h_{timestep}"
+    key = _last_column(cols) if timestep == 0 else f"h_{timestep}"
     if key not in cols:
         raise KeyError(key)
     v = np.asarray(cols[key], dtype=np.float64).ravel()
@@ -58,9 +79,16 @@ def dump_height_slab(path: str, slab, Lx: int, Ly: int, j_begin: int = 0) -> Non
     if a.ndim != 2 or a.shape[0] != Lx or j_begin < 0 or j_begin + a.shape[1] > Ly:
         raise ValueError(f"slab {a.shape} at row {j_begin} does not fit a {Lx} x {Ly} lattice")
     total = Lx * Ly * 8
-    if not os.path.exists(path) or os.path.getsize(path) != total:
-        with open(path, "ab") as f:  # create / size the file without truncating what other ranks already wrote
-            f.truncate(total)
+    # create / size the file without truncating what other ranks already wrote.  O_CREAT without O_TRUNC and an
+    # unconditional ftruncate to the SAME length are idempotent, so concurrent ranks cannot undo each other; a stale
+    # file of another size is resized by whoever comes first (ranks that want a clean file remove it before the dump,
+    # behind a barrier).
+    fd = os.open(path, os.O_RDWR | os.O_CREAT, 0o644)
+    try:
+        if os.fstat(fd).st_size != total:
+            os.ftruncate(fd, total)
+    finally:
+        os.close(fd)
     mm = np.memmap(path, dtype="<f8", mode="r+", shape=(Ly, Lx))  # C order (Ly, Lx) == column-major (Lx, Ly)
     mm[j_begin:j_begin + a.shape[1], :] = a.T
     mm.flush()

@@ -310,3 +310,48 @@ def test_thermal_normals_distribution(G):
     assert c(zx, st.kbtx.numpy() / amp) < lim
     sw.thermal(st, sysc, seed=99, step=5)
     assert np.array_equal(zx, st.kbtx.numpy() / amp)  # counter-based: reproducible
+
+
+def test_thermal_draws_fresh_noise_per_call_like_randn(G):
+    """thermal!(state, sys) in a user loop (scripts/Rivulet_stability.jl:120-124) must not repeat its field: without
+    seed/step the call counter advances the Philox stream; with both, the field is reproducible."""
+    import swalbe_b200 as sw
+
+    sysc = sw.SysConst(Lx=64, Ly=48, param=sw.Taumucs(kbt=1e-6))
+    st = sw.Sys(sysc, "GPU", kind="thermal")
+    sw.thermal(st, sysc)
+    a = st.kbtx.numpy()
+    sw.thermal(st, sysc)
+    b = st.kbtx.numpy()
+    assert not np.array_equal(a, b) and abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 0.1
+    sw.thermal(st, sysc, seed=5, step=9)
+    c = st.kbtx.numpy()
+    sw.thermal(st, sysc, seed=5, step=9)
+    assert np.array_equal(c, st.kbtx.numpy())
+    f1 = sw.randinterface(sw.Field(64, 48), 1.0, 0.01).numpy()
+    f2 = sw.randinterface(sw.Field(64, 48), 1.0, 0.01).numpy()
+    assert not np.array_equal(f1, f2)
+
+
+def test_gradf_scalar_multiplier_and_async_snapshots(G):
+    """∇f!(outx, outy, f, a) with a scalar a (src/differences.jl:171-187 broadcasts it); snapshot! into pinned host memory
+    through a staging plane while the loop keeps running (src/measures.jl:99-105)."""
+    import swalbe_b200 as sw
+
+    Lx, Ly = 40, 33
+    rng = np.random.default_rng(8)
+    f = np.asfortranarray(rng.random((Lx, Ly)))
+    ox, oy, fd = sw.Field(Lx, Ly), sw.Field(Lx, Ly), sw.Field(Lx, Ly).set(f)
+    sw.gradf(ox, oy, fd, 0.37)
+    wx, wy = np.zeros((Lx, Ly), order="F"), np.zeros((Lx, Ly), order="F")
+    oc.grad9(wx, wy, f, a=np.full((Lx, Ly), 0.37, order="F"))
+    assert np.array_equal(ox.numpy(), wx) and np.array_equal(oy.numpy(), wy)
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(Tmax=12, tdump=100, g=-0.001))
+    st = sw.Sys(sysc, "GPU")
+    st.height.set(np.asfortranarray(1.0 + 0.1 * rng.random((Lx, Ly))))
+    snaps, plain = sw.SnapshotBuffer(3, Lx, Ly), np.zeros((3, Lx * Ly))
+    for t in range(1, 13):
+        sw.fused_steps(st, sysc, 1, skip_aux=True)
+        sw.snapshot(snaps, st.height, t, dumping=4)
+        sw.snapshot(plain, st.height, t, dumping=4)
+    assert np.array_equal(snaps.array(), plain) and plain[2].any() and not np.array_equal(plain[0], plain[2])

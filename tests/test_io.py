@@ -23,6 +23,13 @@ def test_restart_from_height_like_the_reference(tmp_path):
         io.restart_from_height(path, timestep=1, size=(10, 11))
     with pytest.raises(ValueError):
         io.restart_from_height(path, kind="jld2", timestep=1, size=(10, 10))
+    # a name without the suffix reads back under the same name; "last column" = highest time step, not insertion order
+    bare = str(tmp_path / "run7")
+    assert io.save_heights(bare, {"h_10": h2.ravel(order="F"), "h_9": h1.ravel(order="F"), "h_2": h1.ravel(order="F")}) == bare + ".npz"
+    assert np.array_equal(io.restart_from_height(bare, timestep=9, size=(10, 10)), h1)
+    assert np.array_equal(io.restart_from_height(bare, timestep=0, size=(10, 10)), h2)
+    assert np.array_equal(io.restart_from_height({"h_10": h2.ravel(order="F"), "h_9": h1.ravel(order="F")}, kind="dict",
+                                                 size=(10, 10)), h2)
     # matrices are flattened column-major on the way in, non-square sizes keep their orientation
     m = np.arange(12, dtype=np.float64).reshape(3, 4)
     io.save_heights(path, {"h_5": m})
@@ -40,6 +47,11 @@ def test_slab_parallel_dump_roundtrip(tmp_path):
     assert np.array_equal(io.load_height_slab(path, Lx, Ly), h)
     assert np.array_equal(io.load_height_slab(path, Lx, Ly, j_begin=5, rows=7), h[:, 5:12])
     assert np.array_equal(np.fromfile(path, dtype="<f8"), h.ravel(order="F"))  # == Julia's write(io, h)
+    stale = str(tmp_path / "stale.raw")  # a left-over file of another size is resized, not appended to
+    open(stale, "wb").write(b"x" * 17)
+    for r in range(ranks):
+        io.dump_height_slab(stale, h[:, r * rows:(r + 1) * rows], Lx, Ly, j_begin=r * rows)
+    assert np.array_equal(io.load_height_slab(stale, Lx, Ly), h)
     with pytest.raises(ValueError):
         io.dump_height_slab(path, h[:, :3], Lx, Ly, j_begin=18)
     with pytest.raises(ValueError):
