@@ -41,7 +41,8 @@ static int env_int(const char *name, int dflt) {
 // for launches of several waves, and max(0.87 us, 0.56 us + 1.86 ns * resident threads) for a single partial wave
 // (0.87 us: dependent-chain latency of a lone CTA, measured on the 100^2 grid; c(NT) fitted to the compute-bound
 // moments-only rates at 8192^2: 2.02 / 2.10 / 2.14 / 2.23 ns for NT = 128 / 160 / 192 / 224 -- more, smaller CTAs hide the
-// per-row barrier better), x1.75 for the thermal kernels, x1.3 for the run-time-option kernel.  The launch cannot beat
+// per-row barrier better), x1.2 for the thermal kernels (single-precision noise on shared Philox blocks; x1.75 with the
+// double-precision generator of round 1), x1.25 for tau != 1, x1.3 for the run-time-option kernel.  The launch cannot beat
 // the HBM floor (120 B per lattice update, 48 B when the populations are not written, at 5.5 TB/s, tools/membench.cu);
 // when several widths are HBM-bound the one with the fewest halo columns per CTA that still keeps >= 3 CTAs per SM wins
 // (measured at 8192^2: NT = 224 and 160 lead, 256 with 2 CTAs/SM trails by 4 %).
@@ -50,8 +51,9 @@ int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g) {
   SW_CUDA(cudaGetDevice(&dev));
   SW_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int force_nt = env_int("SWALBE_NT", 0);
-  const int rmax = std::max(1, env_int("SWALBE_RMAX", 128));
-  const double flavour0 = (key.thermal ? 1.75 : 1.0) * (key.lean_pm > 0 ? 1.0 : 1.3);
+  // rows marched per CTA: the pipeline fill re-reads 6 rows of h (FM: of all nine populations) per chunk
+  const int rmax = std::max(1, env_int("SWALBE_RMAX", key.fm ? 256 : 128));
+  const double flavour0 = (key.thermal ? 1.2 : 1.0) * (key.lean_pm > 0 ? 1.0 : 1.3) * (key.tau1 ? 1.0 : 1.25);
   double flavour = flavour0;
   auto t_iter = [&](int ctas_on_sm, int nt) {
     return std::max(0.87, ctas_on_sm * nt * (1.80 + 0.0018 * nt) * 1e-3 * flavour);
@@ -370,7 +372,11 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   if (fm) {
     key_full.fm = key_mid.fm = true;
     if (!key_mid.opts && !key_mid.thermal && a.pc.pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0)) key_mid.lean_pm = a.pc.pmode;
-    a.fm_prefetch = std::max(0, std::min(16, env_int("SWALBE_FM_PREFETCH", 3)));
+    // measured on B200 (8192^2, tau = 0.9): the L2 prefetch changes nothing up to 3 rows ahead and costs 5-13 % beyond
+    // (profiles/r02_fm_sweep.txt), so it is off; what the second read of a row competes with in L2 is the stream of
+    // new populations, hence the residency hints
+    a.fm_prefetch = std::max(0, std::min(16, env_int("SWALBE_FM_PREFETCH", 0)));
+    a.fm_hints = env_int("SWALBE_FM_HINTS", 3) & 3;
   }
   // bulk-copy (TMA unit) row prefetch: needs 16-byte aligned row segments, i.e. even Lx and 16-B aligned planes
   auto aligned16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };

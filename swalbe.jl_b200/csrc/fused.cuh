@@ -80,6 +80,8 @@ struct FusedArgs {
   unsigned long long *log_wet;
   double hthresh;
   int fm_prefetch;  // FM kernels: rows ahead of the population loads that are prefetched into L2 (0 = off)
+  int fm_hints;     // FM kernels, L2 residency: bit 0 = streaming (evict-first) stores of the new populations, bit 1 = the
+                    // first read of a population row is kept (evict_last) for its second read three rows later
 };
 
 __device__ __forceinline__ void atomic_min_double(double *addr, double v) {
@@ -101,7 +103,7 @@ __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
   }
 }
 
-#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these nine helpers)
+#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these thirteen helpers)
 // 8-byte asynchronous global -> shared copy (LDGSTS); completion is tracked per thread by commit/wait groups,
 // not by the register scoreboard.
 __device__ __forceinline__ void cp_async8(double *smem_dst, const void *gsrc) {
@@ -133,6 +135,24 @@ __device__ __forceinline__ void bulk_g2s(double *smem_dst, const void *gsrc, uns
                : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *gsrc) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gsrc)); }
+// L2 residency hints of the FM flavour: a population row is read twice, three iterations apart; in between the CTAs
+// of the whole grid stream ~5 MB of new populations per row through the same L2
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_drop() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ldg_hint(const double *p, unsigned long long pol) {
+  double v;
+  asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;\n" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_stream(double *p, double v) { asm volatile("st.global.cs.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
   unsigned done = 0;
@@ -221,13 +241,6 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   // bulk-copy variant: one mbarrier per in-flight prefetch group (4 >= D+1), armed and fed by thread 0 only.
   // The strip's NT columns are one contiguous run of the row, or two when the strip crosses the periodic x boundary.
   __shared__ unsigned long long s_bar[4];
-  // log / sincos tables of the in-kernel noise (3 KB, thermal instantiations only)
-  __shared__ __align__(16) unsigned char s_nt_raw[THERMAL ? sizeof(NormalTables) : 16];
-  NormalTables &s_nt = *reinterpret_cast<NormalTables *>(s_nt_raw);
-  if (THERMAL) {
-    normal_tables_fill(s_nt, tid, NT);
-    __syncthreads();
-  }
   int seg_a = 0;  // columns [c_start, c_start + seg_a) then [0, NT - seg_a)
   if (BULK) {
     seg_a = min(NT, Lx - ci);  // (thread 0: ci == c_start; only thread 0 uses it)
@@ -248,13 +261,14 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   cC.init(j0 - 4, Lx, a.Ly, a.wrap_y, ci);  // cospi(theta) field: row P(1), loaded one iteration ahead
   cT.init(j0 - 6, Lx, a.Ly, a.wrap_y, ci);  // old populations (tau != 1): row F(1)
 
-  // thermal noise counter: global cell index of (row F(t), own column), advanced one row per iteration from t = 0
+  // thermal noise: global row of F(t), advanced one row per iteration from t = 0; the Philox block of a row pair
+  // (2k, 2k+1) is drawn at the even row (or at the first row this CTA computes) and its second half carried over
   long long g_row = 0;
-  unsigned long long g_cell = 0;
+  uint32_t nz_w2 = 0, nz_w3 = 0;
+  bool nz_have = false;
   if (THERMAL) {
     g_row = (a.jglobal0 + (long long)(j0 - 7)) % a.Ly_global;
     if (g_row < 0) g_row += a.Ly_global;
-    g_cell = (unsigned long long)Lx * (unsigned long long)g_row + (unsigned long long)ci;
   }
 
   // own-column populations that move along y only: f*0 of rows F(t-1), F(t-2); f*2 of F(t-1..t-3); f*4 of F(t-1)
@@ -274,6 +288,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   const int slipv = OPTS ? a.sc.variant : SWALBE_SLIP_STANDARD;
   const long long fs_in8 = (long long)a.fstride_in * 8, fs_out8 = (long long)a.fstride_out * 8,
                   fs_out2_8 = (long long)a.fstride_out2 * 8;
+
+  const unsigned long long pol_keep = FM ? l2_policy_keep() : 0ull, pol_drop = FM ? l2_policy_drop() : 0ull;
 
   // one pipeline iteration; `steady` is a compile-time tag: std::true_type drops every stage predicate
   auto iter = [&](const int t, auto steady) {
@@ -343,14 +359,24 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
       double fm_n[9];
       const bool need_m = FM && (S || t <= R + 5);  // row N(t+1) = j0-3+t is needed for t+1 in [1, R+6]
       if (need_m) {
+        if (a.fm_hints & 2) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) fm_n[k] = __ldg(at(a.f_in, offN + k * fs_in8));
+          for (int k = 0; k < 9; ++k) fm_n[k] = ldg_hint(at(a.f_in, offN + k * fs_in8), pol_keep);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) fm_n[k] = __ldg(at(a.f_in, offN + k * fs_in8));
+        }
       }
       double ft_n[9];
       if (!TAU1) {
         if (S || (t >= 5 && t <= R + 6)) {  // row F(t+1) = j0-6+t in [j0-1, j0+R]
+          if (FM && (a.fm_hints & 2)) {
 #pragma unroll
-          for (int k = 0; k < 9; ++k) ft_n[k] = __ldg(at(a.f_in, cT.off + k * fs_in8));
+            for (int k = 0; k < 9; ++k) ft_n[k] = ldg_hint(at(a.f_in, cT.off + k * fs_in8), pol_drop);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) ft_n[k] = __ldg(at(a.f_in, cT.off + k * fs_in8));
+          }
         }
         cT.advance(row_bytes, wrapLy, col_bytes);
       }
@@ -388,7 +414,17 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         double kx = 0.0, ky = 0.0;
         const int rF = j0 - 7 + t;
         if (THERMAL) {
-          thermal_pair(hc, a.tc, a.pk, a.step, g_cell, s_nt, kx, ky);
+          const bool odd = (g_row & 1) != 0;  // (CTA-uniform)
+          uint32_t w0, w1;
+          if (!odd || !nz_have) {
+            uint32_t r[4];
+            noise_block(a.pk, a.step, noise_pair_index(Lx, g_row, ci), r);
+            nz_w2 = r[2]; nz_w3 = r[3]; nz_have = true;
+            w0 = odd ? r[2] : r[0]; w1 = odd ? r[3] : r[1];
+          } else {
+            w0 = nz_w2; w1 = nz_w3;
+          }
+          thermal_from_words(hc, a.tc, w0, w1, kx, ky);
           Fx = Fx - kx;
           Fy = Fy - ky;
         }
@@ -439,7 +475,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         if (want_m) moments_site(fn, hn, uxn, uyn);
         if (col_out) {
           if (want_m) { *at(a.h_out, cO.off) = hn; *at(a.ux_out, cO.off) = uxn; *at(a.uy_out, cO.off) = uyn; }
-          if (a.f_out != nullptr) {
+          if (FM && (a.fm_hints & 1)) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) st_stream(at(a.f_out, cO.off + k * fs_out8), fn[k]);
+          } else if (a.f_out != nullptr) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) *at(a.f_out, cO.off + k * fs_out8) = fn[k];
             if (a.f_out2 != nullptr) {
@@ -450,9 +489,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         }
       }
       cO.advance(row_bytes, wrapLy, col_bytes);
-      if (THERMAL) {  // global (row F(t+1), own column)
-        g_cell += (unsigned long long)Lx;
-        if (++g_row == a.Ly_global) { g_row = 0; g_cell = (unsigned long long)ci; }
+      if (THERMAL) {  // global row of F(t+1)
+        if (++g_row == a.Ly_global) g_row = 0;
       }
       ct_c = ct_n;
       f0_b = f0_a; f0_a = fs0;

@@ -166,12 +166,9 @@ __global__ void __launch_bounds__(BX *BY) k_force_sum(double *__restrict__ Fx, d
 __global__ void __launch_bounds__(BX *BY) k_thermal(double *__restrict__ kx, double *__restrict__ ky,
                                                      const double *__restrict__ h, ThermalConsts tc,
                                                      PhiloxKey key, unsigned long long step, int Lx, int Ly) {
-  __shared__ NormalTables s_nt;
-  normal_tables_fill(s_nt, threadIdx.y * BX + threadIdx.x, BX * BY);
-  __syncthreads();
   SITE_GUARD();
   double a, b;
-  thermal_pair(h[c], tc, key, step, (unsigned long long)c, s_nt, a, b);
+  thermal_pair(h[c], tc, key, step, Lx, (long long)j, i, a, b);
   kx[c] = a;
   ky[c] = b;
 }

@@ -52,8 +52,6 @@ int emul_step(double *h, double *ux, double *uy, double *fout, const double *fte
   volatile double it = 1.0 / tau;
   volatile double om = 1.0 - it;
   double *p = scratch, *fs = scratch + N;  // pressure, 9 post-collision planes
-  static NormalTables T;
-  normal_tables_fill(T, 0, 1);
   const ThermalConsts tc = make_thermal(kbt, mu, delta);
   const PhiloxKey K = make_philox_key(seed);
   for (int j = 0; j < Ly; ++j)
@@ -79,7 +77,7 @@ int emul_step(double *h, double *ux, double *uy, double *fout, const double *fte
       double Fx = (-hgx) - sx, Fy = (-hgy) - sy;
       if (kbt > 0.0) {  // thermal!: in-kernel noise keyed on (seed, step, global cell)
         double kx, ky;
-        thermal_pair(hc, tc, K, step, (unsigned long long)c, T, kx, ky);
+        thermal_pair(hc, tc, K, step, Lx, (long long)j, i, kx, ky);
         Fx = Fx - kx;
         Fy = Fy - ky;
       }
@@ -129,14 +127,13 @@ void emul_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) 
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], K, out);
 }
 
-// thermal_pair (noise amplitude x table-driven normals) for cells [0, n) of step `step`
-void emul_thermal(double *kx, double *ky, const double *h, long n, double kbt, double mu, double delta,
+// thermal_pair (single-precision Box-Muller on shared Philox blocks x amplitude) for the cells of an Lx-wide lattice:
+// cell c = i + Lx * j for c in [0, n)
+void emul_thermal(double *kx, double *ky, const double *h, long n, int Lx, double kbt, double mu, double delta,
                   unsigned long long seed, unsigned long long step) {
-  static NormalTables T;
-  normal_tables_fill(T, 0, 1);
   const ThermalConsts tc = make_thermal(kbt, mu, delta);
   const PhiloxKey K = make_philox_key(seed);
-  for (long c = 0; c < n; ++c) thermal_pair(h[c], tc, K, step, (unsigned long long)c, T, kx[c], ky[c]);
+  for (long c = 0; c < n; ++c) thermal_pair(h[c], tc, K, step, Lx, (long long)(c / Lx), (int)(c % Lx), kx[c], ky[c]);
 }
 
 }  // extern "C"

@@ -70,7 +70,7 @@ static inline void __trap() { abort(); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 
-// ---- the nine asynchronous-copy helpers of fused.cuh, as immediate copies / no-ops -----------------------------------------
+// ---- the thirteen asynchronous-copy / cache-hint helpers of fused.cuh, as immediate copies / plain accesses / no-ops -----------------------------------------
 static inline void cp_async8(double *smem_dst, const void *gsrc) { *smem_dst = *(const double *)gsrc; }
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
@@ -80,6 +80,10 @@ static inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
 static inline void bulk_g2s(double *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *) { memcpy(smem_dst, gsrc, bytes); }
 static inline void mbar_wait(unsigned long long *, unsigned) {}
 static inline void prefetch_l2(const void *) {}
+static inline unsigned long long l2_policy_keep() { return 1; }
+static inline unsigned long long l2_policy_drop() { return 2; }
+static inline double ldg_hint(const double *p, unsigned long long) { return *p; }
+static inline void st_stream(double *p, double v) { *p = v; }
 
 #include "../swalbe.jl_b200/csrc/tile.cuh"  // (includes fused.cuh and common.cuh)
 
@@ -199,6 +203,7 @@ int simt_step(const SimtStep *s) {
   a.Fx = s->Fx; a.Fy = s->Fy; a.feq = s->feq; a.vsq = s->vsq;
   a.log_min = s->log_min; a.log_max = s->log_max; a.log_wet = s->log_wet; a.hthresh = s->hthresh;
   a.fm_prefetch = s->fm_prefetch;
+  a.fm_hints = s->fm_prefetch ? 3 : 0;  // (the hinted and the plain code paths both run in the FM test)
   const bool gz = s->g == 0.0, tau1 = s->tau == 1.0;
   const int pm = a.pc.pmode;
   kernel_fn k = nullptr;

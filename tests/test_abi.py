@@ -180,9 +180,22 @@ def test_julia_glue_binds_existing_symbols_with_matching_types():
         assert got == protos[name], f"{name}: Julia {got} vs C {protos[name]}"
         assert ret in ("Cint", "Cstring", "Culonglong"), (name, ret)
     bound = {c[0] for c in calls}
-    for must in ("swalbe_equilibrium_d2q9", "swalbe_bgk_stream_d2q9", "swalbe_moments_d2q9", "swalbe_filmpressure",
-                 "swalbe_hgradp", "swalbe_slippage", "swalbe_time_loop", "swalbe_plan_create", "swalbe_last_error"):
-        assert must in bound, must
+    # every symbol of the header except the two self-tests must be reachable from Julia, the host language north_star
+    # names -- the multi-GPU slab runtime (swalbe_dist_*) included
+    missing = sorted(n for n in protos if n not in bound and not n.startswith("swalbe_selftest_"))
+    assert not missing, f"header symbols without a ccall in SwalbeB200.jl: {missing}"
+    # no type piracy: the glue adds methods to Swalbe's functions and its own, never to Base / CUDA functions
+    assert not re.search(r"^\s*function\s+(?:Base|CUDA|GPUArrays)\.[\w!]+\(", src, flags=re.M)
+    assert not re.search(r"^(?:Base|CUDA|GPUArrays)\.[\w!]+\([^\n]*\)\s*=", src, flags=re.M)
+    # a finalizer may only be attached to a mutable object; CuState / CuState_thermal are immutable (src/initialize.jl:214)
+    for m in re.finditer(r"finalizer\(([^,]+),\s*([^)]+)\)", src):
+        assert "state" not in m.group(2), m.group(0)
+    # the flag values of the header
+    hdr = open(os.path.join(ROOT, "include", "swalbe_b200.h")).read()
+    for name in ("LOOP_LAZY_POPULATIONS", "LOOP_SKIP_AUX", "LOOP_MOMENTS_CONSISTENT", "PRESSURE_POWER_BROAD", "PRESSURE_FAST"):
+        c = int(re.search(r"#define SWALBE_%s (\d+)" % name, hdr).group(1))
+        j = int(re.search(r"const %s = Cint\((\d+)\)" % name, src).group(1))
+        assert c == j, name
     # block balance (function/struct/if/while/do/module ... end), comments and strings stripped
     body = "\n".join(re.sub(r"#.*$", "", re.sub(r'"(?:\\.|[^"\\])*"', '""', ln)) for ln in
                      re.sub(r'"""(?:.|\n)*?"""', '""', src).splitlines())

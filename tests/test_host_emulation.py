@@ -28,7 +28,7 @@ def emul(tmp_path_factory):
     lib.emul_division_mismatches.argtypes = [_p, _p, C.c_long]
     lib.emul_division_mismatches.restype = C.c_long
     lib.emul_philox.argtypes = [_p, _p, _p]
-    lib.emul_thermal.argtypes = [_p, _p, _p, C.c_long, _d, _d, _d, C.c_ulonglong, C.c_ulonglong]
+    lib.emul_thermal.argtypes = [_p, _p, _p, C.c_long, C.c_int, _d, _d, _d, C.c_ulonglong, C.c_ulonglong]
     return lib
 
 
@@ -121,11 +121,11 @@ def test_thermal_pair_statistics_on_host(emul):
     h = np.full(n, 1.3)
     kx, ky = np.zeros(n), np.zeros(n)
     kbt, mu, delta = 1e-6, 1 / 6, 1.0
-    emul.emul_thermal(_ptr(kx), _ptr(ky), _ptr(h), n, kbt, mu, delta, 42, 7)
+    emul.emul_thermal(_ptr(kx), _ptr(ky), _ptr(h), n, 500, kbt, mu, delta, 42, 7)
     var = 2 * kbt * mu * 6 * 1.3 / (2 * 1.3 * 1.3 + 6 * 1.3 * delta + 3 * delta * delta)
     for k in (kx, ky):
         assert abs(k.mean()) < 4 * np.sqrt(var / n) and abs(k.var() / var - 1) < 0.01
     assert abs(np.mean(kx * ky)) < 4 * var / np.sqrt(n)
     kx2 = np.zeros(n)
-    emul.emul_thermal(_ptr(kx2), _ptr(ky), _ptr(h), n, kbt, mu, delta, 42, 7)
+    emul.emul_thermal(_ptr(kx2), _ptr(ky), _ptr(h), n, 500, kbt, mu, delta, 42, 7)
     assert np.array_equal(kx, kx2)  # counter-based: reproducible
