@@ -25,8 +25,8 @@ static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
 static fused_fn pick_kernel(const Variant &var, const KernelKey &k) {
   if (k.fm) return k.lean_pm > 0 ? var.fm_lean[k.lean_pm][k.gz ? 1 : 0] : var.fm_full[k.thermal ? 1 : 0];
   if (k.lean_pm > 0 && k.opts) return var.opts[k.thermal ? 1 : 0][k.lean_pm];
-  if (k.lean_pm > 0 && k.bulk) return var.bulk[k.lean_pm][k.gz ? 1 : 0];
-  if (k.lean_pm > 0) return var.lean[k.thermal ? 1 : 0][k.lean_pm][k.gz ? 1 : 0];
+  if (k.lean_pm > 0 && k.bulk) return (k.ns ? var.bulk_ns : var.bulk)[k.lean_pm][k.gz ? 1 : 0];
+  if (k.lean_pm > 0) return (k.ns ? var.lean_ns : var.lean)[k.thermal ? 1 : 0][k.lean_pm][k.gz ? 1 : 0];
   return var.full[k.tau1 ? 1 : 0][k.thermal ? 1 : 0];
 }
 
@@ -178,6 +178,7 @@ KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean) {
   k.gz = p.g == 0.0;
   k.lazy = false;
   k.fm = false;
+  k.ns = env_int("SWALBE_NSYNC", 0) != 0;  // (honoured by the strict lean tau == 1 kernels only)
   k.opts = p.cospi_theta_field != nullptr || p.slip_variant != SWALBE_SLIP_STANDARD || p.use_inclination != 0;
   if (want_lean && k.tau1 && pmode != PM_GENERIC && !env_int("SWALBE_NO_LEAN", 0))
     k.lean_pm = pmode;
@@ -224,18 +225,23 @@ struct swalbe_plan {
   GraphKey graph_key, seen_key;
   bool have_graph, have_seen;
   int graph_nsteps;
-  LaunchGeom geom[2][2][5][2][2][2][2][2];  // [tau1][thermal][lean_pm][bulk][gz][lazy][opts][fm]
-  bool geom_ok[2][2][5][2][2][2][2][2];
+  // launch geometry per kernel flavour, chosen the first time the flavour is used
+  struct GeomEntry { KernelKey key; LaunchGeom geom; };
+  GeomEntry geoms[32];
+  int ngeoms;
 };
 
 static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
-  LaunchGeom &gg = plan->geom[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts][k.fm];
-  bool &ok = plan->geom_ok[k.tau1][k.thermal][k.lean_pm][k.bulk][k.gz][k.lazy][k.opts][k.fm];
-  if (!ok) {
-    if (int e = choose_geometry(plan->Lx, plan->Ly, k, &gg)) return e;
-    ok = true;
-  }
-  *g = &gg;
+  auto same = [](const KernelKey &x, const KernelKey &y) {
+    return x.tau1 == y.tau1 && x.thermal == y.thermal && x.lean_pm == y.lean_pm && x.bulk == y.bulk && x.gz == y.gz &&
+           x.lazy == y.lazy && x.opts == y.opts && x.fm == y.fm && x.ns == y.ns;
+  };
+  for (int q = 0; q < plan->ngeoms; ++q)
+    if (same(plan->geoms[q].key, k)) { *g = &plan->geoms[q].geom; return 0; }
+  const int slot = plan->ngeoms < 32 ? plan->ngeoms++ : 31;  // (a plan sees a handful of flavours; the last slot is recycled)
+  plan->geoms[slot].key = k;
+  if (int e = choose_geometry(plan->Lx, plan->Ly, k, &plan->geoms[slot].geom)) { plan->ngeoms = slot; return e; }
+  *g = &plan->geoms[slot].geom;
   return 0;
 }
 
@@ -247,7 +253,7 @@ int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly) {
   swalbe_plan *p = new swalbe_plan();
   p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr;
   p->cap_stream = nullptr; p->graph_exec = nullptr; p->have_graph = p->have_seen = false; p->graph_nsteps = 0;
-  memset(p->geom_ok, 0, sizeof(p->geom_ok));
+  p->ngeoms = 0;
   cudaError_t e = cudaMalloc((void **)&p->scratch, sizeof(double) * 3 * (size_t)Lx * Ly);
   if (e != cudaSuccess) {
     delete p;
@@ -376,7 +382,9 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
     // (profiles/r02_fm_sweep.txt), so it is off; what the second read of a row competes with in L2 is the stream of
     // new populations, hence the residency hints
     a.fm_prefetch = std::max(0, std::min(16, env_int("SWALBE_FM_PREFETCH", 0)));
-    a.fm_hints = env_int("SWALBE_FM_HINTS", 3) & 3;
+    // streaming stores: +1.3 %; evict_last / evict_first on the two reads cut the DRAM traffic from 160 to 146 B per
+    // update but expose the DRAM latency of the first read (26 % of the stall samples on its first use): 3 % slower
+    a.fm_hints = env_int("SWALBE_FM_HINTS", 1) & 7;
   }
   // bulk-copy (TMA unit) row prefetch: needs 16-byte aligned row segments, i.e. even Lx and 16-B aligned planes
   auto aligned16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };

@@ -38,6 +38,14 @@
 // N(t+1) (L2-prefetched a few rows ahead), folds them into h for the h ring, and stage C derives u from the populations
 // it needs for the collision anyway.  HBM traffic: 72 B read + 72 B written per lattice update -- the D2Q9 figure.
 //
+// NS flavour ("neighbour sync"): the per-row __syncthreads is replaced by warp-to-warp hand-shakes.  Only x-shifted values
+// cross threads, so a warp that starts iteration t+1 needs exactly its two neighbour warps to have finished iteration t
+// (their ring writes visible: RAW; their reads of the slots it is about to overwrite done: WAR -- every slot written in
+// iteration t+1 was last read in iteration t or earlier).  Each warp owns two mbarriers (even / odd iterations, 32
+// arrivals); a warp arrives on its own and waits on its neighbours'.  Neighbours are never more than one iteration
+// apart, so the two-deep ring cannot alias a phase.  Rows are prefetched per warp: per-thread LDGSTS as before, or --
+// BULK -- lane 0 of every warp moves its warp's 32 columns through the TMA unit onto a per-warp mbarrier.
+//
 // All arithmetic comes from common.cuh (reference evaluation order, no FMA contraction).
 #pragma once
 #include <limits.h>
@@ -81,7 +89,8 @@ struct FusedArgs {
   double hthresh;
   int fm_prefetch;  // FM kernels: rows ahead of the population loads that are prefetched into L2 (0 = off)
   int fm_hints;     // FM kernels, L2 residency: bit 0 = streaming (evict-first) stores of the new populations, bit 1 = the
-                    // first read of a population row is kept (evict_last) for its second read three rows later
+                    // first read of a population row is kept (evict_last) for its second read three rows later, which
+                    // is marked evict_first; bit 2 = the L2 prefetch (fm_prefetch rows ahead) carries the evict_last priority
 };
 
 __device__ __forceinline__ void atomic_min_double(double *addr, double v) {
@@ -103,7 +112,7 @@ __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
   }
 }
 
-#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these thirteen helpers)
+#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these eighteen helpers)
 // 8-byte asynchronous global -> shared copy (LDGSTS); completion is tracked per thread by commit/wait groups,
 // not by the register scoreboard.
 __device__ __forceinline__ void cp_async8(double *smem_dst, const void *gsrc) {
@@ -135,6 +144,7 @@ __device__ __forceinline__ void bulk_g2s(double *smem_dst, const void *gsrc, uns
                : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *gsrc) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gsrc)); }
+__device__ __forceinline__ void prefetch_l2_keep(const void *gsrc) { asm volatile("prefetch.global.L2::evict_last [%0];\n" ::"l"(gsrc)); }
 // L2 residency hints of the FM flavour: a population row is read twice, three iterations apart; in between the CTAs
 // of the whole grid stream ~5 MB of new populations per row through the same L2
 __device__ __forceinline__ unsigned long long l2_policy_keep() {
@@ -153,6 +163,15 @@ __device__ __forceinline__ double ldg_hint(const double *p, unsigned long long p
   return v;
 }
 __device__ __forceinline__ void st_stream(double *p, double v) { asm volatile("st.global.cs.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity);
+// warp hand-shake of the NS flavour (emulated with real atomics on the CPU, unlike the data barriers above)
+__device__ __forceinline__ void ns_init(unsigned long long *bar, unsigned count) { mbar_init(bar, count); }
+__device__ __forceinline__ void ns_arrive(unsigned long long *bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory");  // (release at CTA scope)
+}
+__device__ __forceinline__ void ns_wait(unsigned long long *bar, unsigned parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void ns_syncwarp() { __syncwarp(); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
   unsigned done = 0;
@@ -202,9 +221,10 @@ constexpr int FUSED_LINES = FUSED_H_SLOTS + 4 * R4_LINES + 2 * R2_LINES + 4 * RU
 constexpr int FUSED_PAD = 2;
 constexpr size_t fused_smem_doubles(int NT) { return (size_t)FUSED_LINES * (NT + 2 * FUSED_PAD); }
 
-template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS, bool FM = false>
+template <int NT, int MINB, bool TAU1, bool THERMAL, int PM, bool BULK, bool GZ, bool OPTS, bool FM = false, bool NS = false>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ FusedArgs a) {
   static_assert(!FM || (!TAU1 && !BULK), "the from-moments flavour exists for tau != 1 (at tau == 1 no population is read)");
+  static_assert(!NS || (NT % 32 == 0 && NT / 32 <= 8 && !FM), "neighbour sync: whole warps, at most 8 per CTA");
 #ifdef SW_HOST_EMULATION
   double *const smem = emul_dynamic_smem();
 #else
@@ -242,7 +262,20 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   // The strip's NT columns are one contiguous run of the row, or two when the strip crosses the periodic x boundary.
   __shared__ unsigned long long s_bar[4];
   int seg_a = 0;  // columns [c_start, c_start + seg_a) then [0, NT - seg_a)
-  if (BULK) {
+  // NS: two hand-shake barriers per warp (even / odd iterations) and, with BULK, four data barriers per warp
+  constexpr int NW = NT / 32;
+  __shared__ unsigned long long s_done[NS ? 2 : 1][8];
+  __shared__ unsigned long long s_wbar[NS && BULK ? 8 : 1][4];
+  const int wid = tid >> 5, lane = tid & 31;
+  if (NS) {
+    seg_a = min(32, Lx - ci);  // (lane 0 of a warp: ci is the warp's first column)
+    if (tid < 32) {
+      if (tid < 16) ns_init(&s_done[tid >> 3][tid & 7], 32);
+      if (BULK) mbar_init(&s_wbar[tid >> 2][tid & 3], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  } else if (BULK) {
     seg_a = min(NT, Lx - ci);  // (thread 0: ci == c_start; only thread 0 uses it)
     if (tid == 0) {
 #pragma unroll
@@ -298,8 +331,13 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     const long long offN = cN.off;  // FM: row N(t+1)
     if (FM) {
       if (a.fm_prefetch > 0) {  // (FM launches are periodic in y, wrap_y == 1: every row the cursor reaches exists)
+        if (a.fm_hints & 4) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) prefetch_l2(at(a.f_in, cPf.off + k * fs_in8));
+          for (int k = 0; k < 9; ++k) prefetch_l2_keep(at(a.f_in, cPf.off + k * fs_in8));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) prefetch_l2(at(a.f_in, cPf.off + k * fs_in8));
+        }
       }
       cPf.advance(row_bytes, wrapLy, col_bytes);
       cN.advance(row_bytes, wrapLy, col_bytes);
@@ -307,9 +345,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
       const int tn = t + D;  // h row N(tn) = j0-4+tn is needed for tn in [1, R+6]; u rows F(tn) for tn in [6, R+7]
       const bool need_h = S || (tn >= 1 && tn <= R + 6), need_u = S || (tn >= 6 && tn <= R + 7);
       if (BULK) {
-        if (tid == 0) {
-          unsigned long long *bar = &s_bar[tn & 3];
-          const unsigned nb = (unsigned)NT * 8u;
+        if (NS ? lane == 0 : tid == 0) {
+          unsigned long long *bar = NS ? &s_wbar[wid][tn & 3] : &s_bar[tn & 3];
+          const unsigned nb = (unsigned)(NS ? 32 : NT) * 8u;
           mbar_arrive_expect_tx(bar, (need_h ? nb : 0u) + (need_u ? 2u * nb : 0u));  // 0 bytes: completes at once
           const unsigned ba = (unsigned)seg_a * 8u, bb = nb - ba;
           if (need_h) {
@@ -503,9 +541,19 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
       if (need_m) sh[((t + 1) & 7) * LW] = height_site(fm_n);  // h row N(t+1) into its ring slot (free since iteration t-3)
     }
     // the prefetch issued D-1 iterations ago (h row N(t+1), u rows F(t+1)) must have landed before the next iteration
-    if (BULK) mbar_wait(&s_bar[(t + 1) & 3], (unsigned)((t + 1) >> 2) & 1u);
+    if (BULK) mbar_wait(NS ? &s_wbar[wid][(t + 1) & 3] : &s_bar[(t + 1) & 3], (unsigned)((t + 1) >> 2) & 1u);
     else if (!FM) cp_async_wait<D - 1>();
-    __syncthreads();
+    if (NS) {
+      const int tt = t + D;  // >= 0
+      unsigned long long *mine = &s_done[tt & 1][wid];
+      const unsigned par = (unsigned)(tt >> 1) & 1u;
+      ns_arrive(mine);
+      if (wid > 0) ns_wait(mine - 1, par);
+      if (wid < NW - 1) ns_wait(mine + 1, par);
+      ns_syncwarp();  // the lanes of this warp exchange x-neighbours among themselves, too
+    } else {
+      __syncthreads();
+    }
   };
 
   // ... and do not touch global memory before the previous step's grid has completed and flushed its writes.

@@ -26,6 +26,7 @@ struct KernelKey {
   bool lazy;  // populations are not written by this launch (geometry only: lower HBM floor)
   bool opts;  // lean kernel that takes theta field / slip variant / inclination / logs at run time
   bool fm;    // tau != 1: height / velocity derived from the streamed populations instead of read from their planes
+  bool ns;    // strict lean kernels: neighbour-warp hand-shake instead of the per-row CTA barrier
 };
 
 int choose_geometry(int Lx, int nrows, const KernelKey &key, LaunchGeom *g);

@@ -22,11 +22,12 @@ tile_fn pick_tile(int pm) {
 }  // namespace
 
 // A contact-angle field and nothing else (standard slip, no inclination, no logs: the moving-wettability scripts, mostly
-// 512^2) can take the TF instantiations.  OFF unless SWALBE_TILE_THETA=1: bit parity is established on the CPU (SIMT
-// emulation, tests/test_simt_emulation.py), the GPU measurement that should flip the default is still to be done.
+// 512^2) takes the TF instantiations.  Measured on B200 (profiles/r02_probes_call2.txt, 98-step loops, graph replay):
+// 256^2 10.9 -> 9.6 us/step, 384^2 14.9 -> 9.2, 512^2 18.2 -> 15.2 against the run-time-option marching kernel, equal
+// at 128^2; bit parity on the CPU emulation and on the GPU (tests).  SWALBE_TILE_THETA=0 switches it off.
 static bool tile_theta_enabled() {
   const char *s = getenv("SWALBE_TILE_THETA");
-  return s && *s && atoi(s) != 0;
+  return !(s && *s) || atoi(s) != 0;
 }
 
 bool tile_eligible(const KernelKey &k, const FusedArgs &a) {

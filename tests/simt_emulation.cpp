@@ -12,6 +12,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <sched.h>
+
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -80,10 +83,37 @@ static inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
 static inline void bulk_g2s(double *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *) { memcpy(smem_dst, gsrc, bytes); }
 static inline void mbar_wait(unsigned long long *, unsigned) {}
 static inline void prefetch_l2(const void *) {}
+static inline void prefetch_l2_keep(const void *) {}
 static inline unsigned long long l2_policy_keep() { return 1; }
 static inline unsigned long long l2_policy_drop() { return 2; }
 static inline double ldg_hint(const double *p, unsigned long long) { return *p; }
 static inline void st_stream(double *p, double v) { *p = v; }
+// the warp hand-shake of the NS flavour is emulated FOR REAL (atomics, OS threads that run ahead of each other): this is
+// what the flavour's correctness rests on -- a warp may only see its neighbours' ring slots through these barriers
+struct EmuNsBar {
+  std::atomic<uint32_t> arrived, phase;
+};
+static_assert(sizeof(EmuNsBar) == 8, "one mbarrier word");
+static uint32_t g_ns_expected = 32;
+static inline void ns_init(unsigned long long *bar, unsigned count) {
+  EmuNsBar *b = reinterpret_cast<EmuNsBar *>(bar);
+  b->arrived.store(0); b->phase.store(0);
+  g_ns_expected = count;
+}
+static inline void ns_arrive(unsigned long long *bar) {
+  EmuNsBar *b = reinterpret_cast<EmuNsBar *>(bar);
+  if (b->arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == g_ns_expected) {
+    b->arrived.store(0, std::memory_order_relaxed);
+    b->phase.fetch_add(1, std::memory_order_release);
+  }
+}
+static inline void ns_wait(unsigned long long *bar, unsigned parity) {
+  EmuNsBar *b = reinterpret_cast<EmuNsBar *>(bar);
+  while ((b->phase.load(std::memory_order_acquire) & 1u) == parity) sched_yield();
+}
+static inline void ns_syncwarp();
+
+static inline void ns_syncwarp() { pthread_barrier_wait(&g_warp_barrier[threadIdx.x >> 5]); }
 
 #include "../swalbe.jl_b200/csrc/tile.cuh"  // (includes fused.cuh and common.cuh)
 
@@ -127,6 +157,16 @@ static kernel_fn lean_kernel(int pm) {
     default: return nullptr;
   }
 }
+template <bool GZ, bool BULK, bool TH = false>
+static kernel_fn ns_kernel(int pm) {  // neighbour-sync flavour (no CTA barrier in the row loop)
+  switch (pm) {
+    case PM_BROAD_93: return k_fused_step<ENT, 3, true, TH, PM_BROAD_93, BULK, GZ, false, false, true>;
+    case PM_BROAD_32: return k_fused_step<ENT, 3, true, TH, PM_BROAD_32, BULK, GZ, false, false, true>;
+    case PM_FAST_93: return k_fused_step<ENT, 3, true, TH, PM_FAST_93, BULK, GZ, false, false, true>;
+    case PM_FAST_32: return k_fused_step<ENT, 3, true, TH, PM_FAST_32, BULK, GZ, false, false, true>;
+    default: return nullptr;
+  }
+}
 template <bool GZ>
 static kernel_fn thermal_kernel(int pm) {
   switch (pm) {
@@ -163,7 +203,8 @@ extern "C" {
 struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop put into FusedArgs
   int flavour;     // 0 strict lean, 1 OPTS lean, 2 FULL, 3 strict lean with bulk row prefetch, 4 tile kernel,
                    // 5 strict lean with in-kernel thermal noise, 6 strict lean with CTAs of 224 threads,
-                   // 7 tau != 1 strict lean from-moments (FM), 8 tau != 1 FULL from-moments
+                   // 7 tau != 1 strict lean from-moments (FM), 8 tau != 1 FULL from-moments,
+                   // 9 / 10 / 11 neighbour-sync strict lean: LDGSTS rows / per-warp bulk rows / with thermal noise
   int Lx, Ly, jbeg, jend, W, rows_per_cta, wrap_y;
   double tau, mu, delta, gamma, hmin, hcrit, g, cospi_theta;
   int n, m, pressure_variant, slip_variant, use_incl;
@@ -203,7 +244,7 @@ int simt_step(const SimtStep *s) {
   a.Fx = s->Fx; a.Fy = s->Fy; a.feq = s->feq; a.vsq = s->vsq;
   a.log_min = s->log_min; a.log_max = s->log_max; a.log_wet = s->log_wet; a.hthresh = s->hthresh;
   a.fm_prefetch = s->fm_prefetch;
-  a.fm_hints = s->fm_prefetch ? 3 : 0;  // (the hinted and the plain code paths both run in the FM test)
+  a.fm_hints = s->fm_prefetch ? 7 : 0;  // (the hinted and the plain code paths both run in the FM test)
   const bool gz = s->g == 0.0, tau1 = s->tau == 1.0;
   const int pm = a.pc.pmode;
   kernel_fn k = nullptr;
@@ -224,6 +265,9 @@ int simt_step(const SimtStep *s) {
     launch(k, (s->Lx + s->W - 1) / s->W, (s->jend - s->jbeg + s->rows_per_cta - 1) / s->rows_per_cta, 224, fused_smem_doubles(224), a);
     return 0;
   }
+  else if (s->flavour == 9) k = gz ? ns_kernel<true, false>(pm) : ns_kernel<false, false>(pm);
+  else if (s->flavour == 10) k = gz ? ns_kernel<true, true>(pm) : ns_kernel<false, true>(pm);
+  else if (s->flavour == 11) k = gz ? ns_kernel<true, false, true>(pm) : ns_kernel<false, false, true>(pm);
   else if (s->flavour == 7) k = tau1 ? nullptr : gz ? fm_kernel<true>(pm) : fm_kernel<false>(pm);
   else if (s->flavour == 8) k = tau1 ? nullptr : (kernel_fn)k_fused_step<ENT, 3, false, false, -1, false, false, true, true>;
   else if (s->flavour == 2) k = tau1 ? (kernel_fn)k_fused_step<ENT, 5, true, false, -1, false, false, true>

@@ -145,6 +145,31 @@ def test_general_tau_from_moments_kernels(sw, prm_kw, monkeypatch, small_lattice
     assert np.array_equal((mx - mn).cpu().numpy(), np.asarray(dh)) and wet.cpu().tolist() == [int(v) for v in w]
 
 
+@pytest.mark.parametrize("tile_theta", ["1", "0"], ids=["tile", "marching"])
+@pytest.mark.parametrize("Lx,Ly", [(33, 9), (70, 20), (130, 64), (256, 96)])
+def test_contact_angle_field_small_lattices(sw, monkeypatch, tile_theta, Lx, Ly):
+    """θ(x, y) and nothing else -- the moving-wettability scripts (scripts/Moving_wettability_structs.jl:28-71) at their
+    lattice sizes: the tile kernel instantiated for a contact-angle field (default below SWALBE_TILE_MAX sites) and the
+    run-time-option marching kernel (SWALBE_TILE_THETA=0) against the oracle, with a substrate move in the middle."""
+    monkeypatch.setenv("SWALBE_TILE_THETA", tile_theta)
+    rng = np.random.default_rng(Lx)
+    theta = np.asfortranarray(1 / 9 + 1 / 36 * rng.random((Lx, Ly)))
+    for kw, pv in ((dict(n=3, m=2, hmin=0.07), None), (dict(g=-0.001), "fast")):
+        st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx + Ly, prm_kw=kw)
+        th, inp = sw.Field(Lx, Ly).set(theta), sw.Field(Lx, Ly).set(theta)
+        from swalbe_b200 import _lib
+
+        opt = dict(pressure_variant=_lib.PRESSURE_FAST) if pv else {}
+        ct0 = sw.cospi_field(th).numpy()
+        sw.fused_steps(st, sysc, 4, θ=th, skip_aux=True, **opt)
+        sw.move_substrate(th, inp, 98, 98)
+        sw.fused_steps(st, sysc, 3, θ=th, **opt)
+        okw = dict(pvariant="fast") if pv else {}
+        oc.time_loop(ref, p, nsteps=4, cospi_theta=ct0, **okw)
+        oc.time_loop(ref, p, nsteps=3, cospi_theta=onp.circshift(ct0, (1, 1)), **okw)
+        _compare(st, ref, what=f"theta {Lx}x{Ly}:")
+
+
 def test_fused_equals_operator_by_operator_on_gpu(sw):
     """The fused kernel against the seven per-operator kernels run in the reference's order (both on the GPU)."""
     st, sysc, _, _ = _mk(sw, 130, 61, seed=21, prm_kw=dict(g=0.001))
@@ -193,6 +218,35 @@ def test_geometry_overrides_do_not_change_bits(sw, monkeypatch):
             base = cur
         for n in STATE_FIELDS:
             assert np.array_equal(base[n], cur[n]), (nt, rows, n)
+
+
+@pytest.mark.parametrize("bulk", ["0", "2"], ids=["ldgsts", "per-warp-bulk"])
+def test_neighbour_sync_kernels_same_bits(sw, monkeypatch, bulk):
+    """SWALBE_NSYNC=1: the strict lean kernels that replace the per-row CTA barrier by warp-to-warp mbarrier hand-shakes
+    (per-thread LDGSTS rows and per-warp TMA rows) against the oracle and against the thermal kernel with the barrier."""
+    monkeypatch.setenv("SWALBE_NSYNC", "1")
+    monkeypatch.setenv("SWALBE_TILE_MAX", "0")
+    monkeypatch.setenv("SWALBE_BULK", bulk)
+    for (Lx, Ly), nt in (((600, 130), 0), ((512, 96), 224), ((300, 90), 128), ((258, 40), 160)):
+        if nt:
+            monkeypatch.setenv("SWALBE_NT", str(nt))
+        for kw in (dict(g=-0.001, γ=0.0005), dict(n=3, m=2, hmin=0.07)):
+            st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx + nt, prm_kw=kw)
+            sw.fused_steps(st, sysc, 6)
+            oc.time_loop(ref, p, nsteps=6)
+            _compare(st, ref, what=f"NS {Lx}x{Ly} nt={nt}:")
+    monkeypatch.delenv("SWALBE_NT", raising=False)
+    # thermal: same noise, so the two synchronisation flavours must agree bit for bit
+    sysc = sw.SysConst(Lx=520, Ly=70, param=sw.Taumucs(kbt=1e-6))
+    out = []
+    for ns in ("1", "0"):
+        monkeypatch.setenv("SWALBE_NSYNC", ns)
+        st = sw.Sys(sysc, "GPU", kind="thermal")
+        st.height.set(np.asfortranarray(1.0 + 0.1 * np.random.default_rng(3).random((520, 70))))
+        sw.fused_steps(st, sysc, 5, thermal_seed=11, step0=3)
+        out.append({n: getattr(st, n).numpy() for n in ("height", "velx", "fout", "kbtx")})
+    for n in out[0]:
+        assert np.array_equal(out[0][n], out[1][n]), n
 
 
 # ---- reference whole-loop known answers (test/simulate.jl) through the drop-in drivers ---------------------

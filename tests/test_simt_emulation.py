@@ -16,7 +16,7 @@ from oracle import oracle_np as onp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INC = "/usr/local/cuda/include"
 _d, _i, _p = C.c_double, C.c_int, C.c_void_p
-STRICT, OPTS, FULL, BULK, TILE, THERMAL, STRICT224, FM_LEAN, FM_FULL = range(9)
+STRICT, OPTS, FULL, BULK, TILE, THERMAL, STRICT224, FM_LEAN, FM_FULL, NS_LDGSTS, NS_BULK, NS_THERMAL = range(12)
 
 
 class SimtStep(C.Structure):
@@ -379,3 +379,17 @@ def test_general_tau_from_moments_flavour_on_cpu(simt, Lx, Ly, W, rows):
             a.fout[...] = fsrc
         oc.time_loop(b, p, nsteps=nsteps)
         _same(a, b, FIELDS + (AUX[:-1] if last_full else ()))
+
+
+@pytest.mark.parametrize("flavour,Lx,Ly,W,rows", [(NS_LDGSTS, 25, 26, 120, 26), (NS_LDGSTS, 150, 40, 120, 13), (NS_LDGSTS, 130, 9, 64, 64),
+                                                  (NS_LDGSTS, 5, 5, 4, 2), (NS_BULK, 128, 12, 120, 12), (NS_BULK, 200, 10, 100, 4),
+                                                  (NS_BULK, 64, 14, 120, 5)])
+def test_neighbour_sync_flavour_on_cpu(simt, flavour, Lx, Ly, W, rows):
+    """NS kernels: no CTA barrier in the row loop, each warp hands over to its two neighbour warps through mbarriers (here:
+    real atomics between OS threads that do run ahead of each other), rows prefetched per thread or per warp."""
+    for kw in (dict(g=-0.001, gamma=0.0005), dict(n=3, m=2, hmin=0.07)):
+        p = onp.Params(**kw)
+        a, b = _state(Lx, Ly, 7), _state(Lx, Ly, 7)
+        _run(simt, a, p, 3, flavour, W, rows)
+        oc.time_loop(b, p, nsteps=3)
+        _same(a, b, FIELDS)
