@@ -1,0 +1,204 @@
+// Persistent multi-step kernel for lattices that fit the shared memory of ONE thread-block cluster (<= ~128 x 128 sites;
+// the reference's README example is 100 x 100, src/simulate.jl:338-358).
+//
+// At that size a time step is pure latency: one launch per step costs ~4.4 us even for a single tile (kernel ramp-up,
+// global-memory round trips, launch gap), against < 1 us of dependent arithmetic.  Here the whole lattice lives in the
+// distributed shared memory of a cluster of C CTAs for ALL the steps of a swalbe_time_loop call:
+//
+//   * CTA r of the cluster owns a row slab of the lattice (the multi-GPU decomposition in miniature);
+//   * per step: fetch the 3 halo rows of h and 1 of u from the two neighbour CTAs' shared memory (DSMEM), then the
+//     three dependent stencils as phases over the slab plus its halo -- pressure on rows+4, forces / equilibrium /
+//     collision on rows+2, pull + moments on the slab -- with a __syncthreads between phases and ONE cluster barrier per
+//     step; h and u are double-buffered so that a neighbour may still read step s while step s+1 is being written;
+//   * global memory is touched at the first step (load), by the populations (write-only at tau == 1; every step, or
+//     the last one only with SWALBE_LOOP_LAZY_POPULATIONS) and at the last step (h, u); per-step logs (min / max /
+//     wetted count of the pre-step height: time_loop(sys, state, Δh), the wetted! callback) leave by atomics.
+//
+// Same site functions as every other kernel (common.cuh), so the fields are bit-identical to the per-step kernels.
+// Strict lean only: tau == 1, scalar theta, standard slip, no noise, no inclination.
+#pragma once
+#include "fused.cuh"
+
+#ifndef SW_HOST_EMULATION
+#include <cooperative_groups.h>
+#endif
+
+namespace swalbe {
+
+struct ClusterArgs {
+  FusedArgs a;        // lattice, constants, h_in/ux_in/uy_in (read at step 0), h_out/ux_out/uy_out (written by the last step)
+  int nsteps;
+  int lazy;           // populations: 1 = written by the last step only
+  int rows_max;       // ceil(Ly / cluster size): the slab height the shared-memory layout is sized for
+  double *log_min, *log_max;       // nsteps slots each (NULL = off), pre-set to +-inf / 0 by the host
+  unsigned long long *log_wet;
+};
+
+// rows [cl_row0(r), cl_row0(r+1)) of the lattice belong to CTA r
+__host__ __device__ inline int cl_row0(int r, int C, int Ly) { return (int)(((long long)r * Ly) / C); }
+
+// doubles of dynamic shared memory per CTA for an Lx-wide lattice whose tallest slab has R rows
+constexpr int CLUSTER_RED = 96;  // reduction scratch of the per-step logs (3 x 32 warps at most)
+constexpr size_t cluster_smem_doubles(int Lx, int R) {
+  return (size_t)Lx * (2 * (R + 6) + 4 * (R + 2) + (R + 4) + 9 * (R + 2)) + CLUSTER_RED;
+}
+
+#ifndef SW_HOST_EMULATION  // (tests/simt_emulation.cpp supplies host versions of these four)
+__device__ __forceinline__ unsigned cl_rank() { return cooperative_groups::this_cluster().block_rank(); }
+__device__ __forceinline__ unsigned cl_size() { return cooperative_groups::this_cluster().num_blocks(); }
+__device__ __forceinline__ const double *cl_map(const double *p, unsigned rank) {
+  return cooperative_groups::this_cluster().map_shared_rank(const_cast<double *>(p), rank);
+}
+__device__ __forceinline__ void cl_sync() { cooperative_groups::this_cluster().sync(); }
+#endif
+
+template <int NT, int PM, bool GZ>
+__global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__ ClusterArgs ca) {
+#ifdef SW_HOST_EMULATION
+  double *const smem = emul_dynamic_smem();
+#else
+  extern __shared__ __align__(16) double smem[];
+#endif
+  const FusedArgs &a = ca.a;
+  const int tid = threadIdx.x;
+  const int Lx = a.Lx, Ly = a.Ly, R = ca.rows_max;
+  const int C = (int)cl_size(), rank = (int)cl_rank();
+  const int j0 = cl_row0(rank, C, Ly), rows = cl_row0(rank + 1, C, Ly) - j0;
+  const int dn = (rank + C - 1) % C, up = (rank + 1) % C;  // owners of the rows below / above this slab
+  const int rows_dn = cl_row0(dn + 1, C, Ly) - cl_row0(dn, C, Ly);
+
+  // layout (every CTA the same, sized for R rows): h[2][(R+6) Lx] | ux[2][(R+2) Lx] | uy[2][(R+2) Lx] | p[(R+4) Lx] | f*[9][(R+2) Lx]
+  const size_t nh = (size_t)(R + 6) * Lx, nu = (size_t)(R + 2) * Lx, np = (size_t)(R + 4) * Lx;
+  double *const sh = smem, *const sux = sh + 2 * nh, *const suy = sux + 2 * nu, *const sp = suy + 2 * nu, *const sf = sp + np;
+  double *const r_min = sf + 9 * nu, *const r_max = r_min + 32;
+  unsigned int *const r_wet = reinterpret_cast<unsigned int *>(r_max + 32);
+  // row `l` of the slab (l = -3 .. rows+2 for h, -1 .. rows for u) lives at index (l + 3) resp. (l + 1)
+  auto H = [&](int buf, int l) { return sh + buf * nh + (size_t)(l + 3) * Lx; };
+  auto UX = [&](int buf, int l) { return sux + buf * nu + (size_t)(l + 1) * Lx; };
+  auto UY = [&](int buf, int l) { return suy + buf * nu + (size_t)(l + 1) * Lx; };
+
+  // step 0: slab + halo straight from global memory (periodic rows)
+  for (int idx = tid; idx < (rows + 6) * Lx; idx += NT) {
+    const int l = idx / Lx - 3, i = idx - (l + 3) * Lx;
+    H(0, l)[i] = a.h_in[(size_t)wrapi(j0 + l, Ly) * Lx + i];
+  }
+  for (int idx = tid; idx < (rows + 2) * Lx; idx += NT) {
+    const int l = idx / Lx - 1, i = idx - (l + 1) * Lx;
+    const size_t g = (size_t)wrapi(j0 + l, Ly) * Lx + i;
+    UX(0, l)[i] = a.ux_in[g];
+    UY(0, l)[i] = a.uy_in[g];
+  }
+  __syncthreads();
+
+  const bool logging = ca.log_min != nullptr || ca.log_wet != nullptr;
+  for (int s = 0; s < ca.nsteps; ++s) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    const bool last = s == ca.nsteps - 1;
+    if (s > 0) {
+      // halo rows of this step's input from the neighbours' shared memory: what they wrote in phase D of step s-1
+      cl_sync();
+      const double *hd = cl_map(H(cur, rows_dn - 3), dn), *hu = cl_map(H(cur, 0), up);  // (same layout in every CTA)
+      for (int idx = tid; idx < 3 * Lx; idx += NT) {
+        H(cur, -3)[idx] = hd[idx];
+        H(cur, rows)[idx] = hu[idx];
+      }
+      const double *xd = cl_map(UX(cur, rows_dn - 1), dn), *xu = cl_map(UX(cur, 0), up);
+      const double *yd = cl_map(UY(cur, rows_dn - 1), dn), *yu = cl_map(UY(cur, 0), up);
+      for (int idx = tid; idx < Lx; idx += NT) {
+        UX(cur, -1)[idx] = xd[idx]; UX(cur, rows)[idx] = xu[idx];
+        UY(cur, -1)[idx] = yd[idx]; UY(cur, rows)[idx] = yu[idx];
+      }
+      __syncthreads();
+    }
+
+    // phase B: film pressure on rows -2 .. rows+1   (src/pressure.jl:141-153; fused.cuh stage B)
+    for (int idx = tid; idx < (rows + 4) * Lx; idx += NT) {
+      const int l = idx / Lx - 2, i = idx - (l + 2) * Lx;
+      const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;  // columns i-1 / i+1 (periodic)
+      const double *r0 = H(cur, l - 1), *r1 = H(cur, l), *r2 = H(cur, l + 1);
+      const double hc = r1[i];
+      const double lap = lap9_bracket(hc, r1[im], r0[i], r1[ip], r2[i], r0[im], r0[ip], r2[ip], r2[im]);
+      const double x = div_exact(a.pc.hmin, hc + a.pc.hcrit);
+      const double pw = disjoining_powers(x, PM, a.pc.n, a.pc.m);
+      sp[(size_t)(l + 2) * Lx + i] = (-a.pc.gamma * (a.pc.kappa * pw)) - a.pc.gamma * lap;
+    }
+    __syncthreads();
+
+    // phase C: forces, equilibrium, collision on rows -1 .. rows   (fused.cuh stage C); logs of the pre-step height
+    double d_min = INFINITY, d_max = -INFINITY;
+    unsigned int d_wet = 0;
+    for (int idx = tid; idx < (rows + 2) * Lx; idx += NT) {
+      const int l = idx / Lx - 1, i = idx - (l + 1) * Lx;
+      const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;
+      const double *q0 = sp + (size_t)(l + 1) * Lx, *q1 = q0 + Lx, *q2 = q1 + Lx;  // p rows l-1, l, l+1
+      const double hc = H(cur, l)[i];
+      const double ux = UX(cur, l)[i], uy = UY(cur, l)[i];
+      const double pipjp = q0[im], pimjp = q0[ip], pimjm = q2[ip], pipjm = q2[im];
+      const double gx = grad9_x(q1[im], q1[ip], pipjp, pimjp, pimjm, pipjm);
+      const double gy = grad9_y(q0[i], q2[i], pipjp, pimjp, pimjm, pipjm);
+      const double hgx = hc * gx, hgy = hc * gy;
+      double sx, sy;
+      slip_terms(hc, ux, uy, a.sc, SWALBE_SLIP_STANDARD, sx, sy);
+      const double Fx = (-hgx) - sx, Fy = (-hgy) - sy;
+      double fe[9], vsq, fs[9];
+      equilibrium_site<GZ>(hc, ux, uy, a.ec, fe, vsq);
+      collide_site_tau1(fe, Fx, Fy, fs);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) sf[(size_t)k * nu + (size_t)(l + 1) * Lx + i] = fs[k];
+      if (logging && l >= 0 && l < rows) {
+        d_min = fmin(d_min, hc);
+        d_max = fmax(d_max, hc);
+        d_wet += hc > a.hthresh;
+      }
+    }
+    if (logging) {  // CTA reduction, one atomic per CTA and step (as the marching kernel does)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d_min = fmin(d_min, __shfl_down_sync(0xffffffffu, d_min, o));
+        d_max = fmax(d_max, __shfl_down_sync(0xffffffffu, d_max, o));
+        d_wet += __shfl_down_sync(0xffffffffu, d_wet, o);
+      }
+      if ((tid & 31) == 0) { r_min[tid >> 5] = d_min; r_max[tid >> 5] = d_max; r_wet[tid >> 5] = d_wet; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w) { d_min = fmin(d_min, r_min[w]); d_max = fmax(d_max, r_max[w]); d_wet += r_wet[w]; }
+        if (ca.log_min != nullptr) { atomic_min_double(ca.log_min + s, d_min); atomic_max_double(ca.log_max + s, d_max); }
+        if (ca.log_wet != nullptr) atomicAdd(ca.log_wet + s, (unsigned long long)d_wet);
+      }
+    } else {
+      __syncthreads();
+    }
+
+    // phase D: pull-stream + moments of the slab   (fused.cuh stage D) -> the other h / u buffer
+    if (ca.nsteps == 1) cl_sync();  // in-place calls: nobody may still be loading step 0 from the planes written below
+    const bool write_f = a.f_out != nullptr && (last || !ca.lazy);
+    for (int idx = tid; idx < rows * Lx; idx += NT) {
+      const int l = idx / Lx, i = idx - l * Lx;
+      const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;
+      const size_t c0 = (size_t)l * Lx, c1 = c0 + Lx, c2 = c1 + Lx;  // f* rows l-1, l, l+1
+      double fn[9];
+      fn[0] = sf[0 * nu + c1 + i];
+      fn[1] = sf[1 * nu + c1 + im]; fn[3] = sf[3 * nu + c1 + ip];
+      fn[2] = sf[2 * nu + c0 + i];  fn[4] = sf[4 * nu + c2 + i];
+      fn[5] = sf[5 * nu + c0 + im]; fn[6] = sf[6 * nu + c0 + ip];
+      fn[7] = sf[7 * nu + c2 + ip]; fn[8] = sf[8 * nu + c2 + im];
+      double hn, uxn, uyn;
+      moments_site(fn, hn, uxn, uyn);
+      H(nxt, l)[i] = hn; UX(nxt, l)[i] = uxn; UY(nxt, l)[i] = uyn;
+      const size_t o = (size_t)(j0 + l) * Lx + i;
+      if (last) { a.h_out[o] = hn; a.ux_out[o] = uxn; a.uy_out[o] = uyn; }
+      if (write_f) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a.f_out[o + k * a.fstride_out] = fn[k];
+        if (last && a.f_out2 != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a.f_out2[o + k * a.fstride_out2] = fn[k];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cl_sync();  // a CTA must not exit while a neighbour may still read its shared memory
+}
+
+}  // namespace swalbe

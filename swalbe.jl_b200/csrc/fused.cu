@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "cluster.cuh"
 #include "launch.h"
 #include "variants.h"
 
@@ -421,18 +422,43 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   // moment ping-pong: the caller's planes (A) and the plan's scratch (B); arrange for the LAST step to land in A
   double *A[3] = {st->height, st->velx, st->vely};
   double *B[3] = {plan->scratch, plan->scratch + N, plan->scratch + 2 * N};
+
+  // Lattices that fit the shared memory of one thread-block cluster (<= ~128^2; the README example is 100^2) run all
+  // their lean steps inside ONE persistent kernel launch, in place on the caller's planes (cluster.cuh); the step that
+  // materialises the reference's intermediate fields, if any, follows through the ordinary path.
+  int s_begin = 0;
+  {
+    a.h_in = A[0]; a.ux_in = A[1]; a.uy_in = A[2];
+    int R = 0;
+    size_t smem_bytes = 0;
+    const int ncl = skip_aux ? nsteps : nsteps - 1;
+    const int C = ncl >= 1 ? cluster_plan(key_mid, a, &R, &smem_bytes) : 0;
+    if (C > 0) {
+      ClusterArgs ca = {};
+      ca.a = a;
+      ca.a.h_out = A[0]; ca.a.ux_out = A[1]; ca.a.uy_out = A[2];
+      ca.a.f_out = st->fout;
+      ca.a.f_out2 = ncl == nsteps ? st->ftemp : nullptr;  // fout == ftemp on return (src/collide.jl:103)
+      ca.nsteps = ncl; ca.lazy = lazy ? 1 : 0; ca.rows_max = R;
+      ca.log_min = log_mm ? logs->hmin : nullptr; ca.log_max = log_mm ? logs->hmax : nullptr;
+      ca.log_wet = log_wet ? logs->wetted : nullptr;
+      if (int e = launch_cluster(ca, key_mid, C, smem_bytes, stream)) return e;
+      s_begin = ncl;
+    }
+  }
+  const int nrem = nsteps - s_begin;
   bool src_is_A = true;
   // FM: the moment planes are read by step 0 at most and written by the last step only -- no ping-pong, and no copy
   // unless the same launch does both
   const bool fm_pingpong_free = fm && (fm_first || nsteps > 1);
-  if (fm_pingpong_free ? false : (nsteps & 1)) {
+  if (fm_pingpong_free ? false : (nrem & 1)) {
     for (int q = 0; q < 3; ++q) SW_CUDA(cudaMemcpyAsync(B[q], A[q], sizeof(double) * N, cudaMemcpyDeviceToDevice, stream));
     src_is_A = false;
   }
   // population ping-pong (tau != 1): the reference reads ftemp; streamed result alternates fout/ftemp
   bool fsrc_is_ftemp = true;
 
-  for (int s = 0; s < nsteps; ++s) {
+  for (int s = s_begin; s < nsteps; ++s) {
     const bool last = s == nsteps - 1;
     double **src = src_is_A ? A : B, **dst = src_is_A ? B : A;
     a.h_in = src[0]; a.ux_in = src[1]; a.uy_in = src[2];

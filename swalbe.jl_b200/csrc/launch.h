@@ -39,6 +39,10 @@ namespace swalbe {
 int fill_consts(FusedArgs &a, const swalbe_params &p);
 KernelKey make_key(const swalbe_params &p, int pmode, bool want_lean);
 bool bulk_eligible(int Lx, size_t ncells);
+// persistent multi-step kernel for lattices that fit one thread-block cluster (cluster.cu)
+struct ClusterArgs;
+int cluster_plan(const KernelKey &key, const FusedArgs &a, int *rows_max, size_t *smem_bytes);
+int launch_cluster(const ClusterArgs &ca, const KernelKey &key, int C, size_t smem_bytes, cudaStream_t stream);
 // small-lattice tile flavour of the strict lean step (tile.cu)
 bool tile_eligible(const KernelKey &key, const FusedArgs &a);
 int launch_tile(const FusedArgs &a, const KernelKey &key, cudaStream_t stream);

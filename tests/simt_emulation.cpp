@@ -25,8 +25,12 @@ struct Emu3 {
 static thread_local Emu3 threadIdx, blockIdx;
 static pthread_barrier_t g_cta_barrier;
 static double *g_dynamic_smem = nullptr;
-static inline void __syncthreads() { pthread_barrier_wait(&g_cta_barrier); }
-static inline double *emul_dynamic_smem() { return g_dynamic_smem; }
+// cluster launches run several CTAs at once: each OS thread then carries its own CTA's barrier / smem / shuffle state
+static thread_local pthread_barrier_t *tl_cta_barrier = nullptr, *tl_warp_barrier = nullptr;
+static thread_local double *tl_smem = nullptr;
+static thread_local unsigned long long (*tl_shfl_slot)[32] = nullptr;
+static inline void __syncthreads() { pthread_barrier_wait(tl_cta_barrier ? tl_cta_barrier : &g_cta_barrier); }
+static inline double *emul_dynamic_smem() { return tl_smem ? tl_smem : g_dynamic_smem; }
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __grid_constant__
@@ -60,11 +64,13 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int delta) {
   const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   unsigned long long bits = 0;
   memcpy(&bits, &v, sizeof(T));
-  g_shfl_slot[w][lane] = bits;
-  pthread_barrier_wait(&g_warp_barrier[w]);
+  unsigned long long(*slot)[32] = tl_shfl_slot ? tl_shfl_slot : g_shfl_slot;
+  pthread_barrier_t *wb = tl_warp_barrier ? tl_warp_barrier : g_warp_barrier;
+  slot[w][lane] = bits;
+  pthread_barrier_wait(&wb[w]);
   const unsigned src = lane + (unsigned)delta;
-  const unsigned long long got = src < 32u ? g_shfl_slot[w][src] : bits;
-  pthread_barrier_wait(&g_warp_barrier[w]);
+  const unsigned long long got = src < 32u ? slot[w][src] : bits;
+  pthread_barrier_wait(&wb[w]);
   T out;
   memcpy(&out, &got, sizeof(T));
   return out;
@@ -115,6 +121,16 @@ static inline void ns_syncwarp();
 
 static inline void ns_syncwarp() { pthread_barrier_wait(&g_warp_barrier[threadIdx.x >> 5]); }
 
+// ---- thread-block cluster: rank, size, distributed shared memory, cluster barrier ------------------------------------
+static unsigned g_cluster_size = 1;
+static double *g_cluster_smem[16];
+static pthread_barrier_t g_cluster_barrier;
+static inline unsigned cl_rank() { return blockIdx.x; }
+static inline unsigned cl_size() { return g_cluster_size; }
+static inline const double *cl_map(const double *p, unsigned rank) { return g_cluster_smem[rank] + (p - tl_smem); }
+static inline void cl_sync() { pthread_barrier_wait(&g_cluster_barrier); }
+
+#include "../swalbe.jl_b200/csrc/cluster.cuh"
 #include "../swalbe.jl_b200/csrc/tile.cuh"  // (includes fused.cuh and common.cuh)
 
 using namespace swalbe;
@@ -198,6 +214,48 @@ static kernel_fn tile_kernel(int pm) {
   }
 }
 
+// all CTAs of one cluster at once (C x nthreads OS threads), each with its own barrier, shuffle slots and smem block
+typedef void (*cluster_kernel_fn)(const ClusterArgs);
+static void launch_cluster_emul(cluster_kernel_fn k, unsigned C, unsigned nthreads, size_t dyn_doubles, const ClusterArgs &ca) {
+  std::vector<std::vector<double>> smem(C, std::vector<double>(dyn_doubles + 2, 0.0));
+  std::vector<pthread_barrier_t> cta_bar(C), warp_bar(C * 8);
+  std::vector<unsigned long long> slots((size_t)C * 8 * 32, 0ull);
+  g_cluster_size = C;
+  pthread_barrier_init(&g_cluster_barrier, nullptr, C * nthreads);
+  for (unsigned r = 0; r < C; ++r) {
+    g_cluster_smem[r] = (double *)(((uintptr_t)smem[r].data() + 15) & ~(uintptr_t)15);
+    pthread_barrier_init(&cta_bar[r], nullptr, nthreads);
+    for (unsigned w = 0; w < nthreads / 32; ++w) pthread_barrier_init(&warp_bar[r * 8 + w], nullptr, 32);
+  }
+  std::vector<std::thread> th;
+  th.reserve((size_t)C * nthreads);
+  for (unsigned r = 0; r < C; ++r)
+    for (unsigned t = 0; t < nthreads; ++t)
+      th.emplace_back([&, r, t]() {
+        threadIdx.x = t; blockIdx.x = r; blockIdx.y = 0;
+        tl_cta_barrier = &cta_bar[r]; tl_warp_barrier = &warp_bar[r * 8]; tl_smem = g_cluster_smem[r];
+        tl_shfl_slot = reinterpret_cast<unsigned long long(*)[32]>(&slots[(size_t)r * 8 * 32]);
+        k(ca);
+      });
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&g_cluster_barrier);
+  for (auto &b : cta_bar) pthread_barrier_destroy(&b);
+  for (unsigned r = 0; r < C; ++r)
+    for (unsigned w = 0; w < nthreads / 32; ++w) pthread_barrier_destroy(&warp_bar[r * 8 + w]);
+}
+
+constexpr int CENT = 128;  // CTA width of the emulated cluster kernel
+template <bool GZ>
+static cluster_kernel_fn cluster_kernel(int pm) {
+  switch (pm) {
+    case PM_BROAD_93: return k_cluster_steps<CENT, PM_BROAD_93, GZ>;
+    case PM_BROAD_32: return k_cluster_steps<CENT, PM_BROAD_32, GZ>;
+    case PM_FAST_93: return k_cluster_steps<CENT, PM_FAST_93, GZ>;
+    case PM_FAST_32: return k_cluster_steps<CENT, PM_FAST_32, GZ>;
+    default: return nullptr;
+  }
+}
+
 extern "C" {
 
 struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop put into FusedArgs
@@ -222,29 +280,25 @@ struct SimtStep {  // one launch: what swalbe_time_loop / swalbe_dist_time_loop 
   int fm_prefetch;                 // FM flavours: L2 prefetch distance (a no-op here, but the cursor logic runs)
 };
 
+static int fill_args(const SimtStep *s, FusedArgs &a);
+
+// the persistent cluster kernel: nsteps steps in one launch on a cluster of C CTAs, in place or not; s->log_* point at
+// nsteps slots
+int simt_cluster_steps(const SimtStep *s, int nsteps, int C, int lazy) {
+  ClusterArgs ca = {};
+  if (int e = fill_args(s, ca.a)) return e;
+  if (s->tau != 1.0 || s->ct_field || C < 1 || C > 16 || s->Ly / C < 3) return -2;
+  cluster_kernel_fn k = s->g == 0.0 ? cluster_kernel<true>(ca.a.pc.pmode) : cluster_kernel<false>(ca.a.pc.pmode);
+  if (!k) return -1;
+  ca.nsteps = nsteps; ca.lazy = lazy; ca.rows_max = (s->Ly + C - 1) / C;
+  ca.log_min = s->log_min; ca.log_max = s->log_max; ca.log_wet = s->log_wet;
+  launch_cluster_emul(k, (unsigned)C, CENT, cluster_smem_doubles(s->Lx, ca.rows_max), ca);
+  return 0;
+}
+
 int simt_step(const SimtStep *s) {
   FusedArgs a = {};
-  if (int e = resolve_pmode(s->pressure_variant, s->n, s->m, &a.pc.pmode)) return e;
-  a.pc.gamma = s->gamma; a.pc.kappa = host_kappa(s->cospi_theta, s->n, s->m, s->hmin);
-  a.pc.nm1 = (double)(s->n - 1); a.pc.mm1 = (double)(s->m - 1); a.pc.kden = (double)(s->n - s->m) * s->hmin;
-  a.pc.hmin = s->hmin; a.pc.hcrit = s->hcrit; a.pc.n = s->n; a.pc.m = s->m;
-  a.sc = make_slip(s->delta, s->mu, s->hcrit, s->slip_variant);
-  a.ec = make_eq(s->g);
-  volatile double it = 1.0 / s->tau;
-  volatile double om = 1.0 - it;
-  a.invtau = it; a.omega = om;
-  a.use_incl = s->use_incl; a.incl_ax = s->incl_ax; a.incl_ay = s->incl_ay; a.incl_factor = s->incl_factor;
-  a.Lx = s->Lx; a.Ly = s->Ly; a.jbeg = s->jbeg; a.jend = s->jend; a.W = s->W; a.rows_per_cta = s->rows_per_cta;
-  a.wrap_y = s->wrap_y; a.jglobal0 = s->jglobal0; a.Ly_global = s->Ly_global > 0 ? s->Ly_global : s->Ly;
-  a.tc = make_thermal(s->kbt, s->mu, s->delta); a.pk = make_philox_key(s->seed); a.step = s->step;
-  a.fstride_in = a.fstride_out = a.fstride_out2 = s->fstride;
-  a.h_in = s->h_in; a.ux_in = s->ux_in; a.uy_in = s->uy_in; a.f_in = s->f_in; a.ct_field = s->ct_field;
-  a.h_out = s->h_out; a.ux_out = s->ux_out; a.uy_out = s->uy_out; a.f_out = s->f_out; a.f_out2 = s->f_out2;
-  a.pressure = s->pressure; a.hgx = s->hgx; a.hgy = s->hgy; a.slipx = s->slipx; a.slipy = s->slipy;
-  a.Fx = s->Fx; a.Fy = s->Fy; a.feq = s->feq; a.vsq = s->vsq;
-  a.log_min = s->log_min; a.log_max = s->log_max; a.log_wet = s->log_wet; a.hthresh = s->hthresh;
-  a.fm_prefetch = s->fm_prefetch;
-  a.fm_hints = s->fm_prefetch ? 7 : 0;  // (the hinted and the plain code paths both run in the FM test)
+  if (int e = fill_args(s, a)) return e;
   const bool gz = s->g == 0.0, tau1 = s->tau == 1.0;
   const int pm = a.pc.pmode;
   kernel_fn k = nullptr;
@@ -280,3 +334,29 @@ int simt_step(const SimtStep *s) {
 }
 
 }  // extern "C"
+
+static int fill_args(const SimtStep *s, FusedArgs &a) {
+  if (int e = resolve_pmode(s->pressure_variant, s->n, s->m, &a.pc.pmode)) return e;
+  a.pc.gamma = s->gamma; a.pc.kappa = host_kappa(s->cospi_theta, s->n, s->m, s->hmin);
+  a.pc.nm1 = (double)(s->n - 1); a.pc.mm1 = (double)(s->m - 1); a.pc.kden = (double)(s->n - s->m) * s->hmin;
+  a.pc.hmin = s->hmin; a.pc.hcrit = s->hcrit; a.pc.n = s->n; a.pc.m = s->m;
+  a.sc = make_slip(s->delta, s->mu, s->hcrit, s->slip_variant);
+  a.ec = make_eq(s->g);
+  volatile double it = 1.0 / s->tau;
+  volatile double om = 1.0 - it;
+  a.invtau = it; a.omega = om;
+  a.use_incl = s->use_incl; a.incl_ax = s->incl_ax; a.incl_ay = s->incl_ay; a.incl_factor = s->incl_factor;
+  a.Lx = s->Lx; a.Ly = s->Ly; a.jbeg = s->jbeg; a.jend = s->jend; a.W = s->W; a.rows_per_cta = s->rows_per_cta;
+  a.wrap_y = s->wrap_y; a.jglobal0 = s->jglobal0; a.Ly_global = s->Ly_global > 0 ? s->Ly_global : s->Ly;
+  a.tc = make_thermal(s->kbt, s->mu, s->delta); a.pk = make_philox_key(s->seed); a.step = s->step;
+  a.fstride_in = a.fstride_out = a.fstride_out2 = s->fstride;
+  a.h_in = s->h_in; a.ux_in = s->ux_in; a.uy_in = s->uy_in; a.f_in = s->f_in; a.ct_field = s->ct_field;
+  a.h_out = s->h_out; a.ux_out = s->ux_out; a.uy_out = s->uy_out; a.f_out = s->f_out; a.f_out2 = s->f_out2;
+  a.pressure = s->pressure; a.hgx = s->hgx; a.hgy = s->hgy; a.slipx = s->slipx; a.slipy = s->slipy;
+  a.Fx = s->Fx; a.Fy = s->Fy; a.feq = s->feq; a.vsq = s->vsq;
+  a.log_min = s->log_min; a.log_max = s->log_max; a.log_wet = s->log_wet; a.hthresh = s->hthresh;
+  a.fm_prefetch = s->fm_prefetch;
+  a.fm_hints = s->fm_prefetch ? 7 : 0;  // (the hinted and the plain code paths both run in the FM test)
+  return 0;
+}
+

@@ -40,10 +40,13 @@ def _mk(sw, Lx, Ly, seed, prm_kw, tau_pops=False):
     return st, sysc, ref, onp.Params(**okw)
 
 
-@pytest.fixture(params=["tile", "march"])
+@pytest.fixture(params=["cluster", "tile", "march"])
 def small_lattice_flavour(request, monkeypatch):
-    """Lean steps of lattices <= 512^2 run through the tile kernel by default; "march" forces the marching kernel so
-    that both flavours see every small parity case."""
+    """Lean steps of lattices that fit one thread-block cluster run inside the persistent cluster kernel, lattices
+    <= 512^2 through the tile kernel; "tile" switches the cluster kernel off, "march" both, so that all three flavours
+    see every small parity case."""
+    if request.param != "cluster":
+        monkeypatch.setenv("SWALBE_CLUSTER", "0")
     if request.param == "march":
         monkeypatch.setenv("SWALBE_TILE_MAX", "0")
     return request.param
@@ -247,6 +250,28 @@ def test_neighbour_sync_kernels_same_bits(sw, monkeypatch, bulk):
         out.append({n: getattr(st, n).numpy() for n in ("height", "velx", "fout", "kbtx")})
     for n in out[0]:
         assert np.array_equal(out[0][n], out[1][n]), n
+
+
+@pytest.mark.parametrize("csize", [0, 1, 2, 4, 8, 16])
+def test_persistent_cluster_kernel_sizes_logs_and_chunks(sw, monkeypatch, csize):
+    """The persistent cluster kernel on every cluster size (0 = the library's choice): chunked calls (the drivers'
+    tdump chunks), lazy populations, per-step logs, in place on the state's planes; uneven slabs (100 rows on 8 / 16 CTAs)."""
+    if csize:
+        monkeypatch.setenv("SWALBE_CLUSTER_SIZE", str(csize))
+    for (Lx, Ly), kw in (((100, 100), dict(g=-0.001, γ=0.0005)), ((64, 50), dict(n=3, m=2, hmin=0.07)), ((37, 128), dict())):
+        if csize and Ly // csize < 3:
+            continue
+        st, sysc, ref, p = _mk(sw, Lx, Ly, seed=Lx, prm_kw=kw)
+        logs, done = [], 0
+        for n, lazy in ((3, False), (1, True), (6, True), (2, False)):
+            mn, mx, wet = sw.fused_steps(st, sysc, n, log_minmax=True, log_wetted=True, hthresh=1.0, lazy_populations=lazy,
+                                         skip_aux=done + n < 12)
+            logs.append(((mx - mn).cpu().numpy(), wet.cpu().numpy()))
+            done += n
+        dh, w = oc.time_loop(ref, p, nsteps=12, log_dh=True, log_wetted=True, hthresh=1.0)
+        _compare(st, ref, what=f"cluster {csize} {Lx}x{Ly}:")
+        assert np.array_equal(np.concatenate([a for a, _ in logs]), np.asarray(dh))
+        assert np.array_equal(np.concatenate([b for _, b in logs]), np.asarray(w))
 
 
 # ---- reference whole-loop known answers (test/simulate.jl) through the drop-in drivers ---------------------

@@ -4,6 +4,7 @@ CUDA thread, pthread barrier for __syncthreads, static storage for __shared__) a
 This exercises, without a GPU, the kernels' index logic: strips and halo columns, row cursors with the periodic wrap,
 the software pipeline and its ring slots, the fill / steady / drain instantiations, chunk seams, the tile phases."""
 import ctypes as C
+import ctypes as C_
 import os
 import subprocess
 
@@ -393,3 +394,30 @@ def test_neighbour_sync_flavour_on_cpu(simt, flavour, Lx, Ly, W, rows):
         _run(simt, a, p, 3, flavour, W, rows)
         oc.time_loop(b, p, nsteps=3)
         _same(a, b, FIELDS)
+
+
+@pytest.mark.parametrize("Lx,Ly,C,nsteps", [(25, 26, 4, 5), (100, 100, 8, 3), (33, 12, 4, 4), (40, 17, 2, 6), (9, 7, 1, 3), (64, 48, 16, 2),
+                                            (30, 30, 4, 1)])
+def test_persistent_cluster_kernel_on_cpu(simt, Lx, Ly, C, nsteps):
+    """k_cluster_steps (csrc/cluster.cuh): all steps of a call inside one launch on a thread-block cluster whose CTAs own
+    row slabs in shared memory and read each other's halo rows (distributed shared memory) behind one cluster barrier per
+    step.  Emulated with all CTAs of the cluster running concurrently; uneven slabs (Ly % C != 0), in place on the caller's
+    planes, per-step logs, populations every step or on the last one only -- against the oracle, bit for bit."""
+    simt.simt_cluster_steps.argtypes = [C_.POINTER(SimtStep), C_.c_int, C_.c_int, C_.c_int]
+    for kw, lazy in ((dict(g=-0.001, gamma=0.0005), 0), (dict(n=3, m=2, hmin=0.07), 1)):
+        p = onp.Params(**kw)
+        a, b = _state(Lx, Ly, 61), _state(Lx, Ly, 61)
+        mn, mx = np.full(nsteps, np.inf), np.full(nsteps, -np.inf)
+        wet = np.zeros(nsteps, dtype=np.uint64)
+        q = SimtStep()
+        q.Lx, q.Ly, q.jbeg, q.jend, q.wrap_y = Lx, Ly, 0, Ly, 1
+        q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+        q.cospi_theta, q.n, q.m = onp.cospi(p.theta), p.n, p.m
+        q.h_in, q.ux_in, q.uy_in = _ptr(a.height), _ptr(a.velx), _ptr(a.vely)
+        q.h_out, q.ux_out, q.uy_out = _ptr(a.height), _ptr(a.velx), _ptr(a.vely)  # in place
+        q.f_out, q.f_out2, q.fstride = _ptr(a.fout), _ptr(a.ftemp), Lx * Ly
+        q.log_min, q.log_max, q.log_wet, q.hthresh = _ptr(mn), _ptr(mx), _ptr(wet), 1.0
+        assert simt.simt_cluster_steps(C_.byref(q), nsteps, C, lazy) == 0
+        dh, w = oc.time_loop(b, p, nsteps=nsteps, log_dh=True, log_wetted=True, hthresh=1.0)
+        _same(a, b, FIELDS + ("ftemp",))
+        assert np.array_equal(mx - mn, np.asarray(dh)) and [int(v) for v in wet] == [int(v) for v in w]
