@@ -566,6 +566,9 @@ def main():
         dist.barrier()
         launches = int(lib.swalbe_launch_count() - l0)
         sampler.stop()
+        if not moving:  # device time of the K-step loop on rank 0's own streams (edge strips + halo exchange + interior):
+            # next to the single-GPU kernel time it shows whether the exchange is hidden behind the interior update
+            extra["dist_loop_ms_per_step_rank0"] = round(sim.last_loop_ms() / K, 4)
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()

@@ -36,6 +36,12 @@ int env_i(const char *name, int dflt) {
 // rows+4, collisions on rows+2) is latency the other CTAs' threads would otherwise idle through.
 int cluster_plan(const KernelKey &key, const FusedArgs &a, int *rows_max, size_t *smem_bytes) {
   if (!env_i("SWALBE_CLUSTER", 1)) return 0;
+  // measured on B200 (profiles/r02_probes_call4.txt, us per step against tile kernel + graph replay): 32^2 3.0 vs 4.5,
+  // 64^2 3.7 vs 4.7, 100^2 5.9 vs 4.9 without logs; with per-step logs (no graph replay possible) 100^2 8.6 vs 10.6,
+  // 128^2 a tie -> the default bounds below (SWALBE_CLUSTER_MAX / SWALBE_CLUSTER_MAX_LOGS sites)
+  const bool logs = a.log_min != nullptr || a.log_wet != nullptr;
+  const size_t max_sites = (size_t)std::max(0, logs ? env_i("SWALBE_CLUSTER_MAX_LOGS", 128 * 128) : env_i("SWALBE_CLUSTER_MAX", 80 * 80));
+  if ((size_t)a.Lx * a.Ly > max_sites) return 0;
   if (!(key.tau1 && key.lean_pm > 0 && !key.thermal && a.wrap_y == 1 && a.jbeg == 0 && a.jend == a.Ly && a.ct_field == nullptr &&
         a.sc.variant == SWALBE_SLIP_STANDARD && !a.use_incl))
     return 0;
@@ -49,6 +55,7 @@ int cluster_plan(const KernelKey &key, const FusedArgs &a, int *rows_max, size_t
   for (int C : {16, 8, 4, 2, 1}) {
     if (forced ? C != forced : (C > 1 && a.Ly / C < 4)) continue;
     if (a.Ly / C < 3) continue;  // a halo (3 rows) must come from the immediate neighbour alone
+    if ((size_t)a.Lx * ((a.Ly + C - 1) / C + 4) >= 65536 || a.Lx > 1024) continue;  // (range of the kernel's division-free row index)
     const int R = (a.Ly + C - 1) / C;
     const size_t bytes = cluster_smem_doubles(a.Lx, R) * sizeof(double);
     if (bytes + 2048 > (size_t)max_optin) continue;
@@ -65,6 +72,13 @@ int cluster_plan(const KernelKey &key, const FusedArgs &a, int *rows_max, size_t
     *rows_max = R; *smem_bytes = bytes;
     return C;
   }
+  return 0;
+}
+
+int launch_cluster_logs(const double *part, int C, int nsteps, double *log_min, double *log_max, unsigned long long *log_wet,
+                        cudaStream_t stream) {
+  k_cluster_logs<<<(nsteps + 127) / 128, 128, 0, stream>>>(part, C, nsteps, log_min, log_max, log_wet);
+  SW_LAUNCH_CHECK();
   return 0;
 }
 

@@ -12,7 +12,8 @@
 //     step; h and u are double-buffered so that a neighbour may still read step s while step s+1 is being written;
 //   * global memory is touched at the first step (load), by the populations (write-only at tau == 1; every step, or
 //     the last one only with SWALBE_LOOP_LAZY_POPULATIONS) and at the last step (h, u); per-step logs (min / max /
-//     wetted count of the pre-step height: time_loop(sys, state, Δh), the wetted! callback) leave by atomics.
+//     wetted count of the pre-step height: time_loop(sys, state, Δh), the wetted! callback) leave as per-CTA partial
+//     results by plain stores and are folded by a one-block kernel after the loop (k_cluster_logs).
 //
 // Same site functions as every other kernel (common.cuh), so the fields are bit-identical to the per-step kernels.
 // Strict lean only: tau == 1, scalar theta, standard slip, no noise, no inclination.
@@ -30,8 +31,8 @@ struct ClusterArgs {
   int nsteps;
   int lazy;           // populations: 1 = written by the last step only
   int rows_max;       // ceil(Ly / cluster size): the slab height the shared-memory layout is sized for
-  double *log_min, *log_max;       // nsteps slots each (NULL = off), pre-set to +-inf / 0 by the host
-  unsigned long long *log_wet;
+  double *log_part;   // per-step logs (NULL = off): nsteps x cluster size x 3 partial results (min, max, count) of the
+                      // pre-step height, written with plain stores; k_cluster_logs folds them into the caller's arrays
 };
 
 // rows [cl_row0(r), cl_row0(r+1)) of the lattice belong to CTA r
@@ -90,7 +91,11 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
   }
   __syncthreads();
 
-  const bool logging = ca.log_min != nullptr || ca.log_wet != nullptr;
+  const bool logging = ca.log_part != nullptr;
+  // row of a slab-local site index without an integer division in the step loop: (idx + 1/2) / Lx is at least 1/(2 Lx)
+  // away from every integer, three orders of magnitude more than the float rounding error for idx < 2^16 (host-checked)
+  const float inv_lx = 1.0f / (float)Lx;
+  auto row_of = [&](int idx) { return (int)(((float)idx + 0.5f) * inv_lx); };
   for (int s = 0; s < ca.nsteps; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
     const bool last = s == ca.nsteps - 1;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
 
     // phase B: film pressure on rows -2 .. rows+1   (src/pressure.jl:141-153; fused.cuh stage B)
     for (int idx = tid; idx < (rows + 4) * Lx; idx += NT) {
-      const int l = idx / Lx - 2, i = idx - (l + 2) * Lx;
+      const int l = row_of(idx) - 2, i = idx - (l + 2) * Lx;
       const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;  // columns i-1 / i+1 (periodic)
       const double *r0 = H(cur, l - 1), *r1 = H(cur, l), *r2 = H(cur, l + 1);
       const double hc = r1[i];
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
     double d_min = INFINITY, d_max = -INFINITY;
     unsigned int d_wet = 0;
     for (int idx = tid; idx < (rows + 2) * Lx; idx += NT) {
-      const int l = idx / Lx - 1, i = idx - (l + 1) * Lx;
+      const int l = row_of(idx) - 1, i = idx - (l + 1) * Lx;
       const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;
       const double *q0 = sp + (size_t)(l + 1) * Lx, *q1 = q0 + Lx, *q2 = q1 + Lx;  // p rows l-1, l, l+1
       const double hc = H(cur, l)[i];
@@ -160,10 +165,10 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
       }
       if ((tid & 31) == 0) { r_min[tid >> 5] = d_min; r_max[tid >> 5] = d_max; r_wet[tid >> 5] = d_wet; }
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0) {  // (plain stores: nothing in the step loop waits on global memory)
         for (int w = 1; w < NT / 32; ++w) { d_min = fmin(d_min, r_min[w]); d_max = fmax(d_max, r_max[w]); d_wet += r_wet[w]; }
-        if (ca.log_min != nullptr) { atomic_min_double(ca.log_min + s, d_min); atomic_max_double(ca.log_max + s, d_max); }
-        if (ca.log_wet != nullptr) atomicAdd(ca.log_wet + s, (unsigned long long)d_wet);
+        double *o = ca.log_part + ((size_t)s * C + rank) * 3;
+        o[0] = d_min; o[1] = d_max; o[2] = (double)d_wet;
       }
     } else {
       __syncthreads();
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
     if (ca.nsteps == 1) cl_sync();  // in-place calls: nobody may still be loading step 0 from the planes written below
     const bool write_f = a.f_out != nullptr && (last || !ca.lazy);
     for (int idx = tid; idx < rows * Lx; idx += NT) {
-      const int l = idx / Lx, i = idx - l * Lx;
+      const int l = row_of(idx), i = idx - l * Lx;
       const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;
       const size_t c0 = (size_t)l * Lx, c1 = c0 + Lx, c2 = c1 + Lx;  // f* rows l-1, l, l+1
       double fn[9];
@@ -199,6 +204,20 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
     __syncthreads();
   }
   cl_sync();  // a CTA must not exit while a neighbour may still read its shared memory
+}
+
+// folds the per-CTA partial logs of k_cluster_steps into the caller's per-step arrays
+static __global__ void k_cluster_logs(const double *__restrict__ part, int C, int nsteps, double *__restrict__ log_min,
+                               double *__restrict__ log_max, unsigned long long *__restrict__ log_wet) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsteps) return;
+  double mn = INFINITY, mx = -INFINITY, cnt = 0.0;
+  for (int r = 0; r < C; ++r) {
+    const double *o = part + ((size_t)s * C + r) * 3;
+    mn = fmin(mn, o[0]); mx = fmax(mx, o[1]); cnt += o[2];
+  }
+  if (log_min != nullptr) { log_min[s] = mn; log_max[s] = mx; }
+  if (log_wet != nullptr) log_wet[s] = (unsigned long long)cnt;
 }
 
 }  // namespace swalbe

@@ -220,6 +220,9 @@ struct GraphKey {
 struct swalbe_plan {
   int Lx, Ly;
   double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
+  double *log_part; // partial per-step logs of the cluster kernel (grown on demand)
+  size_t log_part_doubles;
+  int graph_launches;  // kernels inside the captured graph (the launch counter advances by this on replay)
   // CUDA graph of the last repeated loop (small, launch-bound lattices): built the second time the same call is seen
   cudaStream_t cap_stream;
   cudaGraphExec_t graph_exec;
@@ -252,7 +255,7 @@ int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly) {
   if (!plan) return set_error(SWALBE_ERR_ARG, "plan is NULL");
   if (int e = check_extent(Lx, Ly)) return e;
   swalbe_plan *p = new swalbe_plan();
-  p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr;
+  p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr; p->log_part = nullptr; p->log_part_doubles = 0; p->graph_launches = 0;
   p->cap_stream = nullptr; p->graph_exec = nullptr; p->have_graph = p->have_seen = false; p->graph_nsteps = 0;
   p->ngeoms = 0;
   cudaError_t e = cudaMalloc((void **)&p->scratch, sizeof(double) * 3 * (size_t)Lx * Ly);
@@ -269,6 +272,7 @@ int swalbe_plan_destroy(swalbe_plan *plan) {
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
   if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
   cudaFree(plan->scratch);
+  cudaFree(plan->log_part);
   delete plan;
   return 0;
 }
@@ -315,7 +319,7 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
   const GraphKey key = make_graph_key(st, prm, nsteps, flags);
   if (plan->have_graph && memcmp(&key, &plan->graph_key, sizeof(key)) == 0) {
     SW_CUDA(cudaGraphLaunch(plan->graph_exec, stream));
-    count_launch((unsigned)plan->graph_nsteps);
+    count_launch((unsigned)plan->graph_launches);
     return 0;
   }
   if (!(plan->have_seen && memcmp(&key, &plan->seen_key, sizeof(key)) == 0)) {  // first sighting: plain launches
@@ -326,7 +330,9 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
   // cannot be captured), instantiate, and launch the graph in the caller's stream
   if (!plan->cap_stream) SW_CUDA(cudaStreamCreateWithFlags(&plan->cap_stream, cudaStreamNonBlocking));
   SW_CUDA(cudaStreamBeginCapture(plan->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const unsigned long long launches0 = swalbe_launch_count();
   const int rc = enqueue_steps(plan, st, prm, nsteps, step0, flags, logs, plan->cap_stream);
+  const int captured = (int)(swalbe_launch_count() - launches0);
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(plan->cap_stream, &graph);
   if (rc != 0 || ce != cudaSuccess || !graph) {  // capture failed: fall back to plain launches, never to silence
@@ -343,7 +349,7 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
     plan->graph_exec = nullptr;
     return set_error(SWALBE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
   }
-  plan->graph_key = key; plan->have_graph = true; plan->graph_nsteps = nsteps;
+  plan->graph_key = key; plan->have_graph = true; plan->graph_nsteps = nsteps; plan->graph_launches = captured;
   SW_CUDA(cudaGraphLaunch(plan->graph_exec, stream));
   return 0;
 }
@@ -429,6 +435,7 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   int s_begin = 0;
   {
     a.h_in = A[0]; a.ux_in = A[1]; a.uy_in = A[2];
+    a.log_min = log_mm ? logs->hmin : nullptr; a.log_wet = log_wet ? logs->wetted : nullptr;  // (eligibility only)
     int R = 0;
     size_t smem_bytes = 0;
     const int ncl = skip_aux ? nsteps : nsteps - 1;
@@ -440,9 +447,20 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
       ca.a.f_out = st->fout;
       ca.a.f_out2 = ncl == nsteps ? st->ftemp : nullptr;  // fout == ftemp on return (src/collide.jl:103)
       ca.nsteps = ncl; ca.lazy = lazy ? 1 : 0; ca.rows_max = R;
-      ca.log_min = log_mm ? logs->hmin : nullptr; ca.log_max = log_mm ? logs->hmax : nullptr;
-      ca.log_wet = log_wet ? logs->wetted : nullptr;
+      if (log_mm || log_wet) {
+        const size_t need = (size_t)ncl * C * 3;
+        if (need > plan->log_part_doubles) {  // (one-time growth; loops with logs are never graph-captured)
+          if (plan->log_part) SW_CUDA(cudaFree(plan->log_part));
+          plan->log_part = nullptr; plan->log_part_doubles = 0;
+          SW_CUDA(cudaMalloc((void **)&plan->log_part, need * sizeof(double)));
+          plan->log_part_doubles = need;
+        }
+        ca.log_part = plan->log_part;
+      }
       if (int e = launch_cluster(ca, key_mid, C, smem_bytes, stream)) return e;
+      if (ca.log_part)
+        if (int e = launch_cluster_logs(ca.log_part, C, ncl, log_mm ? logs->hmin : nullptr, log_mm ? logs->hmax : nullptr,
+                                        log_wet ? logs->wetted : nullptr, stream)) return e;
       s_begin = ncl;
     }
   }

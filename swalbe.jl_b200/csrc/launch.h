@@ -43,6 +43,8 @@ bool bulk_eligible(int Lx, size_t ncells);
 struct ClusterArgs;
 int cluster_plan(const KernelKey &key, const FusedArgs &a, int *rows_max, size_t *smem_bytes);
 int launch_cluster(const ClusterArgs &ca, const KernelKey &key, int C, size_t smem_bytes, cudaStream_t stream);
+int launch_cluster_logs(const double *part, int C, int nsteps, double *log_min, double *log_max, unsigned long long *log_wet,
+                        cudaStream_t stream);
 // small-lattice tile flavour of the strict lean step (tile.cu)
 bool tile_eligible(const KernelKey &key, const FusedArgs &a);
 int launch_tile(const FusedArgs &a, const KernelKey &key, cudaStream_t stream);

@@ -22,7 +22,7 @@
 struct Emu3 {
   unsigned x = 0, y = 0, z = 0;
 };
-static thread_local Emu3 threadIdx, blockIdx;
+static thread_local Emu3 threadIdx, blockIdx, blockDim;
 static pthread_barrier_t g_cta_barrier;
 static double *g_dynamic_smem = nullptr;
 // cluster launches run several CTAs at once: each OS thread then carries its own CTA's barrier / smem / shuffle state
@@ -291,8 +291,15 @@ int simt_cluster_steps(const SimtStep *s, int nsteps, int C, int lazy) {
   cluster_kernel_fn k = s->g == 0.0 ? cluster_kernel<true>(ca.a.pc.pmode) : cluster_kernel<false>(ca.a.pc.pmode);
   if (!k) return -1;
   ca.nsteps = nsteps; ca.lazy = lazy; ca.rows_max = (s->Ly + C - 1) / C;
-  ca.log_min = s->log_min; ca.log_max = s->log_max; ca.log_wet = s->log_wet;
+  std::vector<double> part((size_t)nsteps * C * 3, 0.0);
+  const bool logs = s->log_min || s->log_wet;
+  ca.log_part = logs ? part.data() : nullptr;
   launch_cluster_emul(k, (unsigned)C, CENT, cluster_smem_doubles(s->Lx, ca.rows_max), ca);
+  if (logs)
+    for (int q = 0; q < nsteps; ++q) {  // k_cluster_logs: one CUDA thread per step
+      threadIdx.x = q; blockIdx.x = 0;
+      k_cluster_logs(part.data(), C, nsteps, s->log_min, s->log_max, s->log_wet);
+    }
   return 0;
 }
 

@@ -445,7 +445,9 @@ def test_repeated_loops_replay_a_cuda_graph_bitwise(sw, prm_kw, tau_pops, nsteps
     for rep in range(4):
         c0 = lib.swalbe_launch_count()
         sw.fused_steps(st, sysc, nsteps)
-        assert lib.swalbe_launch_count() - c0 == nsteps, rep
+        # (one kernel per step -- or, for a lattice that fits a thread-block cluster at tau == 1, the persistent kernel
+        #  for the first nsteps - 1 steps plus the materialising step)
+        assert lib.swalbe_launch_count() - c0 == (2 if (small_lattice_flavour == "cluster" and not tau_pops) else nsteps), rep
         oc.time_loop(ref, p, nsteps=nsteps)
         _compare(st, ref, what=f"repetition {rep}: ")
     # same shapes, different surface tension: a new key -> plain launches again, no stale replay

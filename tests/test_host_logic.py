@@ -114,3 +114,13 @@ def test_wetted_call_shapes(fake):  # src/measures.jl:6-17; known answers of tes
     with pytest.raises(TypeError):
         sw.wetted(area_size, maxheight, 2)
 
+
+
+def test_cluster_kernel_division_free_row_index():
+    """csrc/cluster.cuh computes the row of a slab-local site index as int((idx + 0.5f) * (1.0f / Lx)) inside the step
+    loop; csrc/cluster.cu admits Lx <= 1024 and idx < 65536.  Exact over that whole range."""
+    idx = np.arange(0, 65536, dtype=np.int64)
+    for Lx in range(1, 1025):
+        inv = np.float32(1.0) / np.float32(Lx)
+        got = ((idx.astype(np.float32) + np.float32(0.5)) * inv).astype(np.int64)
+        assert np.array_equal(got, idx // Lx), Lx
