@@ -237,6 +237,50 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *state, const swalbe_
                      unsigned long long step0, int flags, const swalbe_loop_logs *logs, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The 1-D (D1Q3) family: State_1D / SysConst_1D, src/initialize.jl:587-598.  The reference runs it
+ * on the CPU only (no device string in its 1-D allocator or drivers), so these entry points have no upstream GPU
+ * counterpart; they take DEVICE vectors of length L (populations: three contiguous length-L columns, column k =
+ * population k with c0 = 0, c1 = +1, c2 = -1, src/collide.jl:194-196, :303-309).
+ * ------------------------------------------------------------------------------------------- */
+
+/* equilibrium!(feq, height, velocity, gravity)               src/equilibrium.jl:169-181 */
+int swalbe_equilibrium_d1q3(double *feq, const double *height, const double *vel, double g, int L, void *stream);
+/* BGKandStream!(fout, feq, ftemp, F::Vector, tau)            src/collide.jl:179-201 (fout == ftemp on return) */
+int swalbe_bgk_stream_d1q3(double *fout, const double *feq, double *ftemp, const double *F, double tau, int L, void *stream);
+/* moments!(height::Vector, vel, fout)                        src/moments.jl:54-62 */
+int swalbe_moments_d1q3(double *height, double *vel, const double *fout, int L, void *stream);
+/* filmpressure!(output::Vector, f, dgrad, gamma, theta, n, m, hmin, hcrit)   src/pressure.jl:196-227 (variant FAST)
+ * filmpressure!(state::LBM_state_1D, sys; ...)                              src/pressure.jl:230-256 (POWER_BROAD)
+ * dgrad (L x 2 in the reference) is accepted for signature parity and never touched. */
+int swalbe_filmpressure_1d(double *pressure, const double *height, double *dgrad, double gamma, double cospi_theta,
+                           const double *cospi_theta_field, int n, int m, double hmin, double hcrit, int pressure_variant,
+                           int L, void *stream);
+/* ∇f!(output::Vector, f, dgrad, a) | ∇f!(output, f::Vector, dgrad)   src/differences.jl:208-230 (a == NULL: no multiplier);
+ * with f = pressure, a = height this is h∇p!(state::LBM_state_1D)    src/forcing.jl:189-198 */
+int swalbe_grad_1d(double *output, const double *f, const double *a, int L, void *stream);
+/* ∇²f!(output, f::Vector, dgrad)                             src/differences.jl:77-85 */
+int swalbe_lap_1d(double *output, const double *f, int L, void *stream);
+/* slippage!(slip, height, vel, delta, mu)                    src/forcing.jl:68-71 */
+int swalbe_slippage_1d(double *slip, const double *height, const double *vel, double delta, double mu, int L, void *stream);
+/* state.F .= -state.h∇p .- state.slip                        src/simulate.jl:110 */
+int swalbe_force_sum_1d(double *F, const double *hgradp, const double *slip, int L, void *stream);
+
+/* State_1D  src/initialize.jl:587-598 */
+typedef struct swalbe_state_1d {
+  double *fout, *ftemp, *feq;                     /* L*3 */
+  double *height, *vel, *pressure, *F, *slip, *hgradp; /* L */
+  double *dgrad;                                  /* L*2 scratch of the reference; unused, may be NULL */
+} swalbe_state_1d;
+
+/* nsteps iterations of time_loop(sys::SysConst_1D, state::State_1D[, theta | Δh])   src/simulate.jl:98-157.
+ * params: the Taumucs fields and pressure_variant / cospi_theta[_field] of swalbe_params (slip variant, inclination and
+ * thermal fields are ignored); flags: SWALBE_LOOP_SKIP_AUX; logs: hmin / hmax per step (wetted is ignored).
+ * Lattices that fit the shared memory of one CTA (L <= ~7000 at tau == 1) run all steps but the materialising one
+ * inside a single persistent launch.  On return every field of the state holds what the reference's holds. */
+int swalbe_time_loop_1d(const swalbe_state_1d *state, const swalbe_params *params, int L, int nsteps, int flags,
+                        const swalbe_loop_logs *logs, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU: row-slab decomposition along j (Ly), one process per GPU, halo rows over NCCL send/recv.
  * The reference has no multi-GPU path; this is new.  Rank r owns global rows
  * [r*Ly/nranks, (r+1)*Ly/nranks) of every plane; Ly % nranks must be 0.

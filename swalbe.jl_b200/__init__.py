@@ -20,8 +20,9 @@ import math
 
 import numpy as np
 
-from . import _lib
+from . import _lib, one_d
 from ._lib import DomainError, SwalbeError  # noqa: F401
+from .one_d import CuState_1D, SysConst_1D  # noqa: F401
 
 __all__ = [
     "Taumucs", "SysConst", "Sys_const", "Sys", "CuState", "CuState_thermal", "Swalbe_state", "Field", "cospi",
@@ -31,7 +32,7 @@ __all__ = [
     "field_stats", "DomainError", "SwalbeError", "JULIA_NAMES", "viewdists", "viewneighbors", "power_broad", "power_2",
     "power_3", "fast_93", "fast_32", "fused_steps", "singledroplet", "cospi_field", "torus", "rivulet", "sinewave2d",
     "randinterface", "circshift", "move_substrate", "restart_from_height", "save_heights", "dump_height_slab",
-    "load_height_slab", "SnapshotBuffer",
+    "load_height_slab", "SnapshotBuffer", "SysConst_1D", "CuState_1D", "one_d",
 ]
 
 
@@ -116,10 +117,13 @@ class Field:
     reversed shape (K, Ly, Lx); ``jl`` is a permuted view indexed [i, j, k] like Julia (0-based).
     """
 
-    def __init__(self, Lx, Ly, K=None, fill=0.0):
+    def __init__(self, Lx, Ly=None, K=None, fill=0.0):
         torch = _torch()
-        self.shape = (Lx, Ly) if K is None else (Lx, Ly, K)
-        tshape = (Ly, Lx) if K is None else (K, Ly, Lx)
+        if Ly is None:  # a Julia Vector (the 1-D family, swalbe_b200.one_d)
+            self.shape, tshape = (Lx,), (Lx,)
+        else:
+            self.shape = (Lx, Ly) if K is None else (Lx, Ly, K)
+            tshape = (Ly, Lx) if K is None else (K, Ly, Lx)
         self.t = torch.full(tshape, float(fill), dtype=torch.float64, device="cuda")
         self.jl = self.t.permute(*reversed(range(self.t.dim())))
         self._gen = 0  # bumped by touch(): writes through the raw pointer that torch's version counter cannot see
@@ -224,10 +228,14 @@ class _Plan:
             pass
 
 
-def Sys(sysc: SysConst, device: str, *legacy, T=float, kind: str = "simple"):
+def Sys(sysc: SysConst, device: str = "GPU", *legacy, T=float, kind: str = "simple"):
     """Sys(sysc, device; T, kind)  src/initialize.jl:491-572  -> CuState / CuState_thermal, and the older tuple form
     Sys(sysc, device, exotic::Bool, T)  src/initialize.jl:358-475  -> (fout, ftemp, feq, height, velx, vely, vsq,
     pressure, dgrad, Fx, Fy, slipx, slipy, h∇px, h∇py[, fthermalx, fthermaly]).  Only the "GPU" device string exists."""
+    if isinstance(sysc, SysConst_1D):  # Sys(sysc::Consts_1D; T, kind)  src/initialize.jl:587-616 (no device argument upstream)
+        if kind != "simple":
+            raise SwalbeError(f'Sys(::SysConst_1D; kind="{kind}"): only the "simple" 1-D state is built on the device')
+        return CuState_1D(sysc.L)
     if device != "GPU":
         raise SwalbeError(f'Sys(sys, "{device}"): swalbe_b200 implements the "GPU" path only (no CPU fallback)')
     if legacy:
@@ -253,7 +261,12 @@ def Sys(sysc: SysConst, device: str, *legacy, T=float, kind: str = "simple"):
 
 
 def _dims(f: Field):
-    return f.shape[0], f.shape[1]
+    return (f.shape[0], f.shape[1]) if len(f.shape) > 1 else (f.shape[0], 1)  # (a Vector is an L x 1 lattice)
+
+
+def _is_1d(x) -> bool:
+    """State_1D / Vector arguments: the operator belongs to the 1-D family (swalbe_b200.one_d)"""
+    return isinstance(x, one_d.CuState_1D) or (isinstance(x, Field) and len(x.shape) == 1)
 
 
 def equilibrium(*args):
@@ -261,6 +274,11 @@ def equilibrium(*args):
     if isinstance(args[0], CuState):
         st, sys_ = args
         return equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, sys_.param.g)
+    if isinstance(args[0], CuState_1D):  # equilibrium!(state::State_1D, sys)   src/equilibrium.jl:183-184
+        st, sys_ = args
+        return one_d.equilibrium(st.feq, st.height, st.vel, sys_.param.g)
+    if len(args) == 4:                   # equilibrium!(feq, height, velocity, gravity)   :169
+        return one_d.equilibrium(*args)
     feq, h, ux, uy, vsq, g = args
     _lib.call("swalbe_equilibrium_d2q9", _ptr(feq), _ptr(h), _ptr(ux), _ptr(uy), _ptr(vsq), float(g), *_dims(h), _stream())
 
@@ -271,6 +289,11 @@ def BGKandStream(*args, τ=None, tau=None):
         st, sys_ = args
         t = τ if τ is not None else (tau if tau is not None else sys_.param.tau)
         return BGKandStream(st.fout, st.feq, st.ftemp, st.Fx, st.Fy, t)
+    if isinstance(args[0], CuState_1D):  # src/collide.jl:203-204
+        st, sys_ = args
+        return one_d.BGKandStream(st.fout, st.feq, st.ftemp, st.F, sys_.param.tau)
+    if len(args) == 5:                   # BGKandStream!(fout, feq, ftemp, F::Vector, τ)   :179
+        return one_d.BGKandStream(*args)
     fout, feq, ftemp, Fx, Fy, t = args
     _lib.call("swalbe_bgk_stream_d2q9", _ptr(fout), _ptr(feq), _ptr(ftemp), _ptr(Fx), _ptr(Fy), float(t), *_dims(Fx), _stream())
 
@@ -280,6 +303,11 @@ def moments(*args):
     if isinstance(args[0], CuState):
         st = args[0]
         return moments(st.height, st.velx, st.vely, st.fout)
+    if isinstance(args[0], CuState_1D):  # src/moments.jl:66
+        st = args[0]
+        return one_d.moments(st.height, st.vel, st.fout)
+    if len(args) == 3:                   # moments!(height::Vector, vel, fout)   :54
+        return one_d.moments(*args)
     h, ux, uy, f = args
     _lib.call("swalbe_moments_d2q9", _ptr(h), _ptr(ux), _ptr(uy), _ptr(f), *_dims(h), _stream())
 
@@ -309,6 +337,14 @@ def filmpressure(*args, θ=None, γ=None, n=None, m=None, hmin=None, hcrit=None,
     filmpressure!(state::CuState_thermal, sys)                         src/pressure.jl:117 (array form, no keywords)"""
     θ = θ if θ is not None else theta
     γ = γ if γ is not None else gamma
+    if isinstance(args[0], CuState_1D):  # filmpressure!(state::LBM_state_1D, sys; θ, n, m, hmin, hcrit, γ)   src/pressure.jl:230-256
+        st, sys_ = args
+        p = sys_.param
+        return one_d.filmpressure(st.pressure, st.height, st.dgrad, p.gamma if γ is None else γ, p.theta if θ is None else θ,
+                                  p.n if n is None else n, p.m if m is None else m, p.hmin if hmin is None else hmin,
+                                  p.hcrit if hcrit is None else hcrit, variant=_lib.PRESSURE_POWER_BROAD)
+    if _is_1d(args[0]):                  # filmpressure!(output::Vector, f, dgrad, γ, θ, n, m, hmin, hcrit)   :196
+        return one_d.filmpressure(*args)
     if isinstance(args[0], CuState):
         st, sys_ = args
         p = sys_.param
@@ -330,11 +366,15 @@ def filmpressure(*args, θ=None, γ=None, n=None, m=None, hmin=None, hcrit=None,
 
 def hgradp(st: CuState):
     """h∇p!(state)   src/forcing.jl:168-187"""
+    if isinstance(st, CuState_1D):
+        return one_d.hgradp(st)
     _lib.call("swalbe_hgradp", st.hgradpx.ptr, st.hgradpy.ptr, st.pressure.ptr, st.height.ptr, st.Lx, st.Ly, _stream())
 
 
 def gradf(outx, outy, f, *rest):
     """∇f!(outx, outy, f) | ∇f!(outx, outy, f, a) | ∇f!(outx, outy, f, dgrad, a)   src/differences.jl:153-206"""
+    if _is_1d(outx):  # ∇f!(output::Vector, f, dgrad[, a])   src/differences.jl:208-230
+        return one_d.gradf(outx, outy, f, *rest)
     a = rest[-1] if rest else None
     if a is not None and not isinstance(a, Field):  # a scalar multiplier broadcasts like the reference's `a .* (...)`
         a = Field(*_dims(f), fill=float(a))
@@ -343,10 +383,17 @@ def gradf(outx, outy, f, *rest):
 
 def laplacianf(out, f, γ):
     """∇²f!(output, f, γ)   src/differences.jl:57-75"""
+    if _is_1d(out):  # ∇²f!(output, f::Vector, dgrad)   :77-85
+        return one_d.laplacianf(out, f, γ)
     _lib.call("swalbe_lap9", _ptr(out), _ptr(f), float(γ), *_dims(f), _stream())
 
 
 def _slip(variant, args):
+    if isinstance(args[0], CuState_1D):  # slippage!(state::LBM_state_1D, sys)
+        st, sys_ = args
+        return one_d.slippage(st.slip, st.height, st.vel, sys_.param.delta, sys_.param.mu)
+    if _is_1d(args[0]):                  # slippage!(slip, height, vel, δ, μ)   src/forcing.jl:68-71
+        return one_d.slippage(*args)
     if isinstance(args[0], CuState):
         st, sys_ = args
         p = sys_.param
@@ -416,6 +463,8 @@ def inclination(α, st: CuState, t=1000, tstart=0, tsmooth=1):
 def update(st: CuState):
     """The inline force sum of the drivers, `state.Fx .= -state.h∇px .- state.slipx` (src/simulate.jl:18-19);
     for thermal states `... .- state.kbtx` (scripts/Rivulet_stability.jl:123-124).  north_star calls it update!."""
+    if isinstance(st, CuState_1D):
+        return one_d.update(st)
     kx, ky = (st.kbtx.ptr, st.kbty.ptr) if st.thermal else (None, None)
     _lib.call("swalbe_force_sum", st.Fx.ptr, st.Fy.ptr, st.hgradpx.ptr, st.hgradpy.ptr, st.slipx.ptr, st.slipy.ptr, kx, ky,
               st.Lx, st.Ly, _stream())
@@ -596,6 +645,8 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, la
     are only written by the last step of a chunk (`lazy_populations`: ω = 0, nothing reads them -- 48 instead of 120
     bytes per lattice update, same bits on return), at τ ≠ 1 every chunk after the first vouches for its moments so that
     all of its steps derive h and u from the populations (144 instead of 192 bytes)."""
+    if isinstance(sys_, SysConst_1D):
+        return one_d.time_loop(sys_, st, *extra, verbose=verbose)
     p = sys_.param
     θ, dh, cb, measure = None, None, None, None
     if len(extra) == 1 and isinstance(extra[0], list):
@@ -632,8 +683,10 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, la
     return st if cb is None else (st, measure)
 
 
-def run_flat(sys_: SysConst, device: str, verbos=True):
-    """run_flat  src/simulate.jl:236-245"""
+def run_flat(sys_: SysConst, device: str = "GPU", verbos=True):
+    """run_flat  src/simulate.jl:236-245 (2-D), :247-256 (1-D: run_flat(sys::SysConst_1D))"""
+    if isinstance(sys_, SysConst_1D):
+        return one_d.run_flat(sys_, verbos=verbos)
     print("Simulating a flat interface without driving forces (nothing should happen) in two dimensions")
     st = Sys(sys_, device)
     st.height.set(1.0)
@@ -641,8 +694,10 @@ def run_flat(sys_: SysConst, device: str, verbos=True):
     return st.height
 
 
-def run_random(sys_: SysConst, device: str, h0=1.0, ϵ=0.01, verbos=True, rng=None):
-    """run_random  src/simulate.jl:286-294 (randinterface! src/initialvalues.jl:23-33 with a NumPy generator)"""
+def run_random(sys_: SysConst, device: str = "GPU", h0=1.0, ϵ=0.01, verbos=True, rng=None):
+    """run_random  src/simulate.jl:286-294 (randinterface! src/initialvalues.jl:23-33 with a NumPy generator); 1-D :296-304"""
+    if isinstance(sys_, SysConst_1D):
+        return one_d.run_random(sys_, h0=h0, ϵ=ϵ, verbos=verbos, rng=rng)
     print("Simulating a random undulated interface in two dimensions")
     st = Sys(sys_, device)
     rng = rng if rng is not None else np.random.default_rng()

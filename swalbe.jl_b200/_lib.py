@@ -47,6 +47,11 @@ class CParams(C.Structure):
         ("use_thermal", _i), ("seed", _u64)]
 
 
+class CState1D(C.Structure):
+    """struct swalbe_state_1d"""
+    _fields_ = [(n, _vp) for n in ("fout", "ftemp", "feq", "height", "vel", "pressure", "F", "slip", "hgradp", "dgrad")]
+
+
 class CLogs(C.Structure):
     """struct swalbe_loop_logs"""
     _fields_ = [("hmin", _vp), ("hmax", _vp), ("wetted", _vp), ("hthresh", _d)]
@@ -81,6 +86,15 @@ SIGNATURES = {
     "swalbe_plan_create": [C.POINTER(_vp), _i, _i],
     "swalbe_plan_destroy": [_vp],
     "swalbe_time_loop": [_vp, C.POINTER(CState), C.POINTER(CParams), _i, _u64, _i, C.POINTER(CLogs), _vp],
+    "swalbe_equilibrium_d1q3": [_vp, _vp, _vp, _d, _i, _vp],
+    "swalbe_bgk_stream_d1q3": [_vp, _vp, _vp, _vp, _d, _i, _vp],
+    "swalbe_moments_d1q3": [_vp, _vp, _vp, _i, _vp],
+    "swalbe_filmpressure_1d": [_vp, _vp, _vp, _d, _d, _vp, _i, _i, _d, _d, _i, _i, _vp],
+    "swalbe_grad_1d": [_vp, _vp, _vp, _i, _vp],
+    "swalbe_lap_1d": [_vp, _vp, _i, _vp],
+    "swalbe_slippage_1d": [_vp, _vp, _vp, _d, _d, _i, _vp],
+    "swalbe_force_sum_1d": [_vp, _vp, _vp, _i, _vp],
+    "swalbe_time_loop_1d": [C.POINTER(CState1D), C.POINTER(CParams), _i, _i, _i, C.POINTER(CLogs), _vp],
     "swalbe_dist_unique_id": [_vp],
     "swalbe_dist_create": [C.POINTER(_vp), _vp, _i, _i, _i, _i, C.POINTER(CParams)],
     "swalbe_dist_destroy": [_vp],

@@ -1,0 +1,421 @@
+// The 1-D (D1Q3) thin-film family of Swalbe.jl on the device: State_1D / SysConst_1D,
+// src/initialize.jl:587-598; loop body src/simulate.jl:98-116.  The reference runs it on the CPU only (no device string
+// in its 1-D allocator or drivers) at L ~ 1e3 sites, so there is no HBM case here: one step is ~30 FP64 operations per
+// site and pure latency.  Design: every thread recomputes the two neighbour sites it pulls from (5 pressures, 3
+// collisions per site), which leaves ONE barrier per step; lattices that fit the shared memory of one CTA run ALL the
+// steps of a call inside one persistent launch (h, v [and the populations at tau != 1] double-buffered in shared
+// memory), larger ones take one launch per step on global memory with the same site function.
+// Arithmetic: the reference's expressions in its evaluation order, no FMA contraction.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace swalbe {
+namespace {
+
+struct Consts1D {
+  PressureConsts pc;
+  SlipConsts sc;
+  double g05, g025;      // 0.5*g, 0.25*g
+  double omega, invtau;
+  int tau1, array_form;  // array form: fast_93 / fast_32 (src/pressure.jl:196-227); state form: power_broad (:230-256)
+  const double *ct_field;
+};
+
+__device__ __forceinline__ int wrap1(int i, int L) { return i < 0 ? i + L : (i >= L ? i - L : i); }
+
+// film pressure at site j   src/pressure.jl:196-227 / :230-256:  -γ (K pw) - γ ((hip - 2h) + him)
+__device__ __forceinline__ double pressure_1d(const double *h, int j, int L, const Consts1D &c) {
+  const double hc = h[j], hip = h[wrap1(j - 1, L)], him = h[wrap1(j + 1, L)];
+  const double x = div_exact(c.pc.hmin, hc + c.pc.hcrit);
+  const double pw = disjoining_powers(x, c.pc.pmode, c.pc.n, c.pc.m);
+  const double kappa = c.ct_field ? kappa_from_field(c.ct_field[j], c.pc) : c.pc.kappa;
+  return (-c.pc.gamma * (kappa * pw)) - c.pc.gamma * ((hip - 2.0 * hc) + him);
+}
+
+struct Site1D {
+  double p, hgp, slip, F, fe[3], fs[3];
+};
+
+// everything the loop body computes at site j up to the post-collision populations
+__device__ __forceinline__ void collide_1d(const double *h, const double *v, const double *ft, size_t fstride, int j, int L,
+                                           const Consts1D &c, Site1D &s) {
+  const int jm = wrap1(j - 1, L), jp = wrap1(j + 1, L);
+  s.p = pressure_1d(h, j, L, c);
+  const double pip = pressure_1d(h, jm, L, c), pim = pressure_1d(h, jp, L, c);  // circshift(p, 1)[j] = p[j-1], (p, -1)[j] = p[j+1]
+  const double hc = h[j], vc = v[j];
+  s.hgp = (hc * -0.5) * (pip - pim);                                        // src/forcing.jl:189-198
+  const double den = ((2.0 * (hc * hc)) + c.sc.delta6 * hc) + c.sc.delta3s;  // src/forcing.jl:68-71
+  s.slip = div_exact((c.sc.mu6 * hc) * vc, den);
+  s.F = (-s.hgp) - s.slip;                                                  // src/simulate.jl:112
+  const double vv = vc * vc;                                                // src/equilibrium.jl:173-178
+  s.fe[0] = hc * ((1.0 - c.g05 * hc) - vv);
+  s.fe[1] = hc * ((c.g025 * hc + 0.5 * vc) + 0.5 * vv);
+  s.fe[2] = hc * ((c.g025 * hc - 0.5 * vc) + 0.5 * vv);
+  const double hf = 0.5 * s.F;                                              // src/collide.jl:186-191
+  if (c.tau1) {
+    s.fs[0] = s.fe[0]; s.fs[1] = s.fe[1] + hf; s.fs[2] = s.fe[2] - hf;
+  } else {
+    s.fs[0] = c.omega * ft[j] + c.invtau * s.fe[0];
+    s.fs[1] = (c.omega * ft[j + fstride] + c.invtau * s.fe[1]) + hf;
+    s.fs[2] = (c.omega * ft[j + 2 * fstride] + c.invtau * s.fe[2]) - hf;
+  }
+}
+
+struct Out1D {
+  double h, v, f[3];
+};
+
+// one site of one step: pull f1 from i-1, f2 from i+1 (src/collide.jl:194-196), moments (src/moments.jl:54-62)
+__device__ __forceinline__ void step_site_1d(const double *h, const double *v, const double *ft, size_t fstride, int i, int L,
+                                             const Consts1D &c, Out1D &o, Site1D *own) {
+  Site1D a, b, m;
+  collide_1d(h, v, ft, fstride, i, L, c, m);
+  collide_1d(h, v, ft, fstride, wrap1(i - 1, L), L, c, a);
+  collide_1d(h, v, ft, fstride, wrap1(i + 1, L), L, c, b);
+  o.f[0] = m.fs[0]; o.f[1] = a.fs[1]; o.f[2] = b.fs[2];
+  o.h = ((0.0 + o.f[0]) + o.f[1]) + o.f[2];
+  o.v = div_exact(o.f[1] - o.f[2], o.h);
+  if (own) *own = m;
+}
+
+struct Loop1DArgs {
+  int L, nsteps;
+  Consts1D c;
+  double *height, *vel, *fout, *ftemp;  // state planes (fout / ftemp: L x 3)
+  double *log_min, *log_max;            // nsteps slots or NULL
+};
+
+constexpr int T1D = 1024;
+
+// Persistent loop: the whole lattice in the shared memory of one CTA for all the steps of the call; the state planes
+// are read once and written once.  smem: h[2][L] v[2][L] (+ f[2][3][L] at tau != 1).
+__global__ void __launch_bounds__(T1D, 1) k_loop_1d(const __grid_constant__ Loop1DArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double r_min[2][T1D / 32], r_max[2][T1D / 32];  // (by step parity: thread 0 folds step s while the others run s+1)
+  const int L = a.L, tid = threadIdx.x;
+  double *sh = sm, *sv = sm + 2 * (size_t)L, *sf = sm + 4 * (size_t)L;
+  const bool pops = !a.c.tau1;
+  for (int i = tid; i < L; i += T1D) {
+    sh[i] = a.height[i]; sv[i] = a.vel[i];
+    if (pops) { sf[i] = a.ftemp[i]; sf[L + i] = a.ftemp[L + i]; sf[2 * L + i] = a.ftemp[2 * (size_t)L + i]; }
+  }
+  __syncthreads();
+  for (int s = 0; s < a.nsteps; ++s) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    const double *h = sh + cur * (size_t)L, *v = sv + cur * (size_t)L, *ft = sf + cur * 3 * (size_t)L;
+    double *hn = sh + nxt * (size_t)L, *vn = sv + nxt * (size_t)L, *fn = sf + nxt * 3 * (size_t)L;
+    double d_min = INFINITY, d_max = -INFINITY;
+    const bool last = s == a.nsteps - 1;
+    for (int i = tid; i < L; i += T1D) {
+      Out1D o;
+      step_site_1d(h, v, ft, (size_t)L, i, L, a.c, o, nullptr);
+      if (a.log_min) { d_min = fmin(d_min, h[i]); d_max = fmax(d_max, h[i]); }
+      hn[i] = o.h; vn[i] = o.v;
+      if (pops) { fn[i] = o.f[0]; fn[L + i] = o.f[1]; fn[2 * L + i] = o.f[2]; }
+      if (last) {
+        a.height[i] = o.h; a.vel[i] = o.v;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { a.fout[(size_t)k * L + i] = o.f[k]; a.ftemp[(size_t)k * L + i] = o.f[k]; }
+      }
+    }
+    if (a.log_min) {  // max - min of the pre-step height (src/simulate.jl:147)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d_min = fmin(d_min, __shfl_down_sync(0xffffffffu, d_min, o));
+        d_max = fmax(d_max, __shfl_down_sync(0xffffffffu, d_max, o));
+      }
+      if ((tid & 31) == 0) { r_min[cur][tid >> 5] = d_min; r_max[cur][tid >> 5] = d_max; }
+    }
+    __syncthreads();
+    if (a.log_min && tid == 0) {
+      for (int w = 1; w < T1D / 32; ++w) { d_min = fmin(d_min, r_min[cur][w]); d_max = fmax(d_max, r_max[cur][w]); }
+      a.log_min[s] = d_min; a.log_max[s] = d_max;
+    }
+  }
+}
+
+// One step on global memory (any L); `aux`: also materialise pressure / h∇p / slip / F / feq like the reference's state
+__global__ void __launch_bounds__(256) k_step_1d(int L, Consts1D c, const double *__restrict__ h, const double *__restrict__ v,
+                                                  const double *__restrict__ ft, double *__restrict__ hn, double *__restrict__ vn,
+                                                  double *__restrict__ f_out, double *__restrict__ f_out2, double *pressure,
+                                                  double *hgp, double *slip, double *F, double *feq, double *log_min,
+                                                  double *log_max) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d_min = INFINITY, d_max = -INFINITY;
+  if (i < L) {
+    Out1D o;
+    Site1D m;
+    step_site_1d(h, v, ft, (size_t)L, i, L, c, o, &m);
+    d_min = d_max = h[i];
+    hn[i] = o.h; vn[i] = o.v;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      f_out[(size_t)k * L + i] = o.f[k];
+      if (f_out2) f_out2[(size_t)k * L + i] = o.f[k];
+    }
+    if (pressure) {
+      pressure[i] = m.p; hgp[i] = m.hgp; slip[i] = m.slip; F[i] = m.F;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) feq[(size_t)k * L + i] = m.fe[k];
+    }
+  }
+  if (log_min) {
+    __shared__ double r_min[8], r_max[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d_min = fmin(d_min, __shfl_down_sync(0xffffffffu, d_min, o));
+      d_max = fmax(d_max, __shfl_down_sync(0xffffffffu, d_max, o));
+    }
+    if ((threadIdx.x & 31) == 0) { r_min[threadIdx.x >> 5] = d_min; r_max[threadIdx.x >> 5] = d_max; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) { d_min = fmin(d_min, r_min[w]); d_max = fmax(d_max, r_max[w]); }
+      unsigned long long *pmn = (unsigned long long *)log_min, *pmx = (unsigned long long *)log_max;
+      unsigned long long old = *pmn;
+      while (d_min < __longlong_as_double((long long)old)) {
+        const unsigned long long seen = atomicCAS(pmn, old, (unsigned long long)__double_as_longlong(d_min));
+        if (seen == old) break;
+        old = seen;
+      }
+      old = *pmx;
+      while (d_max > __longlong_as_double((long long)old)) {
+        const unsigned long long seen = atomicCAS(pmx, old, (unsigned long long)__double_as_longlong(d_max));
+        if (seen == old) break;
+        old = seen;
+      }
+    }
+  }
+}
+
+// ---- per-operator array forms (for user-written 1-D loops) ------------------------------------------------------
+__global__ void k_eq_1d(double *feq, const double *h, const double *v, double g05, double g025, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const double hc = h[i], vc = v[i], vv = vc * vc;
+  feq[i] = hc * ((1.0 - g05 * hc) - vv);
+  feq[(size_t)L + i] = hc * ((g025 * hc + 0.5 * vc) + 0.5 * vv);
+  feq[2 * (size_t)L + i] = hc * ((g025 * hc - 0.5 * vc) + 0.5 * vv);
+}
+__global__ void k_bgk_1d(double *fout, const double *feq, double *ftemp, const double *F, double omega, double invtau, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pull form of collide + circshift! + copy: reads ftemp/feq/F at i-1, i, i+1
+  if (i >= L) return;
+  const int im = wrap1(i - 1, L), ip = wrap1(i + 1, L);
+  const size_t N = (size_t)L;
+  fout[i] = omega * ftemp[i] + invtau * feq[i];
+  fout[N + i] = (omega * ftemp[N + im] + invtau * feq[N + im]) + 0.5 * F[im];
+  fout[2 * N + i] = (omega * ftemp[2 * N + ip] + invtau * feq[2 * N + ip]) - 0.5 * F[ip];
+}
+__global__ void k_copy3_1d(double *dst, const double *src, int L) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * (size_t)L) dst[i] = src[i];
+}
+__global__ void k_moments_1d(double *h, double *v, const double *f, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const double f0 = f[i], f1 = f[(size_t)L + i], f2 = f[2 * (size_t)L + i];
+  const double hn = ((0.0 + f0) + f1) + f2;
+  h[i] = hn;
+  v[i] = div_exact(f1 - f2, hn);
+}
+__global__ void k_pressure_1d(double *p, const double *h, Consts1D c, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) p[i] = pressure_1d(h, i, L, c);
+}
+__global__ void k_grad_1d(double *out, const double *f, const double *a, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const double d = f[wrap1(i - 1, L)] - f[wrap1(i + 1, L)];
+  out[i] = a ? (a[i] * -0.5) * d : -0.5 * d;  // src/differences.jl:208-230
+}
+__global__ void k_lap_1d(double *out, const double *f, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) out[i] = (f[wrap1(i - 1, L)] - 2.0 * f[i]) + f[wrap1(i + 1, L)];  // src/differences.jl:77-85
+}
+__global__ void k_slip_1d(double *slip, const double *h, const double *v, SlipConsts sc, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const double hc = h[i];
+  slip[i] = div_exact((sc.mu6 * hc) * v[i], ((2.0 * (hc * hc)) + sc.delta6 * hc) + sc.delta3s);
+}
+__global__ void k_force_1d(double *F, const double *hgp, const double *slip, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) F[i] = (-hgp[i]) - slip[i];
+}
+__global__ void k_init_logs_1d(double *mn, double *mx, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { mn[i] = INFINITY; mx[i] = -INFINITY; }
+}
+
+int check_len(int L) {
+  if (L < 1) return set_error(SWALBE_ERR_EXTENT, "L = %d: the lattice needs at least one site", L);
+  return 0;
+}
+
+int fill_consts_1d(Consts1D &c, const swalbe_params &p) {
+  if (int e = resolve_pmode(p.pressure_variant, p.n, p.m, &c.pc.pmode)) return e;
+  if (!(p.tau > 0.0)) return set_error(SWALBE_ERR_ARG, "tau must be positive");
+  c.pc.gamma = p.gamma;
+  c.pc.kappa = host_kappa(p.cospi_theta, p.n, p.m, p.hmin);
+  c.pc.nm1 = (double)(p.n - 1); c.pc.mm1 = (double)(p.m - 1); c.pc.kden = (double)(p.n - p.m) * p.hmin;
+  c.pc.hmin = p.hmin; c.pc.hcrit = p.hcrit; c.pc.n = p.n; c.pc.m = p.m;
+  c.sc = make_slip(p.delta, p.mu, p.hcrit, SWALBE_SLIP_STANDARD);
+  volatile double a = 0.5 * p.g, b = 0.25 * p.g;
+  c.g05 = a; c.g025 = b;
+  volatile double it = 1.0 / p.tau;
+  volatile double om = 1.0 - it;
+  c.invtau = it; c.omega = om; c.tau1 = p.tau == 1.0;
+  c.array_form = p.pressure_variant == SWALBE_PRESSURE_FAST;
+  c.ct_field = p.cospi_theta_field;
+  return 0;
+}
+
+#define GRID1(L) ((unsigned)(((L) + 255) / 256)), 256, 0, (cudaStream_t)stream
+
+}  // namespace
+}  // namespace swalbe
+
+using namespace swalbe;
+
+extern "C" {
+
+int swalbe_equilibrium_d1q3(double *feq, const double *height, const double *vel, double g, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  volatile double a = 0.5 * g, b = 0.25 * g;
+  k_eq_1d<<<GRID1(L)>>>(feq, height, vel, a, b, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_bgk_stream_d1q3(double *fout, const double *feq, double *ftemp, const double *F, double tau, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!(tau > 0.0)) return set_error(SWALBE_ERR_ARG, "tau must be positive");
+  volatile double it = 1.0 / tau;
+  volatile double om = 1.0 - it;
+  k_bgk_1d<<<GRID1(L)>>>(fout, feq, ftemp, F, om, it, L);
+  SW_LAUNCH_CHECK();
+  k_copy3_1d<<<GRID1(3 * (size_t)L)>>>(ftemp, fout, L);  // fout == ftemp on return (src/collide.jl:199)
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_moments_d1q3(double *height, double *vel, const double *fout, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  k_moments_1d<<<GRID1(L)>>>(height, vel, fout, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_filmpressure_1d(double *pressure, const double *height, double *dgrad, double gamma, double cospi_theta,
+                           const double *cospi_theta_field, int n, int m, double hmin, double hcrit, int pressure_variant,
+                           int L, void *stream) {
+  (void)dgrad;
+  if (int e = check_len(L)) return e;
+  swalbe_params p = {};
+  p.tau = 1.0; p.gamma = gamma; p.cospi_theta = cospi_theta; p.cospi_theta_field = cospi_theta_field;
+  p.n = n; p.m = m; p.hmin = hmin; p.hcrit = hcrit; p.pressure_variant = pressure_variant;
+  Consts1D c = {};
+  if (int e = fill_consts_1d(c, p)) return e;
+  k_pressure_1d<<<GRID1(L)>>>(pressure, height, c, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_grad_1d(double *output, const double *f, const double *a, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  k_grad_1d<<<GRID1(L)>>>(output, f, a, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_lap_1d(double *output, const double *f, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  k_lap_1d<<<GRID1(L)>>>(output, f, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_slippage_1d(double *slip, const double *height, const double *vel, double delta, double mu, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  k_slip_1d<<<GRID1(L)>>>(slip, height, vel, make_slip(delta, mu, 0.0, SWALBE_SLIP_STANDARD), L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_force_sum_1d(double *F, const double *hgradp, const double *slip, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  k_force_1d<<<GRID1(L)>>>(F, hgradp, slip, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_time_loop_1d(const swalbe_state_1d *st, const swalbe_params *prm, int L, int nsteps, int flags,
+                        const swalbe_loop_logs *logs, void *stream_) {
+  if (!st || !prm) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop_1d: NULL state/params");
+  if (int e = check_len(L)) return e;
+  if (nsteps < 0) return set_error(SWALBE_ERR_ARG, "nsteps < 0");
+  if (nsteps == 0) return 0;
+#define NEED(f) if (!st->f) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop_1d: state." #f " is NULL")
+  NEED(fout); NEED(ftemp); NEED(feq); NEED(height); NEED(vel); NEED(pressure); NEED(F); NEED(slip); NEED(hgradp);
+#undef NEED
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Consts1D c = {};
+  if (int e = fill_consts_1d(c, *prm)) return e;
+  const bool skip_aux = (flags & SWALBE_LOOP_SKIP_AUX) != 0;
+  const bool log_mm = logs && logs->hmin && logs->hmax;
+  if (log_mm) {
+    k_init_logs_1d<<<(unsigned)((nsteps + 255) / 256), 256, 0, stream>>>(logs->hmin, logs->hmax, nsteps);
+    SW_LAUNCH_CHECK();
+  }
+  // steps [0, npers) inside one persistent launch when the lattice fits one CTA's shared memory; the last step (which
+  // materialises pressure / h∇p / slip / F / feq unless SKIP_AUX) and lattices that do not fit go step by step
+  int dev = 0, max_optin = 0;
+  SW_CUDA(cudaGetDevice(&dev));
+  SW_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t smem = (size_t)L * sizeof(double) * (c.tau1 ? 4 : 10);
+  int npers = skip_aux ? nsteps : nsteps - 1;
+  if (smem + 1024 > (size_t)max_optin || npers < 1) npers = 0;
+  if (npers > 0) {
+    SW_CUDA(cudaFuncSetAttribute(k_loop_1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Loop1DArgs a = {};
+    a.L = L; a.nsteps = npers; a.c = c;
+    a.height = st->height; a.vel = st->vel; a.fout = st->fout; a.ftemp = st->ftemp;
+    a.log_min = log_mm ? logs->hmin : nullptr; a.log_max = log_mm ? logs->hmax : nullptr;
+    k_loop_1d<<<1, T1D, smem, stream>>>(a);
+    SW_LAUNCH_CHECK();
+  }
+  if (npers == nsteps) return 0;
+  // step-by-step part: h, v ping-pong through a scratch pair (stream-ordered allocation, freed in stream order)
+  double *scratch = nullptr;
+  SW_CUDA(cudaMallocAsync((void **)&scratch, 2 * (size_t)L * sizeof(double), stream));
+  double *hA = st->height, *vA = st->vel, *hB = scratch, *vB = scratch + L;
+  bool src_is_A = true;
+  const int nrem = nsteps - npers;
+  if (nrem & 1) {  // arrange for the last step to land in the caller's planes
+    SW_CUDA(cudaMemcpyAsync(hB, hA, (size_t)L * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    SW_CUDA(cudaMemcpyAsync(vB, vA, (size_t)L * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    src_is_A = false;
+  }
+  bool fsrc_is_ftemp = true;  // tau != 1: the populations alternate between ftemp and fout
+  for (int s = npers; s < nsteps; ++s) {
+    const bool last = s == nsteps - 1, aux = last && !skip_aux;
+    const double *h = src_is_A ? hA : hB, *v = src_is_A ? vA : vB;
+    double *hn = src_is_A ? hB : hA, *vn = src_is_A ? vB : vA;
+    const double *ft = fsrc_is_ftemp ? st->ftemp : st->fout;
+    double *fo = c.tau1 ? st->fout : (fsrc_is_ftemp ? st->fout : st->ftemp);
+    k_step_1d<<<GRID1(L)>>>(L, c, h, v, ft, hn, vn, fo, (c.tau1 && last) ? st->ftemp : nullptr, aux ? st->pressure : nullptr,
+                            st->hgradp, st->slip, st->F, st->feq, log_mm ? logs->hmin + s : nullptr,
+                            log_mm ? logs->hmax + s : nullptr);
+    SW_LAUNCH_CHECK();
+    src_is_A = !src_is_A;
+    fsrc_is_ftemp = !fsrc_is_ftemp;
+  }
+  if (!c.tau1) {  // fout == ftemp on return: the newest populations are in the array written last
+    double *newest = fsrc_is_ftemp ? st->ftemp : st->fout, *other = fsrc_is_ftemp ? st->fout : st->ftemp;
+    SW_CUDA(cudaMemcpyAsync(other, newest, 3 * (size_t)L * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  }
+  SW_CUDA(cudaFreeAsync(scratch, stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -599,6 +599,132 @@ function last_loop_ms(sim::DistSim)
     return ms[]
 end
 
+# ---- the 1-D (D1Q3) family on the device (SURVEY.md 8f4) ----------------------------------------------------------
+# Upstream the 1-D family is CPU-only: `Sys(sysc::Consts_1D)` takes no device argument and `State_1D` holds `Vector`s
+# (src/initialize.jl:587-598).  `CuState_1D` is the device twin this glue adds -- same field names -- and the methods
+# below put Swalbe's 1-D operators and `time_loop` on it.  L ~ 1e3 sites is pure latency on a GPU: all steps of a
+# `time_loop` chunk run inside ONE persistent kernel launch with the lattice in shared memory.
+struct CuState_1D <: Swalbe.LBM_state_1D
+    fout::CuArray{Float64,2}; ftemp::CuArray{Float64,2}; feq::CuArray{Float64,2}      # L x 3
+    height::CuArray{Float64,1}; vel::CuArray{Float64,1}; pressure::CuArray{Float64,1}
+    F::CuArray{Float64,1}; slip::CuArray{Float64,1}; h∇p::CuArray{Float64,1}
+    dgrad::CuArray{Float64,2}                                                          # L x 2, unused scratch
+end
+"""`Swalbe.Sys(sys::SysConst_1D)` on the device: height = 1, everything else 0 (src/initialize.jl:587-598)."""
+CuState_1D(sys::Swalbe.SysConst_1D) = CuState_1D(CUDA.zeros(Float64, sys.L, 3), CUDA.zeros(Float64, sys.L, 3),
+    CUDA.zeros(Float64, sys.L, 3), CUDA.ones(Float64, sys.L), CUDA.zeros(Float64, sys.L), CUDA.zeros(Float64, sys.L),
+    CUDA.zeros(Float64, sys.L), CUDA.zeros(Float64, sys.L), CUDA.zeros(Float64, sys.L), CUDA.zeros(Float64, sys.L, 2))
+
+struct CState1D      # struct swalbe_state_1d
+    fout::CuPtr{Float64}; ftemp::CuPtr{Float64}; feq::CuPtr{Float64}
+    height::CuPtr{Float64}; vel::CuPtr{Float64}; pressure::CuPtr{Float64}; F::CuPtr{Float64}; slip::CuPtr{Float64}
+    hgradp::CuPtr{Float64}; dgrad::CuPtr{Float64}
+end
+cstate(s::CuState_1D) = CState1D(pointer(s.fout), pointer(s.ftemp), pointer(s.feq), pointer(s.height), pointer(s.vel),
+    pointer(s.pressure), pointer(s.F), pointer(s.slip), pointer(s.h∇p), pointer(s.dgrad))
+
+function Swalbe.equilibrium!(feq::CuArray{Float64,2}, height::CuArray{Float64,1}, velocity, gravity)   # src/equilibrium.jl:169
+    check(ccall((:swalbe_equilibrium_d1q3, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cint, Ptr{Cvoid}),
+        feq, height, velocity, gravity, length(height), stream()))
+end
+Swalbe.equilibrium!(s::CuState_1D, sys::Swalbe.Consts_1D) = Swalbe.equilibrium!(s.feq, s.height, s.vel, sys.param.g)
+
+function Swalbe.BGKandStream!(fout::CuArray{Float64,2}, feq, ftemp, F::CuArray{Float64,1}, τ)            # src/collide.jl:179
+    check(ccall((:swalbe_bgk_stream_d1q3, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cint, Ptr{Cvoid}),
+        fout, feq, ftemp, F, τ, length(F), stream()))
+end
+Swalbe.BGKandStream!(s::CuState_1D, sys::Swalbe.SysConst_1D) = Swalbe.BGKandStream!(s.fout, s.feq, s.ftemp, s.F, sys.param.τ)
+
+function Swalbe.moments!(height::CuArray{Float64,1}, vel, fout)                                          # src/moments.jl:54
+    check(ccall((:swalbe_moments_d1q3, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Ptr{Cvoid}),
+        height, vel, fout, length(height), stream()))
+end
+Swalbe.moments!(s::CuState_1D) = Swalbe.moments!(s.height, s.vel, s.fout)
+
+function _filmpressure1d!(output, f, dgrad, γ, θ, n, m, hmin, hcrit, variant)
+    ct, ctf, keep = theta_args(θ)
+    GC.@preserve keep check(ccall((:swalbe_filmpressure_1d, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cdouble, CuPtr{Float64}, Cint, Cint, Cdouble, Cdouble, Cint,
+         Cint, Ptr{Cvoid}),
+        output, f, dgrad, γ, ct, ctf, n, m, hmin, hcrit, variant, length(f), stream()), (n, m))
+end
+Swalbe.filmpressure!(output::CuArray{Float64,1}, f, dgrad, γ, θ, n, m, hmin, hcrit) =                     # src/pressure.jl:196
+    _filmpressure1d!(output, f, dgrad, γ, θ, n, m, hmin, hcrit, PRESSURE_FAST)
+Swalbe.filmpressure!(s::CuState_1D, sys::Swalbe.Consts_1D; θ = sys.param.θ, n = sys.param.n, m = sys.param.m,
+                     hmin = sys.param.hmin, hcrit = sys.param.hcrit, γ = sys.param.γ) =                   # :230
+    _filmpressure1d!(s.pressure, s.height, s.dgrad, γ, θ, n, m, hmin, hcrit, PRESSURE_POWER_BROAD)
+
+function _grad1d!(output, f, a)
+    check(ccall((:swalbe_grad_1d, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Ptr{Cvoid}),
+        output, f, a, length(f), stream()))
+end
+Swalbe.∇f!(output::CuArray{Float64,1}, f, dgrad, a::CuArray{Float64,1}) = _grad1d!(output, f, a)          # src/differences.jl:208
+Swalbe.∇f!(output::CuArray{Float64,1}, f::CuArray{Float64,1}, dgrad) = _grad1d!(output, f, NULLF)         # :220
+Swalbe.h∇p!(s::CuState_1D) = _grad1d!(s.h∇p, s.pressure, s.height)                                       # src/forcing.jl:189
+
+function Swalbe.∇²f!(output::CuArray{Float64,1}, f::CuArray{Float64,1}, dgrad)                            # src/differences.jl:77
+    check(ccall((:swalbe_lap_1d, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, Cint, Ptr{Cvoid}), output, f, length(f), stream()))
+end
+
+function Swalbe.slippage!(slip::CuArray{Float64,1}, height, vel, δ, μ)                                    # src/forcing.jl:68
+    check(ccall((:swalbe_slippage_1d, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cdouble, Cint, Ptr{Cvoid}),
+        slip, height, vel, δ, μ, length(height), stream()))
+end
+Swalbe.slippage!(s::CuState_1D, sys::Swalbe.SysConst_1D) = Swalbe.slippage!(s.slip, s.height, s.vel, sys.param.δ, sys.param.μ)
+
+"""update!(state::CuState_1D): `state.F .= -state.h∇p .- state.slip` (src/simulate.jl:110)."""
+function update!(s::CuState_1D)
+    check(ccall((:swalbe_force_sum_1d, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Ptr{Cvoid}),
+        s.F, s.h∇p, s.slip, length(s.F), stream()))
+end
+
+"""`nsteps` iterations of the 1-D loop body (src/simulate.jl:107-114) through swalbe_time_loop_1d."""
+function fused_steps!(state::CuState_1D, sys::Swalbe.SysConst_1D, nsteps::Integer; θ = sys.param.θ,
+                      logs::Union{Nothing,CLogs} = nothing, flags = 0)
+    θargs = theta_args(θ)
+    prm = Ref(cparams(sys.param, θargs, PRESSURE_POWER_BROAD, SLIP[:standard], nothing, nothing))
+    st = Ref(cstate(state))
+    keep = θargs[3]
+    if logs === nothing
+        GC.@preserve keep prm st check(ccall((:swalbe_time_loop_1d, lib), Cint,
+            (Ptr{CState1D}, Ptr{CParams}, Cint, Cint, Cint, Ptr{CLogs}, Ptr{Cvoid}),
+            st, prm, sys.L, nsteps, flags, C_NULL, stream()))
+    else
+        lg = Ref(logs)
+        GC.@preserve keep prm st lg check(ccall((:swalbe_time_loop_1d, lib), Cint,
+            (Ptr{CState1D}, Ptr{CParams}, Cint, Cint, Cint, Ptr{CLogs}, Ptr{Cvoid}),
+            st, prm, sys.L, nsteps, flags, lg, stream()))
+    end
+    return state
+end
+
+# time_loop(sys::SysConst_1D, state[, θ | Δh])  src/simulate.jl:98-157: the mass read-back / print of the reference at
+# t % tdump == 0, the steps between two prints inside one launch
+function _loop1d(sys, state, verbose; θ = sys.param.θ, hmin = nothing, hmax = nothing)
+    t, Tmax, tdump = 1, sys.param.Tmax, max(1, sys.param.tdump)
+    while t <= Tmax
+        if t % tdump == 0
+            mass = sum(state.height)
+            verbose && println("Time step $t mass is $(round(mass, digits=3))")
+        end
+        nxt = min(Tmax + 1, (t ÷ tdump + 1) * tdump)
+        logs = hmin === nothing ? nothing : CLogs(pointer(hmin, t), pointer(hmax, t), CuPtr{Culonglong}(0), 0.055)
+        fused_steps!(state, sys, nxt - t; θ = θ, logs = logs, flags = nxt <= Tmax ? LOOP_SKIP_AUX : Cint(0))
+        t = nxt
+    end
+    return state
+end
+Swalbe.time_loop(sys::Swalbe.SysConst_1D, state::CuState_1D; verbose = false) = _loop1d(sys, state, verbose)
+Swalbe.time_loop(sys::Swalbe.SysConst_1D, state::CuState_1D, θ; verbose = false) = _loop1d(sys, state, verbose; θ = θ)
+function Swalbe.time_loop(sys::Swalbe.SysConst_1D, state::CuState_1D, Δh::Vector; verbose = false)
+    mn, mx = CUDA.zeros(Float64, sys.param.Tmax), CUDA.zeros(Float64, sys.param.Tmax)
+    _loop1d(sys, state, verbose; hmin = mn, hmax = mx)
+    append!(Δh, Array(mx .- mn))
+    return state
+end
+
 # north_star aliases
 const Sys_const = Swalbe.SysConst
 const Swalbe_state = Swalbe.CuState
