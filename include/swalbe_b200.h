@@ -275,7 +275,7 @@ typedef struct swalbe_state_1d {
 /* nsteps iterations of time_loop(sys::SysConst_1D, state::State_1D[, theta | Δh])   src/simulate.jl:98-157.
  * params: the Taumucs fields and pressure_variant / cospi_theta[_field] of swalbe_params (slip variant, inclination and
  * thermal fields are ignored); flags: SWALBE_LOOP_SKIP_AUX; logs: hmin / hmax per step (wetted is ignored).
- * Lattices that fit the shared memory of one CTA (L <= ~7000 at tau == 1) run all steps but the materialising one
+ * Lattices that fit the shared memory of one CTA (L <= ~4800 at tau == 1) run all steps but the materialising one
  * inside a single persistent launch.  On return every field of the state holds what the reference's holds. */
 int swalbe_time_loop_1d(const swalbe_state_1d *state, const swalbe_params *params, int L, int nsteps, int flags,
                         const swalbe_loop_logs *logs, void *stream);

@@ -1,10 +1,9 @@
 // The 1-D (D1Q3) thin-film family of Swalbe.jl on the device: State_1D / SysConst_1D,
 // src/initialize.jl:587-598; loop body src/simulate.jl:98-116.  The reference runs it on the CPU only (no device string
 // in its 1-D allocator or drivers) at L ~ 1e3 sites, so there is no HBM case here: one step is ~30 FP64 operations per
-// site and pure latency.  Design: every thread recomputes the two neighbour sites it pulls from (5 pressures, 3
-// collisions per site), which leaves ONE barrier per step; lattices that fit the shared memory of one CTA run ALL the
-// steps of a call inside one persistent launch (h, v [and the populations at tau != 1] double-buffered in shared
-// memory), larger ones take one launch per step on global memory with the same site function.
+// site and pure latency.  Design: lattices that fit the shared memory of one CTA (L <= ~4800 at tau == 1) run ALL the
+// steps of a call inside one persistent launch, three phases per step over shared-memory arrays; larger ones take one
+// launch per step on global memory, every thread recomputing the two neighbour sites it pulls from.
 // Arithmetic: the reference's expressions in its evaluation order, no FMA contraction.
 #include <math.h>
 
@@ -89,49 +88,73 @@ struct Loop1DArgs {
 constexpr int T1D = 1024;
 
 // Persistent loop: the whole lattice in the shared memory of one CTA for all the steps of the call; the state planes
-// are read once and written once.  smem: h[2][L] v[2][L] (+ f[2][3][L] at tau != 1).
+// are read once and written once.  With ONE SM doing all the work the FP64 pipe is what a step costs, so nothing is
+// recomputed here: three phases per step (pressure | forces, equilibrium, collision | pull + moments) over
+// shared-memory arrays h, v, p, f*[3] (+ the old populations at tau != 1), a barrier after each.
 __global__ void __launch_bounds__(T1D, 1) k_loop_1d(const __grid_constant__ Loop1DArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double r_min[2][T1D / 32], r_max[2][T1D / 32];  // (by step parity: thread 0 folds step s while the others run s+1)
   const int L = a.L, tid = threadIdx.x;
-  double *sh = sm, *sv = sm + 2 * (size_t)L, *sf = sm + 4 * (size_t)L;
-  const bool pops = !a.c.tau1;
+  const Consts1D &c = a.c;
+  double *sh = sm, *sv = sm + (size_t)L, *sp = sm + 2 * (size_t)L, *sfs = sm + 3 * (size_t)L, *sft = sm + 6 * (size_t)L;
+  const bool pops = !c.tau1;
   for (int i = tid; i < L; i += T1D) {
     sh[i] = a.height[i]; sv[i] = a.vel[i];
-    if (pops) { sf[i] = a.ftemp[i]; sf[L + i] = a.ftemp[L + i]; sf[2 * L + i] = a.ftemp[2 * (size_t)L + i]; }
+    if (pops) { sft[i] = a.ftemp[i]; sft[L + i] = a.ftemp[L + i]; sft[2 * L + i] = a.ftemp[2 * (size_t)L + i]; }
   }
   __syncthreads();
   for (int s = 0; s < a.nsteps; ++s) {
-    const int cur = s & 1, nxt = cur ^ 1;
-    const double *h = sh + cur * (size_t)L, *v = sv + cur * (size_t)L, *ft = sf + cur * 3 * (size_t)L;
-    double *hn = sh + nxt * (size_t)L, *vn = sv + nxt * (size_t)L, *fn = sf + nxt * 3 * (size_t)L;
-    double d_min = INFINITY, d_max = -INFINITY;
+    const int par = s & 1;
     const bool last = s == a.nsteps - 1;
-    for (int i = tid; i < L; i += T1D) {
-      Out1D o;
-      step_site_1d(h, v, ft, (size_t)L, i, L, a.c, o, nullptr);
-      if (a.log_min) { d_min = fmin(d_min, h[i]); d_max = fmax(d_max, h[i]); }
-      hn[i] = o.h; vn[i] = o.v;
-      if (pops) { fn[i] = o.f[0]; fn[L + i] = o.f[1]; fn[2 * L + i] = o.f[2]; }
-      if (last) {
-        a.height[i] = o.h; a.vel[i] = o.v;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { a.fout[(size_t)k * L + i] = o.f[k]; a.ftemp[(size_t)k * L + i] = o.f[k]; }
-      }
+    double d_min = INFINITY, d_max = -INFINITY;
+    for (int i = tid; i < L; i += T1D) {  // filmpressure!; max - min of the pre-step height (src/simulate.jl:147)
+      sp[i] = pressure_1d(sh, i, L, c);
+      if (a.log_min) { d_min = fmin(d_min, sh[i]); d_max = fmax(d_max, sh[i]); }
     }
-    if (a.log_min) {  // max - min of the pre-step height (src/simulate.jl:147)
+    if (a.log_min) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         d_min = fmin(d_min, __shfl_down_sync(0xffffffffu, d_min, o));
         d_max = fmax(d_max, __shfl_down_sync(0xffffffffu, d_max, o));
       }
-      if ((tid & 31) == 0) { r_min[cur][tid >> 5] = d_min; r_max[cur][tid >> 5] = d_max; }
+      if ((tid & 31) == 0) { r_min[par][tid >> 5] = d_min; r_max[par][tid >> 5] = d_max; }
     }
     __syncthreads();
     if (a.log_min && tid == 0) {
-      for (int w = 1; w < T1D / 32; ++w) { d_min = fmin(d_min, r_min[cur][w]); d_max = fmax(d_max, r_max[cur][w]); }
+      for (int w = 1; w < T1D / 32; ++w) { d_min = fmin(d_min, r_min[par][w]); d_max = fmax(d_max, r_max[par][w]); }
       a.log_min[s] = d_min; a.log_max[s] = d_max;
     }
+    for (int i = tid; i < L; i += T1D) {  // h∇p!, slippage!, F, equilibrium!, collision (same expressions as collide_1d)
+      const double hc = sh[i], vc = sv[i];
+      const double hgp = (hc * -0.5) * (sp[wrap1(i - 1, L)] - sp[wrap1(i + 1, L)]);
+      const double den = ((2.0 * (hc * hc)) + c.sc.delta6 * hc) + c.sc.delta3s;
+      const double F = (-hgp) - div_exact((c.sc.mu6 * hc) * vc, den);
+      const double vv = vc * vc, hf = 0.5 * F;
+      const double fe0 = hc * ((1.0 - c.g05 * hc) - vv);
+      const double fe1 = hc * ((c.g025 * hc + 0.5 * vc) + 0.5 * vv);
+      const double fe2 = hc * ((c.g025 * hc - 0.5 * vc) + 0.5 * vv);
+      if (c.tau1) {
+        sfs[i] = fe0; sfs[L + i] = fe1 + hf; sfs[2 * L + i] = fe2 - hf;
+      } else {
+        sfs[i] = c.omega * sft[i] + c.invtau * fe0;
+        sfs[L + i] = (c.omega * sft[L + i] + c.invtau * fe1) + hf;
+        sfs[2 * L + i] = (c.omega * sft[2 * L + i] + c.invtau * fe2) - hf;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < L; i += T1D) {  // streaming (pull) + moments!
+      const double f0 = sfs[i], f1 = sfs[L + wrap1(i - 1, L)], f2 = sfs[2 * L + wrap1(i + 1, L)];
+      const double hn = ((0.0 + f0) + f1) + f2;
+      const double vn = div_exact(f1 - f2, hn);
+      sh[i] = hn; sv[i] = vn;
+      if (pops) { sft[i] = f0; sft[L + i] = f1; sft[2 * L + i] = f2; }
+      if (last) {
+        a.height[i] = hn; a.vel[i] = vn;
+        a.fout[i] = f0; a.fout[(size_t)L + i] = f1; a.fout[2 * (size_t)L + i] = f2;
+        a.ftemp[i] = f0; a.ftemp[(size_t)L + i] = f1; a.ftemp[2 * (size_t)L + i] = f2;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -372,7 +395,7 @@ int swalbe_time_loop_1d(const swalbe_state_1d *st, const swalbe_params *prm, int
   int dev = 0, max_optin = 0;
   SW_CUDA(cudaGetDevice(&dev));
   SW_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t smem = (size_t)L * sizeof(double) * (c.tau1 ? 4 : 10);
+  const size_t smem = (size_t)L * sizeof(double) * (c.tau1 ? 6 : 9);  // h, v, p, f*[3] (+ the old populations)
   int npers = skip_aux ? nsteps : nsteps - 1;
   if (smem + 1024 > (size_t)max_optin || npers < 1) npers = 0;
   if (npers > 0) {
