@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
   __syncthreads();
 
   const bool logging = ca.log_part != nullptr;
-  // row of a slab-local site index without an integer division in the step loop: (idx + 1/2) / Lx is at least 1/(2 Lx)
-  // away from every integer, three orders of magnitude more than the float rounding error for idx < 2^16 (host-checked)
-  const float inv_lx = 1.0f / (float)Lx;
-  auto row_of = [&](int idx) { return (int)(((float)idx + 0.5f) * inv_lx); };
+  // site index -> (row, column) without a division in the step loop: thread tid starts every phase at (tid / Lx, tid % Lx)
+  // of the phase's row range and advances by NT sites = (NT / Lx) rows + (NT % Lx) columns with one carry
+  const int l_first = tid / Lx, i_first = tid - l_first * Lx, dl = NT / Lx, di = NT - dl * Lx;
+  const int nhi = (int)nh, nui = (int)nu;  // (all shared-memory offsets fit 32 bits)
   for (int s = 0; s < ca.nsteps; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
     const bool last = s == ca.nsteps - 1;
@@ -117,27 +117,30 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
     }
 
     // phase B: film pressure on rows -2 .. rows+1   (src/pressure.jl:141-153; fused.cuh stage B)
-    for (int idx = tid; idx < (rows + 4) * Lx; idx += NT) {
-      const int l = row_of(idx) - 2, i = idx - (l + 2) * Lx;
+    const double *const hb = sh + cur * nhi;  // this step's h buffer; row l at (l + 3) * Lx
+    for (int idx = tid, lr = l_first, i = i_first; idx < (rows + 4) * Lx; idx += NT) {  // lr = l + 2
       const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;  // columns i-1 / i+1 (periodic)
-      const double *r0 = H(cur, l - 1), *r1 = H(cur, l), *r2 = H(cur, l + 1);
+      const double *r1 = hb + (lr + 1) * Lx, *r0 = r1 - Lx, *r2 = r1 + Lx;
       const double hc = r1[i];
       const double lap = lap9_bracket(hc, r1[im], r0[i], r1[ip], r2[i], r0[im], r0[ip], r2[ip], r2[im]);
       const double x = div_exact(a.pc.hmin, hc + a.pc.hcrit);
       const double pw = disjoining_powers(x, PM, a.pc.n, a.pc.m);
-      sp[(size_t)(l + 2) * Lx + i] = (-a.pc.gamma * (a.pc.kappa * pw)) - a.pc.gamma * lap;
+      sp[lr * Lx + i] = (-a.pc.gamma * (a.pc.kappa * pw)) - a.pc.gamma * lap;
+      i += di; lr += dl;
+      if (i >= Lx) { i -= Lx; ++lr; }
     }
     __syncthreads();
 
     // phase C: forces, equilibrium, collision on rows -1 .. rows   (fused.cuh stage C); logs of the pre-step height
     double d_min = INFINITY, d_max = -INFINITY;
     unsigned int d_wet = 0;
-    for (int idx = tid; idx < (rows + 2) * Lx; idx += NT) {
-      const int l = row_of(idx) - 1, i = idx - (l + 1) * Lx;
+    const double *const uxb = sux + cur * nui, *const uyb = suy + cur * nui;  // row l at (l + 1) * Lx
+    for (int idx = tid, lr = l_first, i = i_first; idx < (rows + 2) * Lx; idx += NT) {  // lr = l + 1
+      const int l = lr - 1;
       const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;
-      const double *q0 = sp + (size_t)(l + 1) * Lx, *q1 = q0 + Lx, *q2 = q1 + Lx;  // p rows l-1, l, l+1
-      const double hc = H(cur, l)[i];
-      const double ux = UX(cur, l)[i], uy = UY(cur, l)[i];
+      const double *q0 = sp + lr * Lx, *q1 = q0 + Lx, *q2 = q1 + Lx;  // p rows l-1, l, l+1
+      const double hc = hb[(lr + 2) * Lx + i];
+      const double ux = uxb[lr * Lx + i], uy = uyb[lr * Lx + i];
       const double pipjp = q0[im], pimjp = q0[ip], pimjm = q2[ip], pipjm = q2[im];
       const double gx = grad9_x(q1[im], q1[ip], pipjp, pimjp, pimjm, pipjm);
       const double gy = grad9_y(q0[i], q2[i], pipjp, pimjp, pimjm, pipjm);
@@ -149,12 +152,14 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
       equilibrium_site<GZ>(hc, ux, uy, a.ec, fe, vsq);
       collide_site_tau1(fe, Fx, Fy, fs);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) sf[(size_t)k * nu + (size_t)(l + 1) * Lx + i] = fs[k];
+      for (int k = 0; k < 9; ++k) sf[k * nui + lr * Lx + i] = fs[k];
       if (logging && l >= 0 && l < rows) {
         d_min = fmin(d_min, hc);
         d_max = fmax(d_max, hc);
         d_wet += hc > a.hthresh;
       }
+      i += di; lr += dl;
+      if (i >= Lx) { i -= Lx; ++lr; }
     }
     if (logging) {  // CTA reduction, one atomic per CTA and step (as the marching kernel does)
 #pragma unroll
@@ -177,19 +182,19 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
     // phase D: pull-stream + moments of the slab   (fused.cuh stage D) -> the other h / u buffer
     if (ca.nsteps == 1) cl_sync();  // in-place calls: nobody may still be loading step 0 from the planes written below
     const bool write_f = a.f_out != nullptr && (last || !ca.lazy);
-    for (int idx = tid; idx < rows * Lx; idx += NT) {
-      const int l = row_of(idx), i = idx - l * Lx;
+    double *const hnb = sh + nxt * nhi, *const uxnb = sux + nxt * nui, *const uynb = suy + nxt * nui;
+    for (int idx = tid, l = l_first, i = i_first; idx < rows * Lx; idx += NT) {
       const int im = i ? i - 1 : Lx - 1, ip = i + 1 < Lx ? i + 1 : 0;
-      const size_t c0 = (size_t)l * Lx, c1 = c0 + Lx, c2 = c1 + Lx;  // f* rows l-1, l, l+1
+      const int c0 = l * Lx, c1 = c0 + Lx, c2 = c1 + Lx;  // f* rows l-1, l, l+1
       double fn[9];
-      fn[0] = sf[0 * nu + c1 + i];
-      fn[1] = sf[1 * nu + c1 + im]; fn[3] = sf[3 * nu + c1 + ip];
-      fn[2] = sf[2 * nu + c0 + i];  fn[4] = sf[4 * nu + c2 + i];
-      fn[5] = sf[5 * nu + c0 + im]; fn[6] = sf[6 * nu + c0 + ip];
-      fn[7] = sf[7 * nu + c2 + ip]; fn[8] = sf[8 * nu + c2 + im];
+      fn[0] = sf[0 * nui + c1 + i];
+      fn[1] = sf[1 * nui + c1 + im]; fn[3] = sf[3 * nui + c1 + ip];
+      fn[2] = sf[2 * nui + c0 + i];  fn[4] = sf[4 * nui + c2 + i];
+      fn[5] = sf[5 * nui + c0 + im]; fn[6] = sf[6 * nui + c0 + ip];
+      fn[7] = sf[7 * nui + c2 + ip]; fn[8] = sf[8 * nui + c2 + im];
       double hn, uxn, uyn;
       moments_site(fn, hn, uxn, uyn);
-      H(nxt, l)[i] = hn; UX(nxt, l)[i] = uxn; UY(nxt, l)[i] = uyn;
+      hnb[(l + 3) * Lx + i] = hn; uxnb[(l + 1) * Lx + i] = uxn; uynb[(l + 1) * Lx + i] = uyn;
       const size_t o = (size_t)(j0 + l) * Lx + i;
       if (last) { a.h_out[o] = hn; a.ux_out[o] = uxn; a.uy_out[o] = uyn; }
       if (write_f) {
@@ -200,6 +205,8 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_steps(const __grid_constant__
           for (int k = 0; k < 9; ++k) a.f_out2[o + k * a.fstride_out2] = fn[k];
         }
       }
+      i += di; l += dl;
+      if (i >= Lx) { i -= Lx; ++l; }
     }
     __syncthreads();
   }
