@@ -565,6 +565,19 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
   const int t_end = R + 8;
   int t = -D;
   for (; t < 9 && t <= t_end; ++t) iter(t, std::false_type{});
+#ifdef SW_UNROLL8
+  // experiment: steady state unrolled by the ring period so that every ring slot is a compile-time constant
+  for (; t < 16 && t <= R + 6 - D; ++t) iter(t, std::true_type{});
+  if (t == 16) {
+    int tt = 16;
+#pragma unroll 1
+    for (; tt + 7 <= R + 6 - D; tt += 8) {
+      iter(tt, std::true_type{}); iter(tt + 1, std::true_type{}); iter(tt + 2, std::true_type{}); iter(tt + 3, std::true_type{});
+      iter(tt + 4, std::true_type{}); iter(tt + 5, std::true_type{}); iter(tt + 6, std::true_type{}); iter(tt + 7, std::true_type{});
+    }
+    t = tt;
+  }
+#endif
   for (; t <= R + 6 - D; ++t) iter(t, std::true_type{});  // (the last prefetched h row is N(R+6))
   for (; t <= t_end; ++t) iter(t, std::false_type{});
 
