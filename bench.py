@@ -401,6 +401,8 @@ def main():
                     help="N>1: weak = L x L per rank (default, the contract), strong = L x L in total (L/N rows per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--check-e2e", action="store_true", help="after each e2e job, redo it as copy + equilibrium! + time_loop + "
+                                                             "copy and compare the heights bitwise (untimed runs only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank-vs-1-GPU bitwise leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -453,12 +455,14 @@ def main():
             inp.set(th)
         state = {"started": False}
 
-        def run(n, s0=0, aux=False, **kw):
-            """n steps; `aux`: the last launch also materialises the reference's intermediate fields (user-level call)"""
+        def run(n, s0=0, aux=False, host_in=None, host_out=None, **kw):
+            """n steps; `aux`: the last launch also materialises the reference's intermediate fields (user-level call);
+            host_in / host_out: pinned host planes the first segment starts from / the last one leaves the height in"""
             segs = segments(s0, n) if moving else [(s0, n, False)]
             for q, (t0, cnt, move) in enumerate(segs):
                 sw.fused_steps(st, sysc, cnt, thermal_seed=thermal_seed, step0=t0, θ=th, skip_aux=not (aux and q == len(segs) - 1),
-                               pressure_variant=_lib.PRESSURE_POWER_BROAD, moments_consistent=state["started"], **kw)
+                               pressure_variant=_lib.PRESSURE_POWER_BROAD, moments_consistent=state["started"],
+                               host_in=host_in if q == 0 else None, host_out=host_out if q == len(segs) - 1 else None, **kw)
                 state["started"] = True
                 if move:
                     sw.move_substrate(th, inp, t0 + cnt, TMOVE)
@@ -502,16 +506,24 @@ def main():
             out_host = torch.empty_like(h_host).pin_memory()
 
             def job(sc):
-                st.height.t.copy_(h_host, non_blocking=True)
                 st.velx.t.zero_(); st.vely.t.zero_()
-                sw.equilibrium(st, sc)
                 if thermal_seed is None:
-                    sw.time_loop(sc, st)
+                    sw.run_host(sc, h_host, out_host, state=st)  # height from the host, time_loop, height to the host
                 else:
                     state["started"] = False
-                    run(sc.param.Tmax, aux=True)
-                out_host.copy_(st.height.t, non_blocking=True)
+                    run(sc.param.Tmax, aux=True, host_in=h_host, host_out=out_host)
                 torch.cuda.synchronize()
+                if args.check_e2e:  # the streamed job against the plain sequence copy, equilibrium!, time_loop, copy
+                    got = out_host.clone()
+                    st.height.t.copy_(h_host, non_blocking=True)
+                    st.velx.t.zero_(); st.vely.t.zero_()
+                    sw.equilibrium(st, sc)
+                    if thermal_seed is None:
+                        sw.time_loop(sc, st)
+                    else:
+                        state["started"] = False
+                        run(sc.param.Tmax, aux=True)
+                    extra["e2e_equals_plain_sequence"] = bool(torch.equal(got, st.height.t.cpu()))
 
             wk2 = dict(wkw)
             wk2.update(Tmax=min(K, 4), tdump=2)
@@ -525,9 +537,10 @@ def main():
             plane = L * rows * 8
             e2e = {"value": round(lu / dt / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": plane // K,
                    "d2h_bytes_per_step": (plane + 16 * 4) // K,
-                   "what": f"pinned-host height -> H2D -> equilibrium! + time_loop({K} steps, mass read-back every tdump, every field of "
-                           "the state materialised on return) -> D2H height; copies amortised over the steps of the job; best of 3 "
-                           "jobs after one warm-up job"}
+                   "what": f"run_host: pinned-host height -> H2D -> time_loop({K} steps, mass read-back every tdump, every field of "
+                           "the state materialised on return) -> D2H height into pinned host memory, both copies inside the timed "
+                           "region, travelling in row bands behind / ahead of the first / last steps (swalbe_time_loop_host); "
+                           "best of 3 jobs after one warm-up job"}
         del st
         torch.cuda.empty_cache()
     else:

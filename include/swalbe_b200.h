@@ -236,6 +236,29 @@ int swalbe_plan_destroy(swalbe_plan *plan);
 int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *state, const swalbe_params *params, int nsteps,
                      unsigned long long step0, int flags, const swalbe_loop_logs *logs, void *stream);
 
+/* The same loop for a job whose initial height lives in HOST memory and / or whose final height goes back to it -- the
+ * pattern of every shipped GPU script: `state.height .= CUDA.adapt(CuArray, h)` ... loop ... `Array(state.height)`
+ * (scripts/Moving_wettability_structs.jl:39,60-71, src/simulate.jl:349-357).  On return (stream-ordered) the state and
+ * height_out_host hold bit for bit what
+ *     cudaMemcpyAsync(state->height, height_in_host, H2D); swalbe_time_loop(...); cudaMemcpyAsync(height_out_host, state->height, D2H)
+ * leaves, but on large lattices (tau == 1) the copies travel as row bands on the plan's own copy streams while the
+ * first steps run behind the upload front and the last steps ahead of the download (csrc/sweep.h): the PCIe time of
+ * the two planes disappears behind ~10 steps of compute each.  Either host pointer may be NULL (no copy in that
+ * direction; both NULL == swalbe_time_loop).  Host buffers: Lx*Ly doubles in the layout of state->height, page-locked
+ * (pageable memory works but serialises).  velx / vely are inputs of the first step as in swalbe_time_loop.
+ * The plan holds the copy streams; the call is asynchronous and returns with the caller's stream waiting on the last
+ * band's download. */
+int swalbe_time_loop_host(swalbe_plan *plan, const swalbe_state *state, const swalbe_params *params, int nsteps,
+                          unsigned long long step0, int flags, const swalbe_loop_logs *logs, const double *height_in_host,
+                          double *height_out_host, void *stream);
+
+/* self-test (host only, needs no device): the operation list of swalbe_time_loop_host for an Lx x Ly lattice -- six ints
+ * per operation {kind (0 upload rows, 1 step launch, 2 download rows), step, jbeg, jend, band, seam}, in issue order --
+ * so that the schedule can be replayed and checked on the CPU.  band_rows / kmax / min_sites <= 0: the defaults.
+ * ops6 == NULL: only *nops is written. */
+int swalbe_selftest_host_loop_schedule(int Lx, int Ly, int nsteps, int has_in, int has_out, int band_rows, int kmax,
+                                       int min_sites, int *ops6, int max_ops, int *nops);
+
 /* ---------------------------------------------------------------------------------------------
  * The 1-D (D1Q3) family: State_1D / SysConst_1D, src/initialize.jl:587-598.  The reference runs it
  * on the CPU only (no device string in its 1-D allocator or drivers), so these entry points have no upstream GPU

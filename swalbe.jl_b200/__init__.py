@@ -601,8 +601,13 @@ def _c_params(p: Taumucs, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None, t
 
 def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None,
                 thermal_seed=None, step0=0, lazy_populations=False, log_minmax=False, log_wetted=False, hthresh=0.055,
-                pressure_variant=None, skip_aux=False, moments_consistent=False):
+                pressure_variant=None, skip_aux=False, moments_consistent=False, host_in=None, host_out=None):
     """nsteps iterations of the loop body src/simulate.jl:15-22 through swalbe_time_loop (one fused kernel/step).
+
+    ``host_in`` / ``host_out`` (pinned CPU torch tensors or NumPy arrays of Lx*Ly float64 in the memory order of
+    ``state.height``, i.e. ``h.T`` C-contiguous): the loop starts from the height in ``host_in`` and / or leaves the final
+    height in ``host_out`` (swalbe_time_loop_host: on large lattices the copies travel in row bands behind which / ahead of
+    which the first / last steps run).  The download is complete once the current stream has been synchronised.
 
     ``moments_consistent`` (τ ≠ 1): the caller vouches that height/velx/vely are the moments of ftemp -- true after any
     earlier fused_steps/time_loop/moments! call on this state, false after writing an initial condition into height --
@@ -626,12 +631,70 @@ def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_varia
     logs.hthresh = hthresh
     flags = ((_lib.LOOP_LAZY_POPULATIONS if lazy_populations else 0) | (_lib.LOOP_SKIP_AUX if skip_aux else 0) |
              (_lib.LOOP_MOMENTS_CONSISTENT if moments_consistent else 0))
-    _lib.call("swalbe_time_loop", st.plan(), C.byref(cs), C.byref(q), int(nsteps), int(step0), flags,
-              C.byref(logs) if (log_minmax or log_wetted) else None, _stream())
+    lg = C.byref(logs) if (log_minmax or log_wetted) else None
+    if host_in is None and host_out is None:
+        _lib.call("swalbe_time_loop", st.plan(), C.byref(cs), C.byref(q), int(nsteps), int(step0), flags, lg, _stream())
+    else:
+        _lib.call("swalbe_time_loop_host", st.plan(), C.byref(cs), C.byref(q), int(nsteps), int(step0), flags, lg,
+                  _host_ptr(host_in, st), _host_ptr(host_out, st), _stream())
+        st.height.touch()
     return mn, mx, wet
 
 
-def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, lazy_populations=True):
+def _host_ptr(x, st):
+    """address of a host plane of Lx*Ly float64 (torch CPU tensor, ideally pinned, or NumPy array)"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.float64 or x.size != st.Lx * st.Ly or not (x.flags.c_contiguous or x.flags.f_contiguous):
+            raise ValueError("host plane: contiguous float64 array of Lx*Ly elements expected")
+        return C.c_void_p(x.ctypes.data)
+    if x.device.type != "cpu" or x.dtype != _torch().float64 or x.numel() != st.Lx * st.Ly or not x.is_contiguous():
+        raise ValueError("host plane: contiguous float64 CPU tensor of Lx*Ly elements expected")
+    return C.c_void_p(x.data_ptr())
+
+
+class _MassDumps:
+    """`mass = sum(state.height)` at every dump step (src/simulate.jl:8-14) without stalling the loop: the reduction runs
+    on the device in stream order (swalbe_field_stats), its 32 bytes travel to pinned host memory asynchronously, and the
+    line is printed as soon as the copy has landed -- same lines, same order, never a host synchronisation in the loop."""
+
+    _ring = None  # pinned staging shared by all loops of the process: 256 dumps in flight
+
+    def __init__(self, verbose):
+        self.verbose, self.pending, self.masses = verbose, [], []
+
+    def push(self, t, height: Field):
+        torch = _torch()
+        cls = _MassDumps
+        if cls._ring is None:
+            cls._ring = (torch.empty((256, 4), dtype=torch.float64).pin_memory(),
+                         torch.empty((256, 4), dtype=torch.float64, device="cuda"), [0])
+        host, dev, nxt = cls._ring
+        if len(self.pending) >= 128:
+            self.flush(block=True)
+        i = nxt[0] % 256
+        nxt[0] += 1
+        _lib.call("swalbe_field_stats", C.c_void_p(dev[i].data_ptr()), height.ptr, 0.055, *_dims(height), _stream())
+        host[i].copy_(dev[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((t, ev, i))
+        self.flush(block=False)
+
+    def flush(self, block):
+        host = _MassDumps._ring[0] if _MassDumps._ring else None
+        while self.pending and (block or self.pending[0][1].query()):
+            t, ev, i = self.pending.pop(0)
+            ev.synchronize()
+            mass = float(host[i, 2])
+            self.masses.append((t, mass))
+            if self.verbose:
+                print(f"Time step {t} mass is {round(mass, 3)}")
+
+
+def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, lazy_populations=True, host_in=None,
+              host_out=None):
     """The four 2-D time_loop methods  src/simulate.jl:6-96:
 
     time_loop(sys, state)                       plain                          :6-25
@@ -644,7 +707,11 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, la
     what the reference's holds; in between, the loop moves as little as the arithmetic allows: at τ = 1 the populations
     are only written by the last step of a chunk (`lazy_populations`: ω = 0, nothing reads them -- 48 instead of 120
     bytes per lattice update, same bits on return), at τ ≠ 1 every chunk after the first vouches for its moments so that
-    all of its steps derive h and u from the populations (144 instead of 192 bytes)."""
+    all of its steps derive h and u from the populations (144 instead of 192 bytes).
+
+    ``host_in`` / ``host_out``: host planes (see fused_steps) the first chunk starts from / the last chunk leaves the final
+    height in -- `state.height .= CUDA.adapt(CuArray, h)` before and `Array(state.height)` after the loop, with the
+    copies hidden behind the first and last steps."""
     if isinstance(sys_, SysConst_1D):
         return one_d.time_loop(sys_, st, *extra, verbose=verbose)
     p = sys_.param
@@ -662,11 +729,10 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, la
     incl = (measure, 0.5 + 0.5 * math.tanh((1000 - 0) / 1)) if cb is inclination else None  # defaults of :363
     t = 1
     tdump = max(1, p.tdump)
+    dumps = _MassDumps(verbose)
     while t <= p.Tmax:
         if t % tdump == 0:
-            mass = field_stats(st.height)[2]
-            if verbose:
-                print(f"Time step {t} mass is {round(mass, 3)}")
+            dumps.push(t, st.height)
         nxt = min(p.Tmax + 1, (t // tdump + 1) * tdump)  # run up to (not including) the next dump step
         if chunk:
             nxt = min(nxt, t + chunk)
@@ -674,13 +740,37 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, la
         # only the final chunk needs feq/pressure/h∇p/slip/F materialised (the state the reference returns)
         mn, mx, wet = fused_steps(st, sys_, n, θ=θ, incl=incl, log_minmax=dh is not None, log_wetted=cb is wetted,
                                   skip_aux=nxt <= p.Tmax, lazy_populations=bool(lazy_populations) and p.tau == 1.0,
-                                  moments_consistent=t > 1)
+                                  moments_consistent=t > 1, host_in=host_in if t == 1 else None,
+                                  host_out=host_out if nxt > p.Tmax else None)
         if dh is not None:
             dh.extend((mx - mn).cpu().tolist())
         if cb is wetted:
             measure.extend(wet.cpu().tolist())
         t = nxt
+    dumps.flush(block=True)
+    if p.Tmax < 1:  # (no step ran: the copies still happen)
+        fused_steps(st, sys_, 0, host_in=host_in, host_out=host_out)
     return st if cb is None else (st, measure)
+
+
+def run_host(sys_: SysConst, h_host, out_host=None, θ=None, kind="simple", verbos=False, state=None):
+    """A whole film job from and to host memory, the shape of every shipped GPU script and of the run_* drivers
+    (src/simulate.jl:338-358): Sys(sys, "GPU"); state.height .= h; time_loop(sys, state[, θ]); Array(state.height).
+    The reference's `equilibrium!` before the loop is skipped when at least one step runs (every field it writes is
+    written again by the last step, and at τ = 1 nothing reads it in between).  ``h_host`` / ``out_host``: see fused_steps;
+    returns (state, out_host) with the download complete."""
+    torch = _torch()
+    st = state if state is not None else Sys(sys_, "GPU", kind=kind)
+    if out_host is None:
+        out_host = torch.empty(sys_.Lx * sys_.Ly, dtype=torch.float64).pin_memory()
+    if sys_.param.Tmax < 1 or sys_.param.tau != 1.0:
+        st.height.t.copy_(h_host.reshape(st.height.t.shape) if not isinstance(h_host, np.ndarray)
+                          else torch.from_numpy(h_host).reshape(st.height.t.shape), non_blocking=True)
+        equilibrium(st, sys_)
+        h_host = None
+    time_loop(sys_, st, *(() if θ is None else (θ,)), verbose=verbos, host_in=h_host, host_out=out_host)
+    torch.cuda.current_stream().synchronize()
+    return st, out_host
 
 
 def run_flat(sys_: SysConst, device: str = "GPU", verbos=True):

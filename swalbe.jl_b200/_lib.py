@@ -86,6 +86,8 @@ SIGNATURES = {
     "swalbe_plan_create": [C.POINTER(_vp), _i, _i],
     "swalbe_plan_destroy": [_vp],
     "swalbe_time_loop": [_vp, C.POINTER(CState), C.POINTER(CParams), _i, _u64, _i, C.POINTER(CLogs), _vp],
+    "swalbe_time_loop_host": [_vp, C.POINTER(CState), C.POINTER(CParams), _i, _u64, _i, C.POINTER(CLogs), _vp, _vp, _vp],
+    "swalbe_selftest_host_loop_schedule": [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i)],
     "swalbe_equilibrium_d1q3": [_vp, _vp, _vp, _d, _i, _vp],
     "swalbe_bgk_stream_d1q3": [_vp, _vp, _vp, _vp, _d, _i, _vp],
     "swalbe_moments_d1q3": [_vp, _vp, _vp, _i, _vp],

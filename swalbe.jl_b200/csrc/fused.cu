@@ -8,6 +8,7 @@
 
 #include "cluster.cuh"
 #include "launch.h"
+#include "sweep.h"
 #include "variants.h"
 
 namespace swalbe {
@@ -230,21 +231,28 @@ struct swalbe_plan {
   bool have_graph, have_seen;
   int graph_nsteps;
   // launch geometry per kernel flavour, chosen the first time the flavour is used
-  struct GeomEntry { KernelKey key; LaunchGeom geom; };
-  GeomEntry geoms[32];
+  struct GeomEntry { KernelKey key; int nrows; LaunchGeom geom; };
+  GeomEntry geoms[96];
   int ngeoms;
+  // swalbe_time_loop_host: copy streams (one per direction: PCIe is full duplex) and their events
+  cudaStream_t s_h2d, s_d2h;
+  cudaEvent_t ev_user, ev_dn, ev_done, ev_up[64];
+  bool have_host_streams;
 };
 
-static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g) {
+// nrows: rows of one launch (the whole lattice, or a band / the seam strips of the host loop's sweeps)
+static int plan_geometry(swalbe_plan *plan, const KernelKey &k, LaunchGeom **g, int nrows = 0) {
   auto same = [](const KernelKey &x, const KernelKey &y) {
     return x.tau1 == y.tau1 && x.thermal == y.thermal && x.lean_pm == y.lean_pm && x.bulk == y.bulk && x.gz == y.gz &&
            x.lazy == y.lazy && x.opts == y.opts && x.fm == y.fm && x.ns == y.ns;
   };
+  if (nrows <= 0) nrows = plan->Ly;
   for (int q = 0; q < plan->ngeoms; ++q)
-    if (same(plan->geoms[q].key, k)) { *g = &plan->geoms[q].geom; return 0; }
-  const int slot = plan->ngeoms < 32 ? plan->ngeoms++ : 31;  // (a plan sees a handful of flavours; the last slot is recycled)
+    if (plan->geoms[q].nrows == nrows && same(plan->geoms[q].key, k)) { *g = &plan->geoms[q].geom; return 0; }
+  const int slot = plan->ngeoms < 96 ? plan->ngeoms++ : 95;  // (a plan sees a handful of flavours; the last slot is recycled)
   plan->geoms[slot].key = k;
-  if (int e = choose_geometry(plan->Lx, plan->Ly, k, &plan->geoms[slot].geom)) { plan->ngeoms = slot; return e; }
+  plan->geoms[slot].nrows = nrows;
+  if (int e = choose_geometry(plan->Lx, nrows, k, &plan->geoms[slot].geom)) { plan->ngeoms = slot; return e; }
   *g = &plan->geoms[slot].geom;
   return 0;
 }
@@ -258,6 +266,7 @@ int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly) {
   p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr; p->log_part = nullptr; p->log_part_doubles = 0; p->graph_launches = 0;
   p->cap_stream = nullptr; p->graph_exec = nullptr; p->have_graph = p->have_seen = false; p->graph_nsteps = 0;
   p->ngeoms = 0;
+  p->s_h2d = p->s_d2h = nullptr; p->have_host_streams = false;
   cudaError_t e = cudaMalloc((void **)&p->scratch, sizeof(double) * 3 * (size_t)Lx * Ly);
   if (e != cudaSuccess) {
     delete p;
@@ -271,6 +280,11 @@ int swalbe_plan_destroy(swalbe_plan *plan) {
   if (!plan) return 0;
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
   if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
+  if (plan->have_host_streams) {  // (copies still in flight are drained by cudaStreamDestroy's deferred release)
+    cudaStreamDestroy(plan->s_h2d); cudaStreamDestroy(plan->s_d2h);
+    cudaEventDestroy(plan->ev_user); cudaEventDestroy(plan->ev_dn); cudaEventDestroy(plan->ev_done);
+    for (cudaEvent_t ev : plan->ev_up) cudaEventDestroy(ev);
+  }
   cudaFree(plan->scratch);
   cudaFree(plan->log_part);
   delete plan;
@@ -521,3 +535,207 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   }
   return 0;
 }
+
+// ---- time loop from / to host memory (sweep.h) --------------------------------------------------------------------------
+
+static int host_streams(swalbe_plan *plan) {
+  if (plan->have_host_streams) return 0;
+  SW_CUDA(cudaStreamCreateWithFlags(&plan->s_h2d, cudaStreamNonBlocking));
+  SW_CUDA(cudaStreamCreateWithFlags(&plan->s_d2h, cudaStreamNonBlocking));
+  SW_CUDA(cudaEventCreateWithFlags(&plan->ev_user, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&plan->ev_dn, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&plan->ev_done, cudaEventDisableTiming));
+  for (cudaEvent_t &ev : plan->ev_up) SW_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  plan->have_host_streams = true;
+  return 0;
+}
+
+static SweepConfig host_loop_config(int Lx, int Ly, int nsteps, bool has_in, bool has_out) {
+  if (!env_int("SWALBE_HOST_STREAM", 1)) return SweepConfig{0, 0, 0, 0};
+  return sweep_configure(Lx, Ly, nsteps, has_in, has_out, env_int("SWALBE_BAND_ROWS", 0), env_int("SWALBE_HOST_KMAX", 0),
+                         (long long)env_int("SWALBE_HOST_MIN_SITES", 0));
+}
+
+static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const swalbe_params *prm, int nsteps,
+                              unsigned long long step0, int flags, const swalbe_loop_logs *logs, const double *hin,
+                              double *hout, cudaStream_t stream) {
+  const int Lx = plan->Lx, Ly = plan->Ly;
+  const size_t N = (size_t)Lx * Ly;
+  if (!st->height) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop_host: state.height is NULL");
+  const bool tau1 = prm->tau == 1.0;
+  SweepConfig cfg = host_loop_config(Lx, Ly, nsteps, hin != nullptr, hout != nullptr);
+  if (!tau1) cfg.nbands = 0;  // (the sweeps are wired for the kernels that read no populations)
+  if (cfg.nbands == 0) {      // small lattices, tau != 1: the copies simply bracket the loop on the caller's stream
+    if (hin) SW_CUDA(cudaMemcpyAsync(st->height, hin, N * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (nsteps > 0)
+      if (int e = enqueue_steps(plan, st, prm, nsteps, step0, flags, logs, stream)) return e;
+    if (hout) SW_CUDA(cudaMemcpyAsync(hout, st->height, N * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    return 0;
+  }
+#define NEED(f) if (!st->f) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop_host: state." #f " is NULL")
+  NEED(fout); NEED(ftemp); NEED(feq); NEED(velx); NEED(vely); NEED(vsq); NEED(pressure);
+  NEED(Fx); NEED(Fy); NEED(slipx); NEED(slipy); NEED(hgradpx); NEED(hgradpy);
+#undef NEED
+  const bool thermal = prm->use_thermal != 0;
+  if (thermal && (!st->kbtx || !st->kbty)) return set_error(SWALBE_ERR_ARG, "thermal loop needs state.kbtx/kbty");
+  const bool lazy = (flags & SWALBE_LOOP_LAZY_POPULATIONS) != 0;
+  const bool skip_aux = (flags & SWALBE_LOOP_SKIP_AUX) != 0;
+  if (logs && ((logs->hmin == nullptr) != (logs->hmax == nullptr)))
+    return set_error(SWALBE_ERR_ARG, "logs.hmin and logs.hmax must both be set or both NULL");
+  if (int e = host_streams(plan)) return e;
+
+  FusedArgs a = {};
+  if (int e = fill_consts(a, *prm)) return e;
+  const KernelKey key_full = make_key(*prm, a.pc.pmode, false);
+  KernelKey key_mid = make_key(*prm, a.pc.pmode, true);
+  if (logs && (logs->hmin || logs->wetted)) key_mid.opts = true;
+  auto aligned16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
+  key_mid.bulk = key_mid.lean_pm > 0 && !key_mid.opts && !key_mid.thermal && !lazy && bulk_eligible(Lx, N) && aligned16(st->height) &&
+                 aligned16(st->velx) && aligned16(st->vely) && aligned16(plan->scratch);
+  key_mid.lazy = lazy;
+  const int kphase = std::max(cfg.k_up, cfg.k_dn);
+  const int band_rows = Ly / cfg.nbands, seam_rows = std::max(3, 3 * kphase / 2 + 1);
+  // [whole lattice | band | seam strip] x [lean step | the step that ends the call]
+  LaunchGeom *g_mid[3] = {nullptr, nullptr, nullptr}, *g_full[3] = {nullptr, nullptr, nullptr};
+  const int geom_rows[3] = {Ly, band_rows, seam_rows};
+  for (int q = 0; q < 3; ++q) {
+    if (int e = plan_geometry(plan, key_mid, &g_mid[q], geom_rows[q])) return e;
+    if (int e = plan_geometry(plan, key_full, &g_full[q], geom_rows[q])) return e;
+  }
+  a.Lx = Lx; a.Ly = Ly;
+  a.wrap_y = 1; a.jglobal0 = 0; a.Ly_global = Ly;
+  a.fstride_in = a.fstride_out = a.fstride_out2 = N;
+  a.ct_field = prm->cospi_theta_field;
+  const bool log_mm = logs && logs->hmin && logs->hmax;
+  const bool log_wet = logs && logs->wetted;
+
+  // moment ping-pong as in the plain loop: the last step lands in the caller's planes (A), so step s reads A when
+  // (nsteps - s) is even; the upload goes straight into the planes step 0 reads
+  double *A[3] = {st->height, st->velx, st->vely};
+  double *B[3] = {plan->scratch, plan->scratch + N, plan->scratch + 2 * N};
+  const bool src0_is_A = (nsteps % 2) == 0;
+  double **src0 = src0_is_A ? A : B;
+
+  // SWALBE_HOST_TRACE=1 (diagnostics; blocks the host at the end of the call): device timeline of the copies and sweeps
+  const bool trace = env_int("SWALBE_HOST_TRACE", 0) != 0, nocopy = env_int("SWALBE_HOST_NOCOPY", 0) != 0;
+  struct Mark { cudaEvent_t ev; char what[48]; };
+  std::vector<Mark> marks;
+  auto mark = [&](cudaStream_t s_, const char *fmt, int x, int y) {
+    if (!trace) return;
+    Mark m;
+    cudaEventCreate(&m.ev);
+    snprintf(m.what, sizeof(m.what), fmt, x, y);
+    cudaEventRecord(m.ev, s_);
+    marks.push_back(m);
+  };
+  // order the copy streams after whatever the caller has queued on the state (the upload overwrites a plane of it)
+  mark(stream, "start", 0, 0);
+  SW_CUDA(cudaEventRecord(plan->ev_user, stream));
+  SW_CUDA(cudaStreamWaitEvent(plan->s_h2d, plan->ev_user, 0));
+  SW_CUDA(cudaStreamWaitEvent(plan->s_d2h, plan->ev_user, 0));
+  const std::vector<SweepOp> ops = sweep_schedule(cfg, Ly, nsteps, hin != nullptr, hout != nullptr);
+  for (const SweepOp &op : ops)  // every upload is queued up front: the copy engine never waits for the launch loop
+    if (op.kind == SWEEP_UPLOAD) {
+      const size_t off = (size_t)op.jbeg * Lx, cnt = (size_t)(op.jend - op.jbeg) * Lx;
+      if (!nocopy) SW_CUDA(cudaMemcpyAsync(src0[0] + off, hin + off, cnt * sizeof(double), cudaMemcpyHostToDevice, plan->s_h2d));
+      SW_CUDA(cudaEventRecord(plan->ev_up[op.band], plan->s_h2d));
+      mark(plan->s_h2d, "upload band %d done", op.band, 0);
+    }
+  if (!src0_is_A) {
+    if (!hin) SW_CUDA(cudaMemcpyAsync(B[0], A[0], sizeof(double) * N, cudaMemcpyDeviceToDevice, stream));
+    for (int q = 1; q < 3; ++q) SW_CUDA(cudaMemcpyAsync(B[q], A[q], sizeof(double) * N, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (log_mm || log_wet) {
+    k_init_logs<<<(nsteps + 255) / 256, 256, 0, stream>>>(log_mm ? logs->hmin : nullptr, log_mm ? logs->hmax : nullptr,
+                                                            log_wet ? logs->wetted : nullptr, nsteps);
+    SW_LAUNCH_CHECK();
+    a.hthresh = logs->hthresh;
+  }
+  for (const SweepOp &op : ops) {
+    if (op.kind == SWEEP_UPLOAD) continue;
+    if (op.kind == SWEEP_DOWNLOAD) {
+      const size_t off = (size_t)op.jbeg * Lx, cnt = (size_t)(op.jend - op.jbeg) * Lx;
+      mark(stream, "rows [%d, %d) final", op.jbeg, op.jend);
+      SW_CUDA(cudaEventRecord(plan->ev_dn, stream));
+      SW_CUDA(cudaStreamWaitEvent(plan->s_d2h, plan->ev_dn, 0));
+      if (!nocopy) SW_CUDA(cudaMemcpyAsync(hout + off, A[0] + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, plan->s_d2h));
+      mark(plan->s_d2h, "download %d done", op.band, 0);
+      continue;
+    }
+    if (op.band >= 0) SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_up[op.band], 0));
+    if (op.jend <= op.jbeg) continue;
+    const int s = op.step;
+    const bool last = s == nsteps - 1;
+    const bool reads_A = ((nsteps - s) % 2) == 0;
+    double **src = reads_A ? A : B, **dst = reads_A ? B : A;
+    FusedArgs b = a;
+    b.h_in = src[0]; b.ux_in = src[1]; b.uy_in = src[2];
+    b.h_out = dst[0]; b.ux_out = dst[1]; b.uy_out = dst[2];
+    b.f_in = nullptr;
+    b.f_out = (!lazy || last) ? st->fout : nullptr;
+    b.f_out2 = last ? st->ftemp : nullptr;  // fout == ftemp on return (src/collide.jl:103)
+    const bool use_full = last && !skip_aux;
+    if (use_full) {
+      b.pressure = st->pressure; b.hgx = st->hgradpx; b.hgy = st->hgradpy; b.slipx = st->slipx; b.slipy = st->slipy;
+      b.Fx = st->Fx; b.Fy = st->Fy; b.feq = st->feq; b.vsq = st->vsq;
+      b.kbtx = thermal ? st->kbtx : nullptr; b.kbty = thermal ? st->kbty : nullptr;
+    }
+    b.step = step0 + (unsigned long long)s;
+    b.log_min = log_mm ? logs->hmin + s : nullptr;
+    b.log_max = log_mm ? logs->hmax + s : nullptr;
+    b.log_wet = log_wet ? logs->wetted + s : nullptr;
+    const int gq = op.seam ? 2 : (op.jend - op.jbeg == Ly ? 0 : 1);
+    const LaunchGeom &g = use_full ? *g_full[gq] : *g_mid[gq];
+    b.rows_per_cta = g.rows_per_cta; b.W = g.W;
+    b.jbeg = op.jbeg; b.jend = op.jend;
+    if (int e = launch_fused(g, b, use_full ? key_full : key_mid, stream)) return e;
+    if (trace && (op.seam == 0) && (s == cfg.k_up - 1 || s == nsteps - 1 || op.jend - op.jbeg == Ly))
+      mark(stream, "step %d rows from %d done", s, op.jbeg);
+  }
+  if (trace) {
+    mark(stream, "compute done", 0, 0);
+    cudaStreamSynchronize(stream); cudaStreamSynchronize(plan->s_h2d); cudaStreamSynchronize(plan->s_d2h);
+    fprintf(stderr, "[swalbe] host loop %d x %d, %d steps: %d bands, sweeps of %d / %d steps%s\n", Lx, Ly, nsteps, cfg.nbands,
+            cfg.k_up, cfg.k_dn, cfg.single ? " (single)" : "");
+    for (size_t q = 0; q < marks.size(); ++q) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[0].ev, marks[q].ev);
+      fprintf(stderr, "[swalbe]   %8.3f ms  %s\n", ms, marks[q].what);
+      if (q) cudaEventDestroy(marks[q].ev);
+    }
+    cudaEventDestroy(marks[0].ev);
+  }
+  if (hout) {  // the caller's stream is done when the last band has left
+    SW_CUDA(cudaEventRecord(plan->ev_done, plan->s_d2h));
+    SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_done, 0));
+  }
+  return 0;
+}
+
+extern "C" {
+
+int swalbe_time_loop_host(swalbe_plan *plan, const swalbe_state *st, const swalbe_params *prm, int nsteps,
+                          unsigned long long step0, int flags, const swalbe_loop_logs *logs, const double *height_in_host,
+                          double *height_out_host, void *stream_) {
+  if (!plan || !st || !prm) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop_host: NULL plan/state/params");
+  if (nsteps < 0) return set_error(SWALBE_ERR_ARG, "nsteps < 0");
+  return enqueue_steps_host(plan, st, prm, nsteps, step0, flags, logs, height_in_host, height_out_host, (cudaStream_t)stream_);
+}
+
+int swalbe_selftest_host_loop_schedule(int Lx, int Ly, int nsteps, int has_in, int has_out, int band_rows, int kmax,
+                                       int min_sites, int *ops6, int max_ops, int *nops) {
+  if (!nops) return set_error(SWALBE_ERR_ARG, "nops is NULL");
+  if (int e = check_extent(Lx, Ly)) return e;
+  const SweepConfig cfg = sweep_configure(Lx, Ly, nsteps, has_in != 0, has_out != 0, band_rows, kmax, min_sites);
+  const std::vector<SweepOp> ops = sweep_schedule(cfg, Ly, nsteps, has_in != 0, has_out != 0);
+  *nops = (int)ops.size();
+  if (!ops6) return 0;
+  if ((int)ops.size() > max_ops) return set_error(SWALBE_ERR_ARG, "schedule has %d operations, room for %d", (int)ops.size(), max_ops);
+  for (size_t q = 0; q < ops.size(); ++q) {
+    const int v[6] = {ops[q].kind, ops[q].step, ops[q].jbeg, ops[q].jend, ops[q].band, ops[q].seam};
+    memcpy(ops6 + 6 * q, v, sizeof(v));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -295,12 +295,24 @@ field of `state` holds what the reference's holds after the same steps (unless `
 """
 function fused_steps!(state::GPUState, sys::SysConst, nsteps::Integer; θ = sys.param.θ, slip::Symbol = :standard,
                       incl = nothing, thermal_seed = nothing, step0 = 0, logs::Union{Nothing,CLogs} = nothing, flags = 0,
-                      pressure_variant = state isa CuState_thermal ? PRESSURE_FAST : PRESSURE_POWER_BROAD)
+                      pressure_variant = state isa CuState_thermal ? PRESSURE_FAST : PRESSURE_POWER_BROAD,
+                      host_in::Union{Nothing,Array{Float64,2}} = nothing, host_out::Union{Nothing,Array{Float64,2}} = nothing)
     θargs = theta_args(θ)
     prm = Ref(cparams(sys.param, θargs, pressure_variant, SLIP[slip], incl, thermal_seed))
     st = Ref(cstate(state))
     h = plan(state)
     keep = θargs[3]
+    if host_in !== nothing || host_out !== nothing
+        # the loop starts from the host matrix `host_in` and / or leaves the final height in `host_out` (both Lx x Ly,
+        # ideally page-locked: CUDA.pin(h)); the copies travel in row bands behind / ahead of the first / last steps
+        lg = logs === nothing ? Ref(CLogs(NULLF, NULLF, CuPtr{Culonglong}(0), 0.055)) : Ref(logs)
+        GC.@preserve keep prm st h lg host_in host_out check(ccall((:swalbe_time_loop_host, lib), Cint,
+            (Ptr{Cvoid}, Ptr{CState}, Ptr{CParams}, Cint, Culonglong, Cint, Ptr{CLogs}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+            h.ptr, st, prm, nsteps, step0, flags, logs === nothing ? Ptr{CLogs}(C_NULL) : lg,
+            host_in === nothing ? Ptr{Float64}(C_NULL) : pointer(host_in),
+            host_out === nothing ? Ptr{Float64}(C_NULL) : pointer(host_out), stream()))
+        return state
+    end
     if logs === nothing
         GC.@preserve keep prm st h check(ccall((:swalbe_time_loop, lib), Cint,
             (Ptr{Cvoid}, Ptr{CState}, Ptr{CParams}, Cint, Culonglong, Cint, Ptr{CLogs}, Ptr{Cvoid}),
@@ -340,7 +352,8 @@ end
 # final chunk materialises feq / pressure / h∇p / slip / F; at τ = 1 the populations are written by the last step of a
 # chunk only (ω = 0: nothing reads them in between; same bits on return); at τ ≠ 1 every chunk after the first vouches
 # for its moments.  `logs`: per-step device logs (Δh, wetted!) land in slices of the caller's buffers.
-function _loop(sys, state, verbose; θ = sys.param.θ, incl = nothing, hmin = nothing, hmax = nothing, wet = nothing)
+function _loop(sys, state, verbose; θ = sys.param.θ, incl = nothing, hmin = nothing, hmax = nothing, wet = nothing,
+               host_in = nothing, host_out = nothing)
     t, Tmax, tdump = 1, sys.param.Tmax, max(1, sys.param.tdump)
     lazy = sys.param.τ == 1 ? LOOP_LAZY_POPULATIONS : Cint(0)
     while t <= Tmax
@@ -355,7 +368,8 @@ function _loop(sys, state, verbose; θ = sys.param.θ, incl = nothing, hmin = no
             logs = CLogs(hmin === nothing ? NULLF : pointer(hmin, t), hmax === nothing ? NULLF : pointer(hmax, t),
                          wet === nothing ? CuPtr{Culonglong}(0) : pointer(wet, t), 0.055)
         end
-        fused_steps!(state, sys, nxt - t; θ = θ, incl = incl, logs = logs, flags = flags)
+        fused_steps!(state, sys, nxt - t; θ = θ, incl = incl, logs = logs, flags = flags,
+                     host_in = t == 1 ? host_in : nothing, host_out = nxt > Tmax ? host_out : nothing)
         t = nxt
     end
     return state
@@ -363,6 +377,21 @@ end
 
 Swalbe.time_loop(sys::SysConst, state::CuState; verbose = false) = _loop(sys, state, verbose)          # :6-25
 Swalbe.time_loop(sys::SysConst, state::CuState, θ; verbose = false) = _loop(sys, state, verbose; θ = θ)  # :26-45
+
+"""
+    run_host!(h_out, sys, state, h_in; θ, verbose)
+
+The shape of every shipped GPU script -- `state.height .= CUDA.adapt(CuArray, h_in)`; `time_loop(sys, state, θ)`;
+`h_out .= Array(state.height)` (scripts/Moving_wettability_structs.jl:39,60-71) -- as one call whose two PCIe copies hide
+behind the first and the last steps of the loop (`swalbe_time_loop_host`).  `h_in`, `h_out`: Lx x Ly host matrices
+(page-lock them once with `CUDA.pin` for the overlap).  The state and `h_out` hold what the plain sequence leaves;
+`synchronize()` before reading `h_out`.
+"""
+function run_host!(h_out::Array{Float64,2}, sys::SysConst, state::CuState, h_in::Array{Float64,2}; θ = sys.param.θ,
+                   verbose = false)
+    _loop(sys, state, verbose; θ = θ, host_in = h_in, host_out = h_out)
+    return h_out
+end
 
 # time_loop(sys, state, Δh::Vector): max - min of the height BEFORE every step, reduced on the device (:47-67)
 function Swalbe.time_loop(sys::SysConst, state::CuState, Δh::Vector; verbose = false)

@@ -421,3 +421,112 @@ def test_persistent_cluster_kernel_on_cpu(simt, Lx, Ly, C, nsteps):
         dh, w = oc.time_loop(b, p, nsteps=nsteps, log_dh=True, log_wetted=True, hthresh=1.0)
         _same(a, b, FIELDS + ("ftemp",))
         assert np.array_equal(mx - mn, np.asarray(dh)) and [int(v) for v in wet] == [int(v) for v in w]
+
+
+# ---- swalbe_time_loop_host: the skewed sweeps behind the upload front / ahead of the download (csrc/sweep.h) ------------
+
+def _host_loop_ops(Lx, Ly, nsteps, has_in, has_out, band_rows, kmax):
+    from swalbe_b200 import _lib
+
+    lib = _lib.load()
+    n = C.c_int(0)
+    _lib.call("swalbe_selftest_host_loop_schedule", Lx, Ly, nsteps, int(has_in), int(has_out), band_rows, kmax, 1, None, 0, C.byref(n))
+    buf = (C.c_int * (6 * n.value))()
+    _lib.call("swalbe_selftest_host_loop_schedule", Lx, Ly, nsteps, int(has_in), int(has_out), band_rows, kmax, 1, buf, n.value,
+              C.byref(n))
+    assert lib is not None
+    return [tuple(buf[6 * q:6 * q + 6]) for q in range(n.value)]
+
+
+def _replay_host_loop(simt, ops, st, p, nsteps, h_host, out_host, early_copies, lazy, W=32, rows=7):
+    """What enqueue_steps_host (csrc/fused.cu) issues, on NumPy planes: A = the state's planes, B = the plan's scratch;
+    `early_copies`: every upload happens before the first launch and every download after the last one (the other legal
+    extreme of the stream order); else they happen exactly where the schedule lists them."""
+    Lx, Ly = st.Lx, st.Ly
+    A = [st.height, st.velx, st.vely]
+    B = [np.full_like(st.height, np.nan), np.full_like(st.height, np.nan), np.full_like(st.height, np.nan)]
+    src0 = A if nsteps % 2 == 0 else B
+    if h_host is not None:
+        src0[0][...] = np.nan  # rows that have not arrived yet must never be used
+    elif src0 is B:
+        B[0][...] = A[0]
+    if src0 is B:
+        B[1][...], B[2][...] = A[1], A[2]
+    ups = [o for o in ops if o[0] == 0]
+    downs = [o for o in ops if o[0] == 2]
+    if early_copies:
+        for _, _, j0, j1, _, _ in ups:
+            src0[0][:, j0:j1] = h_host[:, j0:j1]
+    arrived = set()
+    for kind, s, j0, j1, band, seam in ops:
+        if kind == 0:
+            if not early_copies:
+                src0[0][:, j0:j1] = h_host[:, j0:j1]
+            arrived.add(band)
+        elif kind == 2:
+            if not early_copies:
+                out_host[:, j0:j1] = A[0][:, j0:j1]
+        else:
+            assert band < 0 or band in arrived, "a launch waits for a band that is queued after it"
+            if j1 <= j0:
+                continue
+            last = s == nsteps - 1
+            reads_A = (nsteps - s) % 2 == 0
+            src, dst = (A, B) if reads_A else (B, A)
+            q = SimtStep()
+            q.flavour = FULL if last else STRICT
+            q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = Lx, Ly, j0, j1, W, rows, 1
+            q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+            q.cospi_theta, q.n, q.m, q.pressure_variant, q.slip_variant = onp.cospi(p.theta), p.n, p.m, 0, 0
+            q.h_in, q.ux_in, q.uy_in = (_ptr(a) for a in src)
+            q.h_out, q.ux_out, q.uy_out = (_ptr(a) for a in dst)
+            q.fstride = Lx * Ly
+            q.f_out = _ptr(st.fout) if (last or not lazy) else None
+            if last:
+                q.f_out2 = _ptr(st.ftemp)
+                for name, fld in (("pressure", st.pressure), ("hgx", st.hgradpx), ("hgy", st.hgradpy), ("slipx", st.slipx),
+                                  ("slipy", st.slipy), ("Fx", st.Fx), ("Fy", st.Fy), ("feq", st.feq), ("vsq", st.vsq)):
+                    setattr(q, name, _ptr(fld))
+            assert simt.simt_step(C.byref(q)) == 0
+    if early_copies:
+        for _, _, j0, j1, _, _ in downs:
+            out_host[:, j0:j1] = A[0][:, j0:j1]
+
+
+@pytest.mark.parametrize("nsteps,has_in,has_out", [(3, True, True), (6, True, True), (11, True, True), (4, True, False),
+                                                   (5, False, True), (9, True, False)])
+def test_host_loop_sweeps_on_cpu(simt, nsteps, has_in, has_out):
+    """Every launch of the schedule through the emulated kernels (partial row ranges with the periodic wrap), two moment
+    buffers, rows that have not been uploaded poisoned with NaN: the state and the downloaded plane equal the oracle's
+    after the same number of steps, with the copies replayed at both extremes of what the streams allow."""
+    Lx, Ly, band, kmax = 40, 126, 31, 4
+    ops = _host_loop_ops(Lx, Ly, nsteps, has_in, has_out, band, kmax)
+    steps = [o for o in ops if o[0] == 1]
+    assert any(o[5] for o in steps) and len([o for o in ops if o[0] == 0]) == (4 if has_in else 0)
+    # every step covers every row exactly once
+    for s in range(nsteps):
+        cover = np.zeros(Ly, dtype=int)
+        for _, ss, j0, j1, _, _ in steps:
+            if ss == s and j1 > j0:
+                cover[j0:j1] += 1
+        assert (cover == 1).all(), (s, cover)
+    if has_out:
+        cover = np.zeros(Ly, dtype=int)
+        for o in ops:
+            if o[0] == 2:
+                cover[o[2]:o[3]] += 1
+        assert (cover == 1).all()
+    p = onp.Params(g=-0.001, gamma=0.0005)
+    ref = _state(Lx, Ly, 11)
+    h0 = ref.height.copy()
+    oc.time_loop(ref, p, nsteps=nsteps)
+    for early in (False, True):
+        for lazy in (False, True):
+            st = _state(Lx, Ly, 11)
+            if has_in:
+                st.height[...] = 7.0  # the device plane holds something else: the job starts from the host plane
+            out = np.full((Lx, Ly), np.nan)
+            _replay_host_loop(simt, ops, st, p, nsteps, h0 if has_in else None, out if has_out else None, early, lazy)
+            _same(st, ref, FIELDS + AUX)
+            if has_out:
+                assert np.array_equal(out, ref.height)
