@@ -221,6 +221,13 @@ typedef struct swalbe_loop_logs {
   double *hmin, *hmax;        /* device, nsteps each: min/max of height BEFORE each step (src/simulate.jl:56); NULL = off */
   unsigned long long *wetted; /* device, nsteps: count(height > hthresh) in the callback slot (src/simulate.jl:89); NULL = off */
   double hthresh;             /* 0.055 in wetted!  src/measures.jl:13 */
+  /* mass log: `mass = sum(state.height)` of the drivers' dump steps (src/simulate.jl:8-14) without leaving the loop.
+   * hsum[m] = sum of the height BEFORE step hsum_first + m*hsum_every of the call (0-based), for every such step below
+   * nsteps.  Device memory or page-locked host memory: each value is written with a system-scope store as soon as it is
+   * known, so a host thread may poll a slot it pre-set to NaN and print progress while the loop runs.  The sum is formed
+   * row by row in a fixed order (it does not depend on how the loop is cut into launches).  NULL = off. */
+  double *hsum;
+  int hsum_first, hsum_every;
 } swalbe_loop_logs;
 
 typedef struct swalbe_plan swalbe_plan; /* opaque: library-owned scratch (3 moment planes) + launch geometry */

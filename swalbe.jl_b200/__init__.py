@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import time
 
 import numpy as np
 
@@ -601,13 +602,17 @@ def _c_params(p: Taumucs, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None, t
 
 def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_variant=_lib.SLIP_STANDARD, incl=None,
                 thermal_seed=None, step0=0, lazy_populations=False, log_minmax=False, log_wetted=False, hthresh=0.055,
-                pressure_variant=None, skip_aux=False, moments_consistent=False, host_in=None, host_out=None):
+                pressure_variant=None, skip_aux=False, moments_consistent=False, host_in=None, host_out=None,
+                mass_log=None):
     """nsteps iterations of the loop body src/simulate.jl:15-22 through swalbe_time_loop (one fused kernel/step).
 
     ``host_in`` / ``host_out`` (pinned CPU torch tensors or NumPy arrays of Lx*Ly float64 in the memory order of
     ``state.height``, i.e. ``h.T`` C-contiguous): the loop starts from the height in ``host_in`` and / or leaves the final
     height in ``host_out`` (swalbe_time_loop_host: on large lattices the copies travel in row bands behind which / ahead of
     which the first / last steps run).  The download is complete once the current stream has been synchronised.
+
+    ``mass_log = (first, every, out)``: out[m] = sum(height) BEFORE step first + m*every of this call (0-based), written by
+    the device as soon as it is known; ``out``: float64 CUDA tensor or pinned CPU tensor (pre-set to NaN to poll it).
 
     ``moments_consistent`` (τ ≠ 1): the caller vouches that height/velx/vely are the moments of ftemp -- true after any
     earlier fused_steps/time_loop/moments! call on this state, false after writing an initial condition into height --
@@ -631,7 +636,15 @@ def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_varia
     logs.hthresh = hthresh
     flags = ((_lib.LOOP_LAZY_POPULATIONS if lazy_populations else 0) | (_lib.LOOP_SKIP_AUX if skip_aux else 0) |
              (_lib.LOOP_MOMENTS_CONSISTENT if moments_consistent else 0))
-    lg = C.byref(logs) if (log_minmax or log_wetted) else None
+    if mass_log is not None:
+        logs.hsum_first, logs.hsum_every, out = int(mass_log[0]), int(mass_log[1]), mass_log[2]
+        if out.dtype != torch.float64 or not out.is_contiguous() or (out.device.type == "cpu" and not out.is_pinned()):
+            raise ValueError("mass_log: contiguous float64 CUDA tensor or pinned CPU tensor expected")
+        need = 0 if nsteps <= logs.hsum_first else (nsteps - 1 - logs.hsum_first) // max(1, logs.hsum_every) + 1
+        if out.numel() < need:
+            raise ValueError(f"mass_log: {need} slots needed, {out.numel()} given")
+        logs.hsum = out.data_ptr()
+    lg = C.byref(logs) if (log_minmax or log_wetted or mass_log is not None) else None
     if host_in is None and host_out is None:
         _lib.call("swalbe_time_loop", st.plan(), C.byref(cs), C.byref(q), int(nsteps), int(step0), flags, lg, _stream())
     else:
@@ -652,6 +665,27 @@ def _host_ptr(x, st):
     if x.device.type != "cpu" or x.dtype != _torch().float64 or x.numel() != st.Lx * st.Ly or not x.is_contiguous():
         raise ValueError("host plane: contiguous float64 CPU tensor of Lx*Ly elements expected")
     return C.c_void_p(x.data_ptr())
+
+
+_ONE_CALL_SITES = 1 << 21  # time_loop: lattices from this size on run as one library call (see time_loop)
+
+
+def _mass_buffer(n):
+    """Pinned host slots for the in-loop mass log, pre-set to NaN.  The buffer is owned by the module and never returned to
+    torch's pinned-memory cache: the device writes into it from inside a loop that may still be running when time_loop
+    returns, so it is only reused once the loop that used it last has finished."""
+    torch = _torch()
+    busy = getattr(_mass_buffer, "busy", None)
+    if busy is not None:
+        busy.synchronize()
+        _mass_buffer.busy = None
+    buf = getattr(_mass_buffer, "buf", None)
+    if buf is None or buf.numel() < max(1, n):
+        buf = torch.empty(max(16, 2 * n), dtype=torch.float64).pin_memory()
+        _mass_buffer.old = getattr(_mass_buffer, "old", []) + [getattr(_mass_buffer, "buf", None)]  # (kept alive)
+        _mass_buffer.buf = buf
+    buf.fill_(float("nan"))
+    return buf
 
 
 class _MassDumps:
@@ -687,10 +721,12 @@ class _MassDumps:
         while self.pending and (block or self.pending[0][1].query()):
             t, ev, i = self.pending.pop(0)
             ev.synchronize()
-            mass = float(host[i, 2])
-            self.masses.append((t, mass))
-            if self.verbose:
-                print(f"Time step {t} mass is {round(mass, 3)}")
+            self._emit(t, float(host[i, 2]))
+
+    def _emit(self, t, mass):
+        self.masses.append((t, mass))
+        if self.verbose:
+            print(f"Time step {t} mass is {round(mass, 3)}")
 
 
 def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, lazy_populations=True, host_in=None,
@@ -729,6 +765,31 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, la
     incl = (measure, 0.5 + 0.5 * math.tanh((1000 - 0) / 1)) if cb is inclination else None  # defaults of :363
     t = 1
     tdump = max(1, p.tdump)
+    if sys_.Lx * sys_.Ly >= _ONE_CALL_SITES and not chunk and p.Tmax >= 1:
+        # Large lattices: the whole loop is ONE library call.  The mass of every dump step is summed on the device inside
+        # the loop (logs.hsum) and lands in pinned host memory by itself; a verbose loop prints each line as it arrives.
+        # (Small lattices keep the chunks between two dumps: repeated chunks are what the CUDA-graph replay needs.)
+        torch = _torch()
+        ndumps = p.Tmax // tdump
+        host = _mass_buffer(ndumps)
+        mn, mx, wet = fused_steps(st, sys_, p.Tmax, θ=θ, incl=incl, log_minmax=dh is not None, log_wetted=cb is wetted,
+                                  lazy_populations=bool(lazy_populations) and p.tau == 1.0, host_in=host_in, host_out=host_out,
+                                  mass_log=(tdump - 1, tdump, host) if ndumps else None)
+        done = torch.cuda.Event()
+        done.record()
+        _mass_buffer.busy = done
+        if verbose:
+            for m in range(ndumps):
+                while math.isnan(host[m].item()):
+                    if done.query() and math.isnan(host[m].item()):
+                        raise SwalbeError("time_loop: the loop finished without writing the mass of a dump step")
+                    time.sleep(5e-5)
+                print(f"Time step {(m + 1) * tdump} mass is {round(host[m].item(), 3)}")
+        if dh is not None:
+            dh.extend((mx - mn).cpu().tolist())
+        if cb is wetted:
+            measure.extend(wet.cpu().tolist())
+        return st if cb is None else (st, measure)
     dumps = _MassDumps(verbose)
     while t <= p.Tmax:
         if t % tdump == 0:

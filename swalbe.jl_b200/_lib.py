@@ -54,7 +54,8 @@ class CState1D(C.Structure):
 
 class CLogs(C.Structure):
     """struct swalbe_loop_logs"""
-    _fields_ = [("hmin", _vp), ("hmax", _vp), ("wetted", _vp), ("hthresh", _d)]
+    _fields_ = [("hmin", _vp), ("hmax", _vp), ("wetted", _vp), ("hthresh", _d), ("hsum", _vp), ("hsum_first", _i),
+                ("hsum_every", _i)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/swalbe_b200.h one to one

@@ -20,6 +20,38 @@ __global__ void k_init_logs(double *mn, double *mx, unsigned long long *wet, int
   if (wet) wet[i] = 0ull;
 }
 
+// mass log (logs->hsum): sum of one row of the height in a fixed order, then of the row sums in a fixed order -- the result
+// does not depend on how a loop is cut into launches (whole lattice, bands of a host-loop sweep, seam strips)
+__global__ void __launch_bounds__(256) k_rowsum(const double *__restrict__ h, int Lx, int j0, double *__restrict__ rowsum) {
+  __shared__ double sh[256];
+  const int row = j0 + blockIdx.x;
+  const double *p = h + (size_t)row * Lx;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < Lx; i += 256) v += p[i];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowsum[row] = sh[0];
+}
+__global__ void __launch_bounds__(1024) k_rowsum_final(const double *__restrict__ rowsum, int Ly, double *out) {
+  __shared__ double sh[1024];
+  double v = 0.0;
+  for (int j = threadIdx.x; j < Ly; j += 1024) v += rowsum[j];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *(volatile double *)out = sh[0];  // (out may be page-locked host memory that a host thread polls)
+    __threadfence_system();
+  }
+}
+
 // ---- kernel variant table (instantiated in fused_v*.cu) ---------------------------------------------
 static const Variant *const g_variants[] = {&g_variant_128, &g_variant_160, &g_variant_192, &g_variant_224, &g_variant_256};
 static const int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
@@ -221,6 +253,8 @@ struct GraphKey {
 struct swalbe_plan {
   int Lx, Ly;
   double *scratch;  // 3 moment planes (ping-pong partner of the caller's height/velx/vely)
+  double *rowsum;   // row sums of the height (mass log): rowsum_planes x Ly, allocated on first use
+  int rowsum_planes;
   double *log_part; // partial per-step logs of the cluster kernel (grown on demand)
   size_t log_part_doubles;
   int graph_launches;  // kernels inside the captured graph (the launch counter advances by this on replay)
@@ -263,7 +297,7 @@ int swalbe_plan_create(swalbe_plan **plan, int Lx, int Ly) {
   if (!plan) return set_error(SWALBE_ERR_ARG, "plan is NULL");
   if (int e = check_extent(Lx, Ly)) return e;
   swalbe_plan *p = new swalbe_plan();
-  p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr; p->log_part = nullptr; p->log_part_doubles = 0; p->graph_launches = 0;
+  p->Lx = Lx; p->Ly = Ly; p->scratch = nullptr; p->rowsum = nullptr; p->rowsum_planes = 0; p->log_part = nullptr; p->log_part_doubles = 0; p->graph_launches = 0;
   p->cap_stream = nullptr; p->graph_exec = nullptr; p->have_graph = p->have_seen = false; p->graph_nsteps = 0;
   p->ngeoms = 0;
   p->s_h2d = p->s_d2h = nullptr; p->have_host_streams = false;
@@ -286,6 +320,7 @@ int swalbe_plan_destroy(swalbe_plan *plan) {
     for (cudaEvent_t ev : plan->ev_up) cudaEventDestroy(ev);
   }
   cudaFree(plan->scratch);
+  cudaFree(plan->rowsum);
   cudaFree(plan->log_part);
   delete plan;
   return 0;
@@ -293,6 +328,8 @@ int swalbe_plan_destroy(swalbe_plan *plan) {
 
 static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe_params *prm, int nsteps,
                          unsigned long long step0, int flags, const swalbe_loop_logs *logs, cudaStream_t stream);
+static int enqueue_steps_dumps(swalbe_plan *plan, const swalbe_state *st, const swalbe_params *prm, int nsteps,
+                               unsigned long long step0, int flags, const swalbe_loop_logs *logs, cudaStream_t stream);
 
 static GraphKey make_graph_key(const swalbe_state *st, const swalbe_params *p, int nsteps, int flags) {
   GraphKey k;
@@ -316,7 +353,7 @@ static GraphKey make_graph_key(const swalbe_state *st, const swalbe_params *p, i
 static bool graph_candidate(const swalbe_plan *plan, const swalbe_params *prm, int nsteps, const swalbe_loop_logs *logs,
                             cudaStream_t stream) {
   if (!env_int("SWALBE_GRAPH", 1) || nsteps < 8 || nsteps > 16384 || prm->use_thermal) return false;  // (graph size bound)
-  if (logs && (logs->hmin || logs->hmax || logs->wetted)) return false;
+  if (logs && (logs->hmin || logs->hmax || logs->wetted || logs->hsum)) return false;
   if ((size_t)plan->Lx * plan->Ly > (size_t)std::max(0, env_int("SWALBE_GRAPH_MAX", 1024 * 1024))) return false;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -329,7 +366,7 @@ int swalbe_time_loop(swalbe_plan *plan, const swalbe_state *st, const swalbe_par
   if (nsteps < 0) return set_error(SWALBE_ERR_ARG, "nsteps < 0");
   if (nsteps == 0) return 0;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!graph_candidate(plan, prm, nsteps, logs, stream)) return enqueue_steps(plan, st, prm, nsteps, step0, flags, logs, stream);
+  if (!graph_candidate(plan, prm, nsteps, logs, stream)) return enqueue_steps_dumps(plan, st, prm, nsteps, step0, flags, logs, stream);
   const GraphKey key = make_graph_key(st, prm, nsteps, flags);
   if (plan->have_graph && memcmp(&key, &plan->graph_key, sizeof(key)) == 0) {
     SW_CUDA(cudaGraphLaunch(plan->graph_exec, stream));
@@ -536,6 +573,78 @@ static int enqueue_steps(swalbe_plan *plan, const swalbe_state *st, const swalbe
   return 0;
 }
 
+// ---- mass log: sum(height) BEFORE selected steps (logs->hsum) -----------------------------------------------------------
+
+struct MassLog {
+  double *out = nullptr;  // device-side address of logs->hsum
+  int first = 0, every = 0, nsteps = 0;
+  bool on() const { return out != nullptr; }
+  bool wants(int i) const { return on() && i >= first && i < nsteps && (i - first) % every == 0; }
+  double *slot(int i) const { return out + (i - first) / every; }
+  int next_after(int i) const {  // smallest logged state index > i, or nsteps
+    if (!on()) return nsteps;
+    int n = i < first ? first : first + ((i - first) / every + 1) * every;
+    return n < nsteps ? n : nsteps;
+  }
+};
+
+// planes: states whose rows may be summed concurrently (sweeps of the host loop that span more than one logged step)
+static int mass_log_setup(swalbe_plan *plan, const swalbe_loop_logs *logs, int nsteps, MassLog *m, int planes = 1) {
+  *m = MassLog();
+  m->nsteps = nsteps;
+  if (!logs || !logs->hsum) return 0;
+  if (logs->hsum_every < 1 || logs->hsum_first < 0) return set_error(SWALBE_ERR_ARG, "logs.hsum needs hsum_every >= 1 and hsum_first >= 0");
+  cudaPointerAttributes at;
+  SW_CUDA(cudaPointerGetAttributes(&at, logs->hsum));
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) m->out = logs->hsum;
+  else if (at.type == cudaMemoryTypeHost && at.devicePointer) m->out = (double *)at.devicePointer;
+  else return set_error(SWALBE_ERR_ARG, "logs.hsum must be device memory or page-locked (mapped) host memory");
+  m->first = logs->hsum_first; m->every = logs->hsum_every;
+  if (plan->rowsum_planes < planes) {
+    if (plan->rowsum) SW_CUDA(cudaFree(plan->rowsum));  // (stream-ordered with every launch that used it: cudaFree synchronises)
+    plan->rowsum = nullptr; plan->rowsum_planes = 0;
+    SW_CUDA(cudaMalloc((void **)&plan->rowsum, sizeof(double) * (size_t)plan->Ly * planes));
+    plan->rowsum_planes = planes;
+  }
+  return 0;
+}
+static int mass_rows(swalbe_plan *plan, const double *h, int jbeg, int jend, cudaStream_t stream, int plane = 0) {
+  if (jend <= jbeg) return 0;
+  k_rowsum<<<jend - jbeg, 256, 0, stream>>>(h, plan->Lx, jbeg, plan->rowsum + (size_t)plane * plan->Ly);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+static int mass_final(swalbe_plan *plan, double *slot, cudaStream_t stream, int plane = 0) {
+  k_rowsum_final<<<1, 1024, 0, stream>>>(plan->rowsum + (size_t)plane * plan->Ly, plan->Ly, slot);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+// the plain loop cut at the logged steps (every piece lands in the caller's planes, where the rows are summed)
+static int enqueue_steps_dumps(swalbe_plan *plan, const swalbe_state *st, const swalbe_params *prm, int nsteps,
+                               unsigned long long step0, int flags, const swalbe_loop_logs *logs, cudaStream_t stream) {
+  MassLog ml;
+  if (int e = mass_log_setup(plan, logs, nsteps, &ml)) return e;
+  if (!ml.on()) return enqueue_steps(plan, st, prm, nsteps, step0, flags, logs, stream);
+  if (!st->height) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop: state.height is NULL");
+  for (int s = 0; s < nsteps;) {
+    if (ml.wants(s)) {
+      if (int e = mass_rows(plan, st->height, 0, plan->Ly, stream)) return e;
+      if (int e = mass_final(plan, ml.slot(s), stream)) return e;
+    }
+    const int nxt = ml.next_after(s);
+    swalbe_loop_logs sub = *logs;
+    sub.hsum = nullptr;
+    if (sub.hmin) sub.hmin += s;
+    if (sub.hmax) sub.hmax += s;
+    if (sub.wetted) sub.wetted += s;
+    const int f = flags | (nxt < nsteps ? SWALBE_LOOP_SKIP_AUX : 0) | (s > 0 ? SWALBE_LOOP_MOMENTS_CONSISTENT : 0);
+    if (int e = enqueue_steps(plan, st, prm, nxt - s, step0 + (unsigned long long)s, f, &sub, stream)) return e;
+    s = nxt;
+  }
+  return 0;
+}
+
 // ---- time loop from / to host memory (sweep.h) --------------------------------------------------------------------------
 
 static int host_streams(swalbe_plan *plan) {
@@ -568,7 +677,7 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
   if (cfg.nbands == 0) {      // small lattices, tau != 1: the copies simply bracket the loop on the caller's stream
     if (hin) SW_CUDA(cudaMemcpyAsync(st->height, hin, N * sizeof(double), cudaMemcpyHostToDevice, stream));
     if (nsteps > 0)
-      if (int e = enqueue_steps(plan, st, prm, nsteps, step0, flags, logs, stream)) return e;
+      if (int e = enqueue_steps_dumps(plan, st, prm, nsteps, step0, flags, logs, stream)) return e;
     if (hout) SW_CUDA(cudaMemcpyAsync(hout, st->height, N * sizeof(double), cudaMemcpyDeviceToHost, stream));
     return 0;
   }
@@ -608,6 +717,22 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
   a.ct_field = prm->cospi_theta_field;
   const bool log_mm = logs && logs->hmin && logs->hmax;
   const bool log_wet = logs && logs->wetted;
+  // mass log: the rows of a logged state are summed right behind the launch (or upload) that produces them
+  MassLog ml;
+  const int mass_planes = (logs && logs->hsum && logs->hsum_every > 0) ? kphase / logs->hsum_every + 2 : 1;
+  if (int e = mass_log_setup(plan, logs, nsteps, &ml, mass_planes)) return e;
+  std::vector<int> mass_rows_done(mass_planes, 0);
+  auto mass_piece = [&](int state, const double *h, int jbeg, int jend) -> int {
+    const int pl = ((state - ml.first) / ml.every) % mass_planes;
+    if (int e = mass_rows(plan, h, jbeg, jend, stream, pl)) return e;
+    mass_rows_done[pl] += jend - jbeg;
+    if (mass_rows_done[pl] == Ly) {
+      mass_rows_done[pl] = 0;
+      return mass_final(plan, ml.slot(state), stream, pl);
+    }
+    return 0;
+  };
+  int up_beg[64] = {0}, up_end[64] = {0};
 
   // moment ping-pong as in the plain loop: the last step lands in the caller's planes (A), so step s reads A when
   // (nsteps - s) is even; the upload goes straight into the planes step 0 reads
@@ -639,6 +764,7 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
       const size_t off = (size_t)op.jbeg * Lx, cnt = (size_t)(op.jend - op.jbeg) * Lx;
       if (!nocopy) SW_CUDA(cudaMemcpyAsync(src0[0] + off, hin + off, cnt * sizeof(double), cudaMemcpyHostToDevice, plan->s_h2d));
       SW_CUDA(cudaEventRecord(plan->ev_up[op.band], plan->s_h2d));
+      up_beg[op.band] = op.jbeg; up_end[op.band] = op.jend;
       mark(plan->s_h2d, "upload band %d done", op.band, 0);
     }
   if (!src0_is_A) {
@@ -651,6 +777,8 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
     SW_LAUNCH_CHECK();
     a.hthresh = logs->hthresh;
   }
+  if (ml.wants(0) && !hin)
+    if (int e = mass_piece(0, src0[0], 0, Ly)) return e;
   for (const SweepOp &op : ops) {
     if (op.kind == SWEEP_UPLOAD) continue;
     if (op.kind == SWEEP_DOWNLOAD) {
@@ -662,7 +790,11 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
       mark(plan->s_d2h, "download %d done", op.band, 0);
       continue;
     }
-    if (op.band >= 0) SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_up[op.band], 0));
+    if (op.band >= 0) {
+      SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_up[op.band], 0));
+      if (ml.wants(0))
+        if (int e = mass_piece(0, src0[0], up_beg[op.band], up_end[op.band])) return e;
+    }
     if (op.jend <= op.jbeg) continue;
     const int s = op.step;
     const bool last = s == nsteps - 1;
@@ -689,6 +821,8 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
     b.rows_per_cta = g.rows_per_cta; b.W = g.W;
     b.jbeg = op.jbeg; b.jend = op.jend;
     if (int e = launch_fused(g, b, use_full ? key_full : key_mid, stream)) return e;
+    if (ml.wants(s + 1))
+      if (int e = mass_piece(s + 1, dst[0], op.jbeg, op.jend)) return e;
     if (trace && (op.seam == 0) && (s == cfg.k_up - 1 || s == nsteps - 1 || op.jend - op.jbeg == Ly))
       mark(stream, "step %d rows from %d done", s, op.jbeg);
   }

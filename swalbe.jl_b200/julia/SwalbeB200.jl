@@ -232,7 +232,10 @@ struct CParams       # struct swalbe_params
 end
 struct CLogs         # struct swalbe_loop_logs
     hmin::CuPtr{Float64}; hmax::CuPtr{Float64}; wetted::CuPtr{Culonglong}; hthresh::Cdouble
+    hsum::Ptr{Float64}; hsum_first::Cint; hsum_every::Cint
 end
+# (no mass log: the Julia drivers below read `sum(state.height)` between their chunks like the reference does)
+CLogs(hmin, hmax, wetted, hthresh) = CLogs(hmin, hmax, wetted, hthresh, Ptr{Float64}(C_NULL), Cint(0), Cint(0))
 
 cstate(s::CuState) = CState(pointer(s.fout), pointer(s.ftemp), pointer(s.feq), pointer(s.height), pointer(s.velx),
     pointer(s.vely), pointer(s.vsq), pointer(s.pressure), pointer(s.Fx), pointer(s.Fy), pointer(s.slipx), pointer(s.slipy),

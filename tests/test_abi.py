@@ -60,7 +60,7 @@ def test_struct_layouts_match_header():
 
     assert C.sizeof(_lib.CState) == 17 * 8
     assert C.sizeof(_lib.CParams) == 8 * 8 + 2 * 4 + 8 + 8 + 2 * 4 + 4 + 4 + 3 * 8 + 4 + 4 + 8
-    assert C.sizeof(_lib.CLogs) == 32
+    assert C.sizeof(_lib.CLogs) == 48
 
 
 def test_no_cpu_fallback():

@@ -140,7 +140,47 @@ def test_host_loop_default_bands_large_lattice(sw):
         _plain_vs_host(sw, None, sysc, h0, z, z, nsteps, only=("both",), lazy_populations=True)
 
 
-def test_mass_prints_are_asynchronous_but_complete(sw, capsys):
+@pytest.mark.parametrize("nsteps,first,every", [(23, 2, 4), (9, 0, 1), (30, 9, 10), (5, 7, 3)])
+def test_mass_log_inside_the_loop(sw, monkeypatch, nsteps, first, every):
+    """logs.hsum: sum(height) BEFORE the selected steps, produced inside the loop -- by the plain loop (device slots), by the
+    host loop's sweeps (pinned host slots, rows summed band by band behind the launches that produce them): the same
+    bits either way (fixed row-wise order), and the oracle's masses to round-off."""
+    import torch
+
+    _bands(monkeypatch, 50)
+    Lx, Ly = 150, 200
+    h0, ux0, uy0 = _inputs(Lx, Ly, nsteps)
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(g=-0.001, γ=0.0005))
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = h0; ref.velx[...] = ux0; ref.vely[...] = uy0
+    want = []
+    for s in range(nsteps):
+        if s >= first and (s - first) % every == 0:
+            want.append(ref.height.sum())
+        oc.time_loop(ref, onp.Params(g=-0.001, gamma=0.0005), nsteps=1)
+    nslots = max(1, len(want))
+    a = sw.Sys(sysc, "GPU")
+    a.height.set(h0); a.velx.set(ux0); a.vely.set(uy0)
+    dev = torch.full((nslots,), float("nan"), dtype=torch.float64, device="cuda")
+    sw.fused_steps(a, sysc, nsteps, mass_log=(first, every, dev))
+    b = sw.Sys(sysc, "GPU")
+    b.velx.set(ux0); b.vely.set(uy0)
+    host = torch.full((nslots,), float("nan"), dtype=torch.float64).pin_memory()
+    hout = torch.empty(Lx * Ly, dtype=torch.float64).pin_memory()
+    sw.fused_steps(b, sysc, nsteps, mass_log=(first, every, host), host_in=_pinned(h0), host_out=hout, lazy_populations=True)
+    torch.cuda.synchronize()
+    got_a, got_b = dev.cpu().numpy()[:len(want)], host.numpy()[:len(want)]
+    assert np.array_equal(got_a, got_b)
+    assert np.allclose(got_a, np.array(want), rtol=1e-13, atol=0)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name).numpy(), getattr(ref, name)), name
+        assert np.array_equal(getattr(b, name).numpy(), getattr(ref, name)), name
+    if len(want) < nslots:
+        assert np.isnan(dev.cpu().numpy()[len(want):]).all()
+
+
+@pytest.mark.parametrize("one_call", [False, True])
+def test_mass_prints_are_asynchronous_but_complete(sw, capsys, monkeypatch, one_call):
     """time_loop(verbose=True): one line per dump step (t % tdump == 0), in order, with the mass of the state BEFORE that
     step (src/simulate.jl:8-14); the read-back does not synchronise the loop, the lines are all there on return."""
     Lx, Ly = 96, 80
@@ -148,7 +188,15 @@ def test_mass_prints_are_asynchronous_but_complete(sw, capsys):
     sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(Tmax=35, tdump=5))
     st = sw.Sys(sysc, "GPU")
     st.height.set(h0)
+    if one_call:  # the path of large lattices: the whole loop is one library call with the in-loop mass log
+        monkeypatch.setattr(sw, "_ONE_CALL_SITES", 1)
     sw.time_loop(sysc, st, verbose=True)
+    other = sw.Sys(sysc, "GPU")
+    other.height.set(h0)
+    monkeypatch.setattr(sw, "_ONE_CALL_SITES", 1 if not one_call else 1 << 40)
+    sw.time_loop(sysc, other)
+    for name in FIELDS:
+        assert np.array_equal(getattr(st, name).numpy(), getattr(other, name).numpy()), name
     lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("Time step")]
     assert [int(ln.split()[2]) for ln in lines] == [5, 10, 15, 20, 25, 30, 35]
     for ln in lines:
@@ -160,6 +208,7 @@ def test_time_loop_and_run_host_drivers(sw, monkeypatch):
     import torch
 
     _bands(monkeypatch, 40)
+    monkeypatch.setattr(sw, "_ONE_CALL_SITES", 1)
     Lx, Ly = 128, 250
     h0, _, _ = _inputs(Lx, Ly, 8)
     sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(Tmax=50, tdump=20))

@@ -438,7 +438,7 @@ def _host_loop_ops(Lx, Ly, nsteps, has_in, has_out, band_rows, kmax):
     return [tuple(buf[6 * q:6 * q + 6]) for q in range(n.value)]
 
 
-def _replay_host_loop(simt, ops, st, p, nsteps, h_host, out_host, early_copies, lazy, W=32, rows=7):
+def _replay_host_loop(simt, ops, st, p, nsteps, h_host, out_host, early_copies, lazy, W=40, rows=16):
     """What enqueue_steps_host (csrc/fused.cu) issues, on NumPy planes: A = the state's planes, B = the plan's scratch;
     `early_copies`: every upload happens before the first launch and every download after the last one (the other legal
     extreme of the stream order); else they happen exactly where the schedule lists them."""
@@ -493,8 +493,7 @@ def _replay_host_loop(simt, ops, st, p, nsteps, h_host, out_host, early_copies, 
             out_host[:, j0:j1] = A[0][:, j0:j1]
 
 
-@pytest.mark.parametrize("nsteps,has_in,has_out", [(3, True, True), (6, True, True), (11, True, True), (4, True, False),
-                                                   (5, False, True), (9, True, False)])
+@pytest.mark.parametrize("nsteps,has_in,has_out", [(3, True, True), (11, True, True), (5, False, True), (9, True, False)])
 def test_host_loop_sweeps_on_cpu(simt, nsteps, has_in, has_out):
     """Every launch of the schedule through the emulated kernels (partial row ranges with the periodic wrap), two moment
     buffers, rows that have not been uploaded poisoned with NaN: the state and the downloaded plane equal the oracle's
@@ -520,13 +519,12 @@ def test_host_loop_sweeps_on_cpu(simt, nsteps, has_in, has_out):
     ref = _state(Lx, Ly, 11)
     h0 = ref.height.copy()
     oc.time_loop(ref, p, nsteps=nsteps)
-    for early in (False, True):
-        for lazy in (False, True):
-            st = _state(Lx, Ly, 11)
-            if has_in:
-                st.height[...] = 7.0  # the device plane holds something else: the job starts from the host plane
-            out = np.full((Lx, Ly), np.nan)
-            _replay_host_loop(simt, ops, st, p, nsteps, h0 if has_in else None, out if has_out else None, early, lazy)
-            _same(st, ref, FIELDS + AUX)
-            if has_out:
-                assert np.array_equal(out, ref.height)
+    for early, lazy in ((False, False), (True, True)):
+        st = _state(Lx, Ly, 11)
+        if has_in:
+            st.height[...] = 7.0  # the device plane holds something else: the job starts from the host plane
+        out = np.full((Lx, Ly), np.nan)
+        _replay_host_loop(simt, ops, st, p, nsteps, h0 if has_in else None, out if has_out else None, early, lazy)
+        _same(st, ref, FIELDS + AUX)
+        if has_out:
+            assert np.array_equal(out, ref.height)
