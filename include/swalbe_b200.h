@@ -295,16 +295,58 @@ int swalbe_slippage_1d(double *slip, const double *height, const double *vel, do
 /* state.F .= -state.h∇p .- state.slip                        src/simulate.jl:110 */
 int swalbe_force_sum_1d(double *F, const double *hgradp, const double *slip, int L, void *stream);
 
-/* State_1D  src/initialize.jl:587-598 */
+/* force sum of the loops that carry a third term: F = -h∇p - slip - extra
+ * (run_gamma: extra = ∇γ, src/simulate.jl:544; thermal 1-D loops: extra = kbt) */
+int swalbe_force_sum3_1d(double *F, const double *hgradp, const double *slip, const double *extra, int L, void *stream);
+/* thermal!(fluc, height, kbt, mu, delta)                     src/forcing.jl:322-333 (State_thermal_1D: :335-336)
+ * counter-based normals keyed on (seed, step, site), like swalbe_thermal */
+int swalbe_thermal_1d(double *fluc, const double *height, double kbt, double mu, double delta, unsigned long long seed,
+                      unsigned long long step, int L, void *stream);
+/* inclination!(alpha::Float64, state::State_1D; t, tstart, tsmooth)   src/forcing.jl:379-389
+ * factor = 0.5 + 0.5*tanh((t - tstart)/tsmooth), evaluated by the caller.  F += h*alpha*factor */
+int swalbe_inclination_1d(double *F, const double *height, double alpha, double factor, int L, void *stream);
+/* ∇γ!(state)        src/forcing.jl:423-432   (height == NULL):  -3/2 * (γ[i-1] - γ[i+1]) / 2
+ * ∇γ!(state, sys)   src/forcing.jl:434-447   (height != NULL):  (2h² + 6δh + 3δ²)/(6h) * h/2 * (γ[i-1] - γ[i+1]) / 2 */
+int swalbe_gradgamma_1d(double *dgamma, const double *gamma, const double *height, double delta, int L, void *stream);
+/* filmpressure!(state::State_gamma_1D, sys; θ, n, m, hmin, hcrit, γ)   src/pressure.jl:284-315: power_broad, the surface
+ *   tension a scalar (gamma_field == NULL) or a per-site field (run_gamma passes γ = gamma::Vector, src/simulate.jl:541);
+ *   ftemp != NULL: the disjoining and the Laplace contribution are also stored in columns 1 and 2 of ftemp (L*3), as the
+ *   reference does (:307-312).
+ * filmpressure!(output::Vector, f, dgrad, rho, γ, θ, n, m, hmin, hcrit; Gamma)   src/pressure.jl:318-338 (active matter):
+ *   rho != NULL, tension γ + Gamma*rho.
+ * filmpressure!(state::Expanded_1D, sys; ...)   src/pressure.jl:258-282: gamma_field == rho == ftemp == NULL. */
+int swalbe_filmpressure_gamma_1d(double *pressure, const double *height, double gamma, const double *gamma_field,
+                                 const double *rho, double Gamma, double cospi_theta, const double *cospi_theta_field, int n,
+                                 int m, double hmin, double hcrit, double *ftemp, int L, void *stream);
+/* BGKandStream!(state::StateWithBound_1D, sys::SysConstWithBound_1D)   src/collide.jl:214-249: bounce-back walls.
+ * border0 / border1: the masks sys.border[1] / sys.border[2] written by obslist! (src/obstacle.jl:41-53) as device
+ * vectors; fbound: L*3, columns 1 and 2 receive the held-back populations.  fout == ftemp on return. */
+int swalbe_bgk_stream_bound_d1q3(double *fout, const double *feq, double *ftemp, double *fbound, const double *F,
+                                 const double *border0, const double *border1, double tau, int L, void *stream);
+/* update_rho!(rho, rho_int, height, dgrad, differentials; D, M)   src/forcing.jl:399-417
+ * differentials: L*4 (lap rho, grad rho, lap h, grad h are left there as in the reference) */
+int swalbe_update_rho_1d(double *rho, double *rho_int, const double *height, double *differentials, double D, double M, int L,
+                         void *stream);
+
+/* State_1D  src/initialize.jl:587-598 and the fields its expanded kinds add (:304-341); NULL where the kind has none */
 typedef struct swalbe_state_1d {
   double *fout, *ftemp, *feq;                     /* L*3 */
   double *height, *vel, *pressure, *F, *slip, *hgradp; /* L */
   double *dgrad;                                  /* L*2 scratch of the reference; unused, may be NULL */
+  double *gamma, *dgamma;                         /* L: State_gamma_1D / StateWithBound_1D γ, ∇γ */
+  double *kbt;                                    /* L: State_thermal_1D */
+  double *fbound;                                 /* L*3: StateWithBound_1D */
 } swalbe_state_1d;
 
+/* flags of swalbe_time_loop_1d on top of SWALBE_LOOP_SKIP_AUX: the loop body of run_gamma (src/simulate.jl:541-547) */
+#define SWALBE_LOOP_GAMMA_FIELD 8  /* filmpressure!(state, sys, γ = state.gamma): the tension is the per-site field */
+#define SWALBE_LOOP_MARANGONI 16   /* F = -h∇p - slip - state.dgamma */
+
 /* nsteps iterations of time_loop(sys::SysConst_1D, state::State_1D[, theta | Δh])   src/simulate.jl:98-157.
- * params: the Taumucs fields and pressure_variant / cospi_theta[_field] of swalbe_params (slip variant, inclination and
- * thermal fields are ignored); flags: SWALBE_LOOP_SKIP_AUX; logs: hmin / hmax per step (wetted is ignored).
+ * params: the Taumucs fields, pressure_variant / cospi_theta[_field] and use_inclination / incl_ax / incl_factor (the
+ * callback slot of time_loop(sys, state, inclination!, α), src/simulate.jl:159-179) of swalbe_params (slip variant and
+ * thermal fields are ignored); flags: SWALBE_LOOP_SKIP_AUX, SWALBE_LOOP_GAMMA_FIELD, SWALBE_LOOP_MARANGONI; logs:
+ * hmin / hmax per step (wetted and hsum are ignored).
  * Lattices that fit the shared memory of one CTA (L <= ~4800 at tau == 1) run all steps but the materialising one
  * inside a single persistent launch.  On return every field of the state holds what the reference's holds. */
 int swalbe_time_loop_1d(const swalbe_state_1d *state, const swalbe_params *params, int L, int nsteps, int flags,

@@ -132,3 +132,122 @@ def time_loop(st: State1D, p, nsteps=None, **kw):
         dh.append(float(st.height.max() - st.height.min()))
         step(st, p, **kw)
     return dh
+
+
+# ---- the expanded 1-D kinds: State_thermal_1D, State_gamma_1D, StateWithBound_1D (src/initialize.jl:304-341, :587-616) -----
+# Pinned against the reference's known answers: test/collide.jl:141-150 (bounce-back state at tau = 1 without forces ==
+# plain streaming), test/forcing.jl:165-204 (inclination, surface-tension gradient, constant-field rho update),
+# test/pressure.jl:56-131 (State_gamma_1D pressure, active-matter pressure).
+
+
+def inclination(F, height, alpha, t=1000, tstart=0, tsmooth=1):
+    """inclination!(α::Float64, state::State_1D; t, tstart, tsmooth)   src/forcing.jl:379-389"""
+    F[...] = F + height * alpha * (0.5 + 0.5 * np.tanh((t - tstart) / tsmooth))
+
+
+def gradgamma(out, gamma, height=None, delta=None):
+    """∇γ!(state)  src/forcing.jl:423-432  |  ∇γ!(state, sys)  :434-447"""
+    fip, fim = np.roll(gamma, 1), np.roll(gamma, -1)
+    if height is None:
+        out[...] = -3 / 2 * ((fip - fim) / 2.0)
+    else:
+        h = height
+        out[...] = (2 * (h * h) + 6 * delta * h + 3 * (delta * delta)) / (6 * h) * h / 2 * ((fip - fim) / 2.0)
+
+
+def filmpressure_gamma(output, f, gamma, cospi_theta, n, m, hmin, hcrit, rho=None, Gamma=0.0, ftemp=None):
+    """filmpressure!(state::State_gamma_1D, sys; γ)   src/pressure.jl:284-315 (γ scalar or length-L array, ftemp columns 1, 2
+    receive the two contributions) | filmpressure!(state::Expanded_1D, sys)  :258-282 (ftemp=None) |
+    filmpressure!(output::Vector, f, dgrad, rho, γ, θ, n, m, hmin, hcrit; Gamma)  :318-338 (rho given)"""
+    hip, him = np.roll(f, 1), np.roll(f, -1)
+    g = gamma if rho is None else gamma + Gamma * rho
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x = hmin / (f + hcrit)
+        disj = -g * (_kappa(cospi_theta, n, m, hmin) * (power_broad(x, n) - power_broad(x, m)))
+    lap = hip - 2 * f + him
+    if ftemp is not None:
+        ftemp[:, 1] = disj
+        ftemp[:, 2] = -g * lap
+    output[...] = disj - g * lap
+
+
+def obslist1D(obs):
+    """obslist1D(obs)   src/obstacle.jl:6-35 -> interior, [obsright, obsleft]"""
+    L = len(obs)
+    interior, obsleft, obsright = np.zeros(L), np.zeros(L), np.zeros(L)
+    for i in range(L):
+        ip, im = (i + 1) % L, (i - 1) % L
+        interior[i] = 1 if (obs[i] == 1 and obs[ip] == 1 and obs[im] == 1) else 0
+        obsleft[i] = 1 if (obs[i] == 1 and obs[im] == 1) else 0
+        obsright[i] = 1 if (obs[i] == 1 and obs[ip] == 1) else 0
+    return interior, [obsright, obsleft]
+
+
+def BGKandStream_bound(fout, feq, ftemp, fbound, F, border, tau):
+    """BGKandStream!(state::StateWithBound_1D, sys::SysConstWithBound_1D)   src/collide.jl:214-249"""
+    fe0, fe1, fe2 = viewdists_1D(feq)
+    ft0, ft1, ft2 = viewdists_1D(ftemp)
+    fo0, fo1, fo2 = viewdists_1D(fout)
+    _, fb1, fb2 = viewdists_1D(fbound)
+    omeg, it = 1 - 1 / tau, 1 / tau
+    fo0[...] = omeg * ft0 + it * fe0
+    fo1[...] = (omeg * ft1 + it * fe1) + 1 / 2 * F
+    fo2[...] = (omeg * ft2 + it * fe2) - 1 / 2 * F
+    fb1[...] = fo1 * border[0]
+    fb2[...] = fo2 * border[1]
+    fo1[...] = fo1 - fb1
+    fo2[...] = fo2 - fb2
+    ft0[...] = fo0
+    ft1[...] = np.roll(fo1, 1)
+    ft2[...] = np.roll(fo2, -1)
+    ft1[...] = ft1 + fb2
+    ft2[...] = ft2 + fb1
+    fout[...] = ftemp
+
+
+def update_rho(rho, rho_int, height, differentials, D=1.0, M=0.0):
+    """update_rho!(rho, rho_int, height, dgrad, differentials; D, M)   src/forcing.jl:399-417"""
+    lap_rho, grad_rho, lap_h, grad_h = (differentials[:, k] for k in range(4))
+    lap(lap_rho, rho)
+    grad(grad_rho, rho)
+    lap(lap_h, height)
+    grad(grad_h, height)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rho_int[...] = (D * lap_rho - M * (grad_rho * grad_rho + rho * lap_rho)
+                        - D * (grad_rho * grad_h / height + rho * (lap_h / height - (grad_h / height) * (grad_h / height))))
+    rho[...] = rho + rho_int
+
+
+def thermal_amplitude(height, kbt, mu, delta):
+    """the factor of the unit normals in thermal!(fluc, height, kᵦT, μ, δ)   src/forcing.jl:322-333"""
+    return np.sqrt(2 * kbt * mu * 6 * height / (2 * height * height + 6 * height * delta + 3 * delta * delta))
+
+
+def step_gamma(st: State1D, p, gamma, dgamma, cospi_theta=None, alpha=None, incl_factor=None):
+    """one iteration of the loop of run_gamma (src/simulate.jl:541-547); gamma / dgamma None: the plain loop; alpha: the
+    callback slot of time_loop(sys, state, inclination!, α)  :159-179"""
+    ct = cospi(p.theta) if cospi_theta is None else cospi_theta
+    if gamma is None:
+        filmpressure(st.pressure, st.height, st.dgrad, p.gamma, ct, p.n, p.m, p.hmin, p.hcrit, variant="power_broad")
+    else:
+        filmpressure_gamma(st.pressure, st.height, gamma, ct, p.n, p.m, p.hmin, p.hcrit, ftemp=st.ftemp)
+    hgradp(st.hgradp, st.pressure, st.height)
+    slippage(st.slip, st.height, st.vel, p.delta, p.mu)
+    st.F[...] = (-st.hgradp - st.slip) if dgamma is None else (-st.hgradp - st.slip - dgamma)
+    if alpha is not None:
+        st.F[...] = st.F + st.height * alpha * incl_factor
+    equilibrium(st.feq, st.height, st.vel, p.g)
+    BGKandStream(st.fout, st.feq, st.ftemp, st.F, p.tau)
+    moments(st.height, st.vel, st.fout)
+
+
+def step_bound(st: State1D, fbound, p, border, cospi_theta=None):
+    """one iteration of time_loop(sys::SysConstWithBound_1D, state::StateWithBound_1D)   src/simulate.jl:181-204"""
+    ct = cospi(p.theta) if cospi_theta is None else cospi_theta
+    filmpressure_gamma(st.pressure, st.height, p.gamma, ct, p.n, p.m, p.hmin, p.hcrit)
+    hgradp(st.hgradp, st.pressure, st.height)
+    slippage(st.slip, st.height, st.vel, p.delta, p.mu)
+    st.F[...] = -st.hgradp - st.slip
+    equilibrium(st.feq, st.height, st.vel, p.g)
+    BGKandStream_bound(st.fout, st.feq, st.ftemp, fbound, st.F, border, p.tau)
+    moments(st.height, st.vel, st.fout)

@@ -23,7 +23,8 @@ import numpy as np
 
 from . import _lib, one_d
 from ._lib import DomainError, SwalbeError  # noqa: F401
-from .one_d import CuState_1D, SysConst_1D  # noqa: F401
+from .one_d import (CuState_1D, CuState_gamma_1D, CuState_thermal_1D, CuStateWithBound_1D, SysConst_1D,  # noqa: F401
+                    SysConstWithBound_1D)
 
 __all__ = [
     "Taumucs", "SysConst", "Sys_const", "Sys", "CuState", "CuState_thermal", "Swalbe_state", "Field", "cospi",
@@ -233,10 +234,8 @@ def Sys(sysc: SysConst, device: str = "GPU", *legacy, T=float, kind: str = "simp
     """Sys(sysc, device; T, kind)  src/initialize.jl:491-572  -> CuState / CuState_thermal, and the older tuple form
     Sys(sysc, device, exotic::Bool, T)  src/initialize.jl:358-475  -> (fout, ftemp, feq, height, velx, vely, vsq,
     pressure, dgrad, Fx, Fy, slipx, slipy, h∇px, h∇py[, fthermalx, fthermaly]).  Only the "GPU" device string exists."""
-    if isinstance(sysc, SysConst_1D):  # Sys(sysc::Consts_1D; T, kind)  src/initialize.jl:587-616 (no device argument upstream)
-        if kind != "simple":
-            raise SwalbeError(f'Sys(::SysConst_1D; kind="{kind}"): only the "simple" 1-D state is built on the device')
-        return CuState_1D(sysc.L)
+    if isinstance(sysc, (SysConst_1D, SysConstWithBound_1D)):  # Sys(sysc::Consts_1D; T, kind)  src/initialize.jl:587-616
+        return one_d.Sys_1D(sysc, kind)                         # (no device argument upstream)
     if device != "GPU":
         raise SwalbeError(f'Sys(sys, "{device}"): swalbe_b200 implements the "GPU" path only (no CPU fallback)')
     if legacy:
@@ -267,7 +266,7 @@ def _dims(f: Field):
 
 def _is_1d(x) -> bool:
     """State_1D / Vector arguments: the operator belongs to the 1-D family (swalbe_b200.one_d)"""
-    return isinstance(x, one_d.CuState_1D) or (isinstance(x, Field) and len(x.shape) == 1)
+    return isinstance(x, one_d.LBM_state_1D) or (isinstance(x, Field) and len(x.shape) == 1)
 
 
 def equilibrium(*args):
@@ -275,8 +274,8 @@ def equilibrium(*args):
     if isinstance(args[0], CuState):
         st, sys_ = args
         return equilibrium(st.feq, st.height, st.velx, st.vely, st.vsq, sys_.param.g)
-    if isinstance(args[0], CuState_1D):  # equilibrium!(state::State_1D, sys)   src/equilibrium.jl:183-184
-        st, sys_ = args
+    if isinstance(args[0], one_d.LBM_state_1D):  # equilibrium!(state::State_1D | Expanded_1D, sys)   src/equilibrium.jl:183-190
+        st, sys_ = one_d.base(args[0]), args[1]
         return one_d.equilibrium(st.feq, st.height, st.vel, sys_.param.g)
     if len(args) == 4:                   # equilibrium!(feq, height, velocity, gravity)   :169
         return one_d.equilibrium(*args)
@@ -290,8 +289,10 @@ def BGKandStream(*args, τ=None, tau=None):
         st, sys_ = args
         t = τ if τ is not None else (tau if tau is not None else sys_.param.tau)
         return BGKandStream(st.fout, st.feq, st.ftemp, st.Fx, st.Fy, t)
-    if isinstance(args[0], CuState_1D):  # src/collide.jl:203-204
-        st, sys_ = args
+    if isinstance(args[0], CuStateWithBound_1D) and isinstance(args[1], SysConstWithBound_1D):  # bounce-back  src/collide.jl:214-249
+        return one_d.BGKandStream_bound(*args)
+    if isinstance(args[0], one_d.LBM_state_1D):  # src/collide.jl:203-211
+        st, sys_ = one_d.base(args[0]), args[1]
         return one_d.BGKandStream(st.fout, st.feq, st.ftemp, st.F, sys_.param.tau)
     if len(args) == 5:                   # BGKandStream!(fout, feq, ftemp, F::Vector, τ)   :179
         return one_d.BGKandStream(*args)
@@ -304,8 +305,8 @@ def moments(*args):
     if isinstance(args[0], CuState):
         st = args[0]
         return moments(st.height, st.velx, st.vely, st.fout)
-    if isinstance(args[0], CuState_1D):  # src/moments.jl:66
-        st = args[0]
+    if isinstance(args[0], one_d.LBM_state_1D):  # src/moments.jl:66-71
+        st = one_d.base(args[0])
         return one_d.moments(st.height, st.vel, st.fout)
     if len(args) == 3:                   # moments!(height::Vector, vel, fout)   :54
         return one_d.moments(*args)
@@ -332,18 +333,22 @@ def _theta_args(θ):
     return cospi(θ), None
 
 
-def filmpressure(*args, θ=None, γ=None, n=None, m=None, hmin=None, hcrit=None, theta=None, gamma=None):
+def filmpressure(*args, θ=None, γ=None, n=None, m=None, hmin=None, hcrit=None, theta=None, gamma=None, Gamma=0.0):
     """filmpressure!(output, f, dgrad, γ, θ, n, m, hmin, hcrit)        src/pressure.jl:72-115 (fast_93/fast_32)
     filmpressure!(state, sys; θ, γ, n, m, hmin, hcrit)                src/pressure.jl:119-155 (power_broad)
     filmpressure!(state::CuState_thermal, sys)                         src/pressure.jl:117 (array form, no keywords)"""
     θ = θ if θ is not None else theta
     γ = γ if γ is not None else gamma
+    if isinstance(args[0], one_d.Expanded_1D):  # src/pressure.jl:258-282 (Expanded_1D), :284-315 (State_gamma_1D)
+        return one_d.filmpressure_expanded(args[0], args[1], θ=θ, n=n, m=m, hmin=hmin, hcrit=hcrit, γ=γ)
     if isinstance(args[0], CuState_1D):  # filmpressure!(state::LBM_state_1D, sys; θ, n, m, hmin, hcrit, γ)   src/pressure.jl:230-256
         st, sys_ = args
         p = sys_.param
         return one_d.filmpressure(st.pressure, st.height, st.dgrad, p.gamma if γ is None else γ, p.theta if θ is None else θ,
                                   p.n if n is None else n, p.m if m is None else m, p.hmin if hmin is None else hmin,
                                   p.hcrit if hcrit is None else hcrit, variant=_lib.PRESSURE_POWER_BROAD)
+    if _is_1d(args[0]) and len(args) == 10:  # filmpressure!(output::Vector, f, dgrad, rho, γ, θ, n, m, hmin, hcrit; Gamma)   :318
+        return one_d.filmpressure_rho(*args, Gamma=Gamma)
     if _is_1d(args[0]):                  # filmpressure!(output::Vector, f, dgrad, γ, θ, n, m, hmin, hcrit)   :196
         return one_d.filmpressure(*args)
     if isinstance(args[0], CuState):
@@ -367,7 +372,7 @@ def filmpressure(*args, θ=None, γ=None, n=None, m=None, hmin=None, hcrit=None,
 
 def hgradp(st: CuState):
     """h∇p!(state)   src/forcing.jl:168-187"""
-    if isinstance(st, CuState_1D):
+    if isinstance(st, one_d.LBM_state_1D):
         return one_d.hgradp(st)
     _lib.call("swalbe_hgradp", st.hgradpx.ptr, st.hgradpy.ptr, st.pressure.ptr, st.height.ptr, st.Lx, st.Ly, _stream())
 
@@ -390,8 +395,8 @@ def laplacianf(out, f, γ):
 
 
 def _slip(variant, args):
-    if isinstance(args[0], CuState_1D):  # slippage!(state::LBM_state_1D, sys)
-        st, sys_ = args
+    if isinstance(args[0], one_d.LBM_state_1D):  # slippage!(state::LBM_state_1D | Expanded_1D, sys)   src/forcing.jl:73-83
+        st, sys_ = one_d.base(args[0]), args[1]
         return one_d.slippage(st.slip, st.height, st.vel, sys_.param.delta, sys_.param.mu)
     if _is_1d(args[0]):                  # slippage!(slip, height, vel, δ, μ)   src/forcing.jl:68-71
         return one_d.slippage(*args)
@@ -445,6 +450,12 @@ def thermal(*args, seed=None, step=None):
         _noise["calls"] += 1
     if seed is None:
         seed = _noise_seed()
+    if isinstance(args[0], CuState_thermal_1D):  # thermal!(state::State_thermal_1D, sys)   src/forcing.jl:335-336
+        st, sys_ = args
+        p = sys_.param
+        return one_d.thermal(st.kbt, st.basestate.height, p.kbt, p.mu, p.delta, seed, step)
+    if len(args) == 5:                           # thermal!(fluc, height, kᵦT, μ, δ)   src/forcing.jl:322-333
+        return one_d.thermal(*args, seed, step)
     if isinstance(args[0], CuState):
         st, sys_ = args
         p = sys_.param
@@ -456,6 +467,8 @@ def thermal(*args, seed=None, step=None):
 
 def inclination(α, st: CuState, t=1000, tstart=0, tsmooth=1):
     """inclination!(α, state; t, tstart, tsmooth)   src/forcing.jl:363-368"""
+    if isinstance(st, one_d.LBM_state_1D):  # inclination!(α::Float64, state::State_1D | Expanded_1D)   src/forcing.jl:379-389
+        return one_d.inclination(α, st, t=t, tstart=tstart, tsmooth=tsmooth)
     factor = 0.5 + 0.5 * math.tanh((t - tstart) / tsmooth)
     _lib.call("swalbe_inclination", st.Fx.ptr, st.Fy.ptr, st.height.ptr, float(α[0]), float(α[1]), factor, st.Lx, st.Ly,
               _stream())
@@ -464,7 +477,7 @@ def inclination(α, st: CuState, t=1000, tstart=0, tsmooth=1):
 def update(st: CuState):
     """The inline force sum of the drivers, `state.Fx .= -state.h∇px .- state.slipx` (src/simulate.jl:18-19);
     for thermal states `... .- state.kbtx` (scripts/Rivulet_stability.jl:123-124).  north_star calls it update!."""
-    if isinstance(st, CuState_1D):
+    if isinstance(st, one_d.LBM_state_1D):
         return one_d.update(st)
     kx, ky = (st.kbtx.ptr, st.kbty.ptr) if st.thermal else (None, None)
     _lib.call("swalbe_force_sum", st.Fx.ptr, st.Fy.ptr, st.hgradpx.ptr, st.hgradpy.ptr, st.slipx.ptr, st.slipy.ptr, kx, ky,
@@ -748,7 +761,7 @@ def time_loop(sys_: SysConst, st: CuState, *extra, verbose=False, chunk=None, la
     ``host_in`` / ``host_out``: host planes (see fused_steps) the first chunk starts from / the last chunk leaves the final
     height in -- `state.height .= CUDA.adapt(CuArray, h)` before and `Array(state.height)` after the loop, with the
     copies hidden behind the first and last steps."""
-    if isinstance(sys_, SysConst_1D):
+    if isinstance(sys_, (SysConst_1D, SysConstWithBound_1D)):
         return one_d.time_loop(sys_, st, *extra, verbose=verbose)
     p = sys_.param
     θ, dh, cb, measure = None, None, None, None
@@ -979,8 +992,11 @@ def run_dropletpatterned(sys_: SysConst, device: str, radius=20, θ0=1 / 6, cent
     return st.height
 
 
-def run_dropletforced(sys_: SysConst, device: str, radius=20, θ0=1 / 6, center=None, fx=0.0, fy=0.0, verbos=True):
+def run_dropletforced(sys_: SysConst, device: str = "GPU", radius=20, θ0=1 / 6, center=None, fx=0.0, fy=0.0, verbos=True,
+                      f=None):
     """run_dropletforced  src/simulate.jl:462-484"""
+    if isinstance(sys_, SysConst_1D):  # run_dropletforced(sys::SysConst_1D; radius, θ₀, center, θₛ, f)   src/simulate.jl:486-503
+        return one_d.run_dropletforced(sys_, radius=radius, θ0=θ0, center=center, f=fx if f is None else f, verbos=verbos)
     bodyforce = [fx, fy]
     print("Simulating a sliding droplet in two dimensions")
     center = center or (sys_.Lx // 2, sys_.Ly // 2)
@@ -992,6 +1008,8 @@ def run_dropletforced(sys_: SysConst, device: str, radius=20, θ0=1 / 6, center=
     return st.height, st.velx, st.vely
 
 
+gradgamma, update_rho, obslist, run_gamma, two_droplets = (one_d.gradgamma, one_d.update_rho, one_d.obslist, one_d.run_gamma,
+                                                           one_d.two_droplets)
 from .io import dump_height_slab, load_height_slab, restart_from_height, save_heights  # noqa: E402
 
 JULIA_NAMES = {
@@ -1004,5 +1022,6 @@ JULIA_NAMES = {
     "SysConst": SysConst, "Sys_const": Sys_const, "Taumucs": Taumucs, "CuState": CuState,
     "CuState_thermal": CuState_thermal, "Swalbe_state": Swalbe_state, "viewdists": viewdists,
     "viewneighbors": viewneighbors, "singledroplet": singledroplet, "torus": torus, "rivulet": rivulet,
-    "randinterface!": randinterface, "circshift!": circshift, "move_substrate!": move_substrate, "restart_from_height": restart_from_height, "power_broad": power_broad, "fast_93": fast_93, "fast_32": fast_32,
+    "∇γ!": one_d.gradgamma, "update_rho!": one_d.update_rho, "obslist!": one_d.obslist, "run_gamma": one_d.run_gamma,
+    "two_droplets": one_d.two_droplets, "randinterface!": randinterface, "circshift!": circshift, "move_substrate!": move_substrate, "restart_from_height": restart_from_height, "power_broad": power_broad, "fast_93": fast_93, "fast_32": fast_32,
 }

@@ -16,6 +16,7 @@ OK, ERR_DOMAIN, ERR_EXTENT, ERR_CUDA, ERR_NCCL, ERR_ARG = range(6)
 PRESSURE_POWER_BROAD, PRESSURE_FAST = 0, 1
 SLIP_STANDARD, SLIP_HCRIT, SLIP_RING_RIV = 0, 1, 2
 LOOP_DEFAULT, LOOP_LAZY_POPULATIONS, LOOP_SKIP_AUX, LOOP_MOMENTS_CONSISTENT = 0, 1, 2, 4
+LOOP_GAMMA_FIELD, LOOP_MARANGONI = 8, 16  # swalbe_time_loop_1d
 NCCL_UNIQUE_ID_BYTES = 128
 
 
@@ -49,7 +50,8 @@ class CParams(C.Structure):
 
 class CState1D(C.Structure):
     """struct swalbe_state_1d"""
-    _fields_ = [(n, _vp) for n in ("fout", "ftemp", "feq", "height", "vel", "pressure", "F", "slip", "hgradp", "dgrad")]
+    _fields_ = [(n, _vp) for n in ("fout", "ftemp", "feq", "height", "vel", "pressure", "F", "slip", "hgradp", "dgrad",
+                                   "gamma", "dgamma", "kbt", "fbound")]
 
 
 class CLogs(C.Structure):
@@ -97,6 +99,13 @@ SIGNATURES = {
     "swalbe_lap_1d": [_vp, _vp, _i, _vp],
     "swalbe_slippage_1d": [_vp, _vp, _vp, _d, _d, _i, _vp],
     "swalbe_force_sum_1d": [_vp, _vp, _vp, _i, _vp],
+    "swalbe_force_sum3_1d": [_vp, _vp, _vp, _vp, _i, _vp],
+    "swalbe_thermal_1d": [_vp, _vp, _d, _d, _d, _u64, _u64, _i, _vp],
+    "swalbe_inclination_1d": [_vp, _vp, _d, _d, _i, _vp],
+    "swalbe_gradgamma_1d": [_vp, _vp, _vp, _d, _i, _vp],
+    "swalbe_filmpressure_gamma_1d": [_vp, _vp, _d, _vp, _vp, _d, _d, _vp, _i, _i, _d, _d, _vp, _i, _vp],
+    "swalbe_bgk_stream_bound_d1q3": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp],
+    "swalbe_update_rho_1d": [_vp, _vp, _vp, _vp, _d, _d, _i, _vp],
     "swalbe_time_loop_1d": [C.POINTER(CState1D), C.POINTER(CParams), _i, _i, _i, C.POINTER(CLogs), _vp],
     "swalbe_dist_unique_id": [_vp],
     "swalbe_dist_create": [C.POINTER(_vp), _vp, _i, _i, _i, _i, C.POINTER(CParams)],

@@ -19,6 +19,12 @@ struct Consts1D {
   double omega, invtau;
   int tau1, array_form;  // array form: fast_93 / fast_32 (src/pressure.jl:196-227); state form: power_broad (:230-256)
   const double *ct_field;
+  // State_gamma_1D loops (run_gamma, src/simulate.jl:518-560): surface tension per site in the pressure, and a force
+  // subtracted after the slip (the surface-tension gradient);  time_loop(sys, state, inclination!, α) (:159-179): body force
+  const double *gamma_field;  // NULL: the scalar pc.gamma
+  const double *force_extra;  // NULL: none
+  int use_incl;
+  double incl_a, incl_factor;
 };
 
 __device__ __forceinline__ int wrap1(int i, int L) { return i < 0 ? i + L : (i >= L ? i - L : i); }
@@ -29,7 +35,15 @@ __device__ __forceinline__ double pressure_1d(const double *h, int j, int L, con
   const double x = div_exact(c.pc.hmin, hc + c.pc.hcrit);
   const double pw = disjoining_powers(x, c.pc.pmode, c.pc.n, c.pc.m);
   const double kappa = c.ct_field ? kappa_from_field(c.ct_field[j], c.pc) : c.pc.kappa;
-  return (-c.pc.gamma * (kappa * pw)) - c.pc.gamma * ((hip - 2.0 * hc) + him);
+  const double gam = c.gamma_field ? c.gamma_field[j] : c.pc.gamma;  // filmpressure!(state::State_gamma_1D, sys; γ = field)  :284-315
+  return (-gam * (kappa * pw)) - gam * ((hip - 2.0 * hc) + him);
+}
+// F = -h∇p - slip [- ∇γ] [+ h α s(t)]   src/simulate.jl:112, :544 (run_gamma), src/forcing.jl:379-383 (inclination!)
+__device__ __forceinline__ double force_1d(double hgp, double slip, double hc, int j, const Consts1D &c) {
+  double F = (-hgp) - slip;
+  if (c.force_extra) F = F - c.force_extra[j];
+  if (c.use_incl) F = F + (hc * c.incl_a) * c.incl_factor;
+  return F;
 }
 
 struct Site1D {
@@ -46,7 +60,7 @@ __device__ __forceinline__ void collide_1d(const double *h, const double *v, con
   s.hgp = (hc * -0.5) * (pip - pim);                                        // src/forcing.jl:189-198
   const double den = ((2.0 * (hc * hc)) + c.sc.delta6 * hc) + c.sc.delta3s;  // src/forcing.jl:68-71
   s.slip = div_exact((c.sc.mu6 * hc) * vc, den);
-  s.F = (-s.hgp) - s.slip;                                                  // src/simulate.jl:112
+  s.F = force_1d(s.hgp, s.slip, hc, j, c);                                  // src/simulate.jl:112
   const double vv = vc * vc;                                                // src/equilibrium.jl:173-178
   s.fe[0] = hc * ((1.0 - c.g05 * hc) - vv);
   s.fe[1] = hc * ((c.g025 * hc + 0.5 * vc) + 0.5 * vv);
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(T1D, 1) k_loop_1d(const __grid_constant__ Loop
       const double hc = sh[i], vc = sv[i];
       const double hgp = (hc * -0.5) * (sp[wrap1(i - 1, L)] - sp[wrap1(i + 1, L)]);
       const double den = ((2.0 * (hc * hc)) + c.sc.delta6 * hc) + c.sc.delta3s;
-      const double F = (-hgp) - div_exact((c.sc.mu6 * hc) * vc, den);
+      const double F = force_1d(hgp, div_exact((c.sc.mu6 * hc) * vc, den), hc, i, c);
       const double vv = vc * vc, hf = 0.5 * F;
       const double fe0 = hc * ((1.0 - c.g05 * hc) - vv);
       const double fe1 = hc * ((c.g025 * hc + 0.5 * vc) + 0.5 * vv);
@@ -270,6 +284,92 @@ __global__ void k_init_logs_1d(double *mn, double *mx, int n) {
   if (i < n) { mn[i] = INFINITY; mx[i] = -INFINITY; }
 }
 
+// thermal!(fluc, height, kbt, mu, delta)   src/forcing.jl:322-333: one normal per site from the generator of the 2-D
+// operator (counter = (site, step), the second normal of the pair is dropped)
+__global__ void k_thermal_1d(double *fluc, const double *h, ThermalConsts tc, PhiloxKey key, unsigned long long step, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  double a, b;
+  thermal_pair(h[i], tc, key, step, L, 0ll, i, a, b);
+  fluc[i] = a;
+}
+__global__ void k_incl_1d(double *F, const double *h, double alpha, double factor, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) F[i] = F[i] + (h[i] * alpha) * factor;  // src/forcing.jl:379-383
+}
+// ∇γ!(state)        src/forcing.jl:423-432:  -3/2 * ((γ[i-1] - γ[i+1]) / 2)
+// ∇γ!(state, sys)   src/forcing.jl:434-447:  (2h² + 6δh + 3δ²) / (6h) * h / 2 * ((γ[i-1] - γ[i+1]) / 2)
+__global__ void k_gradgamma_1d(double *out, const double *gam, const double *h, double delta6, double delta3s, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const double d = (gam[wrap1(i - 1, L)] - gam[wrap1(i + 1, L)]) / 2.0;
+  if (!h) { out[i] = -1.5 * d; return; }
+  const double hc = h[i];
+  out[i] = ((((2.0 * (hc * hc) + delta6 * hc) + delta3s) / (6.0 * hc)) * hc / 2.0) * d;
+}
+// filmpressure!(state::State_gamma_1D, sys; γ)   src/pressure.jl:284-315 (power_broad; γ scalar or per site; the two
+// contributions are also parked in columns 1 and 2 of ftemp) and the active-matter array form
+// filmpressure!(output, f, dgrad, rho, γ, θ, n, m, hmin, hcrit; Gamma)   :318-338 with the tension γ + Gamma*rho
+__global__ void k_pressure_gamma_1d(double *p, const double *h, Consts1D c, double gamma, const double *rho, double Gamma,
+                                    double *ft1, double *ft2, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const double hc = h[i], hip = h[wrap1(i - 1, L)], him = h[wrap1(i + 1, L)];
+  const double x = div_exact(c.pc.hmin, hc + c.pc.hcrit);
+  const double pw = disjoining_powers(x, c.pc.pmode, c.pc.n, c.pc.m);
+  const double kappa = c.ct_field ? kappa_from_field(c.ct_field[i], c.pc) : c.pc.kappa;
+  double gam = c.gamma_field ? c.gamma_field[i] : gamma;
+  if (rho) gam = gam + Gamma * rho[i];
+  const double disj = -gam * (kappa * pw);
+  const double lap = rho ? ((hip - 2.0 * hc) + him) : ((hip - 2.0 * hc) + him);
+  if (ft1) { ft1[i] = disj; ft2[i] = -gam * lap; }
+  p[i] = disj - gam * lap;
+}
+// BGKandStream!(state::StateWithBound_1D, sys::SysConstWithBound_1D)   src/collide.jl:214-249: collision, the populations
+// that would enter a wall node (border masks) are held back, streamed, and returned to the opposite direction
+__global__ void k_bgk_bound_1d(double *fout, const double *feq, double *ftemp_out, const double *ftemp, double *fbound,
+                               const double *F, const double *b0, const double *b1, double omega, double invtau, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const size_t N = (size_t)L;
+  auto post1 = [&](int j) { return (omega * ftemp[N + j] + invtau * feq[N + j]) + 0.5 * F[j]; };
+  auto post2 = [&](int j) { return (omega * ftemp[2 * N + j] + invtau * feq[2 * N + j]) - 0.5 * F[j]; };
+  const int im = wrap1(i - 1, L), ip = wrap1(i + 1, L);
+  const double fo1 = post1(i), fo2 = post2(i);
+  const double fb1 = fo1 * b0[i], fb2 = fo2 * b1[i];
+  fbound[N + i] = fb1; fbound[2 * N + i] = fb2;
+  const double fo1m = post1(im), fo2p = post2(ip);
+  const double s1 = fo1m - fo1m * b0[im];  // (fo1 - fb1) streamed from i-1
+  const double s2 = fo2p - fo2p * b1[ip];  // (fo2 - fb2) streamed from i+1
+  const double n0 = omega * ftemp[i] + invtau * feq[i];
+  const double n1 = s1 + fb2, n2 = s2 + fb1;
+  fout[i] = n0; fout[N + i] = n1; fout[2 * N + i] = n2;
+  ftemp_out[i] = n0; ftemp_out[N + i] = n1; ftemp_out[2 * N + i] = n2;
+}
+// update_rho!(rho, rho_int, height, dgrad, differentials; D, M)   src/forcing.jl:399-417
+__global__ void k_update_rho_1d(double *rho_out, double *rho_int, const double *rho, const double *h, double *diff, double D,
+                                double M, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const size_t N = (size_t)L;
+  const int im = wrap1(i - 1, L), ip = wrap1(i + 1, L);
+  const double r = rho[i], hc = h[i];
+  const double lap_rho = (rho[im] - 2.0 * r) + rho[ip];   // ∇²f!  src/differences.jl:77-85
+  const double grad_rho = -0.5 * (rho[im] - rho[ip]);      // ∇f!   src/differences.jl:220-230
+  const double lap_h = (h[im] - 2.0 * hc) + h[ip];
+  const double grad_h = -0.5 * (h[im] - h[ip]);
+  diff[i] = lap_rho; diff[N + i] = grad_rho; diff[2 * N + i] = lap_h; diff[3 * N + i] = grad_h;
+  const double gh = grad_h / hc;
+  const double ri = (D * lap_rho - M * (grad_rho * grad_rho + r * lap_rho)) -
+                    D * ((grad_rho * grad_h) / hc + r * (lap_h / hc - gh * gh));
+  rho_int[i] = ri;
+  rho_out[i] = r + ri;
+}
+__global__ void k_force3_1d(double *F, const double *hgp, const double *slip, const double *extra, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) F[i] = ((-hgp[i]) - slip[i]) - extra[i];
+}
+
 int check_len(int L) {
   if (L < 1) return set_error(SWALBE_ERR_EXTENT, "L = %d: the lattice needs at least one site", L);
   return 0;
@@ -290,6 +390,8 @@ int fill_consts_1d(Consts1D &c, const swalbe_params &p) {
   c.invtau = it; c.omega = om; c.tau1 = p.tau == 1.0;
   c.array_form = p.pressure_variant == SWALBE_PRESSURE_FAST;
   c.ct_field = p.cospi_theta_field;
+  c.gamma_field = nullptr; c.force_extra = nullptr;
+  c.use_incl = p.use_inclination; c.incl_a = p.incl_ax; c.incl_factor = p.incl_factor;
   return 0;
 }
 
@@ -372,6 +474,89 @@ int swalbe_force_sum_1d(double *F, const double *hgradp, const double *slip, int
   return 0;
 }
 
+int swalbe_force_sum3_1d(double *F, const double *hgradp, const double *slip, const double *extra, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!F || !hgradp || !slip || !extra) return set_error(SWALBE_ERR_ARG, "swalbe_force_sum3_1d: NULL argument");
+  k_force3_1d<<<GRID1(L)>>>(F, hgradp, slip, extra, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_thermal_1d(double *fluc, const double *height, double kbt, double mu, double delta, unsigned long long seed,
+                      unsigned long long step, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!fluc || !height) return set_error(SWALBE_ERR_ARG, "swalbe_thermal_1d: NULL argument");
+  k_thermal_1d<<<GRID1(L)>>>(fluc, height, make_thermal(kbt, mu, delta), make_philox_key(seed), step, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_inclination_1d(double *F, const double *height, double alpha, double factor, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!F || !height) return set_error(SWALBE_ERR_ARG, "swalbe_inclination_1d: NULL argument");
+  k_incl_1d<<<GRID1(L)>>>(F, height, alpha, factor, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_gradgamma_1d(double *dgamma, const double *gamma, const double *height, double delta, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!dgamma || !gamma) return set_error(SWALBE_ERR_ARG, "swalbe_gradgamma_1d: NULL argument");
+  volatile double d6 = 6.0 * delta, d2 = delta * delta;
+  volatile double d3s = 3.0 * d2;
+  k_gradgamma_1d<<<GRID1(L)>>>(dgamma, gamma, height, d6, d3s, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_filmpressure_gamma_1d(double *pressure, const double *height, double gamma, const double *gamma_field,
+                                 const double *rho, double Gamma, double cospi_theta, const double *cospi_theta_field, int n,
+                                 int m, double hmin, double hcrit, double *ftemp, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!pressure || !height) return set_error(SWALBE_ERR_ARG, "swalbe_filmpressure_gamma_1d: NULL argument");
+  swalbe_params p = {};
+  p.tau = 1.0; p.gamma = gamma; p.cospi_theta = cospi_theta; p.cospi_theta_field = cospi_theta_field;
+  p.n = n; p.m = m; p.hmin = hmin; p.hcrit = hcrit; p.pressure_variant = SWALBE_PRESSURE_POWER_BROAD;
+  Consts1D c = {};
+  if (int e = fill_consts_1d(c, p)) return e;
+  c.gamma_field = gamma_field;
+  k_pressure_gamma_1d<<<GRID1(L)>>>(pressure, height, c, gamma, rho, Gamma, ftemp ? ftemp + (size_t)L : nullptr,
+                                    ftemp ? ftemp + 2 * (size_t)L : nullptr, L);
+  SW_LAUNCH_CHECK();
+  return 0;
+}
+
+int swalbe_bgk_stream_bound_d1q3(double *fout, const double *feq, double *ftemp, double *fbound, const double *F,
+                                 const double *border0, const double *border1, double tau, int L, void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!fout || !feq || !ftemp || !fbound || !F || !border0 || !border1)
+    return set_error(SWALBE_ERR_ARG, "swalbe_bgk_stream_bound_d1q3: NULL argument");
+  if (!(tau > 0.0)) return set_error(SWALBE_ERR_ARG, "tau must be positive");
+  volatile double it = 1.0 / tau;
+  volatile double om = 1.0 - it;
+  // ftemp is read at i-1, i, i+1 and written at i: the new populations go to fout first, then fout -> ftemp
+  double *tmp = nullptr;
+  SW_CUDA(cudaMallocAsync((void **)&tmp, 3 * (size_t)L * sizeof(double), (cudaStream_t)stream));
+  k_bgk_bound_1d<<<GRID1(L)>>>(fout, feq, tmp, ftemp, fbound, F, border0, border1, om, it, L);
+  SW_LAUNCH_CHECK();
+  SW_CUDA(cudaMemcpyAsync(ftemp, tmp, 3 * (size_t)L * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  SW_CUDA(cudaFreeAsync(tmp, (cudaStream_t)stream));
+  return 0;
+}
+
+int swalbe_update_rho_1d(double *rho, double *rho_int, const double *height, double *differentials, double D, double M, int L,
+                         void *stream) {
+  if (int e = check_len(L)) return e;
+  if (!rho || !rho_int || !height || !differentials) return set_error(SWALBE_ERR_ARG, "swalbe_update_rho_1d: NULL argument");
+  double *tmp = nullptr;  // rho is read at i-1, i, i+1 and written at i
+  SW_CUDA(cudaMallocAsync((void **)&tmp, (size_t)L * sizeof(double), (cudaStream_t)stream));
+  k_update_rho_1d<<<GRID1(L)>>>(tmp, rho_int, rho, height, differentials, D, M, L);
+  SW_LAUNCH_CHECK();
+  SW_CUDA(cudaMemcpyAsync(rho, tmp, (size_t)L * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  SW_CUDA(cudaFreeAsync(tmp, (cudaStream_t)stream));
+  return 0;
+}
+
 int swalbe_time_loop_1d(const swalbe_state_1d *st, const swalbe_params *prm, int L, int nsteps, int flags,
                         const swalbe_loop_logs *logs, void *stream_) {
   if (!st || !prm) return set_error(SWALBE_ERR_ARG, "swalbe_time_loop_1d: NULL state/params");
@@ -384,6 +569,17 @@ int swalbe_time_loop_1d(const swalbe_state_1d *st, const swalbe_params *prm, int
   cudaStream_t stream = (cudaStream_t)stream_;
   Consts1D c = {};
   if (int e = fill_consts_1d(c, *prm)) return e;
+  if (flags & SWALBE_LOOP_GAMMA_FIELD) {
+    if (!st->gamma) return set_error(SWALBE_ERR_ARG, "SWALBE_LOOP_GAMMA_FIELD needs state.gamma");
+    // the reference's State_gamma_1D pressure parks its two contributions in ftemp ("fine as long as tau = 1",
+    // src/pressure.jl:307-312): at tau != 1 that changes the collision, which the fused loop does not imitate
+    if (!c.tau1) return set_error(SWALBE_ERR_ARG, "SWALBE_LOOP_GAMMA_FIELD requires tau == 1 (src/pressure.jl:307)");
+    c.gamma_field = st->gamma;
+  }
+  if (flags & SWALBE_LOOP_MARANGONI) {
+    if (!st->dgamma) return set_error(SWALBE_ERR_ARG, "SWALBE_LOOP_MARANGONI needs state.dgamma");
+    c.force_extra = st->dgamma;
+  }
   const bool skip_aux = (flags & SWALBE_LOOP_SKIP_AUX) != 0;
   const bool log_mm = logs && logs->hmin && logs->hmax;
   if (log_mm) {

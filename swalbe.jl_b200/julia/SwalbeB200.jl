@@ -651,9 +651,70 @@ struct CState1D      # struct swalbe_state_1d
     fout::CuPtr{Float64}; ftemp::CuPtr{Float64}; feq::CuPtr{Float64}
     height::CuPtr{Float64}; vel::CuPtr{Float64}; pressure::CuPtr{Float64}; F::CuPtr{Float64}; slip::CuPtr{Float64}
     hgradp::CuPtr{Float64}; dgrad::CuPtr{Float64}
+    gamma::CuPtr{Float64}; dgamma::CuPtr{Float64}; kbt::CuPtr{Float64}; fbound::CuPtr{Float64}
 end
-cstate(s::CuState_1D) = CState1D(pointer(s.fout), pointer(s.ftemp), pointer(s.feq), pointer(s.height), pointer(s.vel),
-    pointer(s.pressure), pointer(s.F), pointer(s.slip), pointer(s.h∇p), pointer(s.dgrad))
+cstate(s::CuState_1D; γ = NULLF, ∇γ = NULLF, kbt = NULLF, fbound = NULLF) = CState1D(pointer(s.fout), pointer(s.ftemp),
+    pointer(s.feq), pointer(s.height), pointer(s.vel), pointer(s.pressure), pointer(s.F), pointer(s.slip), pointer(s.h∇p),
+    pointer(s.dgrad), γ, ∇γ, kbt, fbound)
+
+# ---- the expanded 1-D kinds (State_thermal_1D, State_gamma_1D, StateWithBound_1D; src/initialize.jl:304-341) on device
+# vectors.  Upstream these states hold `Vector`s; a device twin only needs the same field names, so the array forms below
+# take the CuArrays directly and a script builds its state as a NamedTuple or its own struct.
+const LOOP_GAMMA_FIELD = Cint(8)
+const LOOP_MARANGONI = Cint(16)
+
+"state.F .= -state.h∇p .- state.slip .- extra  (run_gamma, src/simulate.jl:544: extra = ∇γ; thermal loops: extra = kbt)"
+function force_sum3!(F::CuArray{Float64,1}, h∇p::CuArray{Float64,1}, slip::CuArray{Float64,1}, extra::CuArray{Float64,1})
+    check(ccall((:swalbe_force_sum3_1d, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Ptr{Cvoid}),
+        F, h∇p, slip, extra, length(F), stream()))
+end
+
+function Swalbe.thermal!(fluc::CuArray{Float64,1}, height::CuArray{Float64,1}, kᵦT, μ, δ; seed = nothing, step = nothing)  # src/forcing.jl:322
+    check(ccall((:swalbe_thermal_1d, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cdouble, Cdouble, Culonglong, Culonglong, Cint, Ptr{Cvoid}),
+        fluc, height, kᵦT, μ, δ, seed === nothing ? default_seed() : UInt64(seed), step === nothing ? next_noise_step() : UInt64(step),
+        length(height), stream()))
+end
+
+"inclination!(α::Float64, state::State_1D; t, tstart, tsmooth)  src/forcing.jl:379-389 on device vectors"
+function inclination1d!(F::CuArray{Float64,1}, height::CuArray{Float64,1}, α::Float64; t = 1000, tstart = 0, tsmooth = 1)
+    check(ccall((:swalbe_inclination_1d, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cdouble, Cint, Ptr{Cvoid}),
+        F, height, α, 0.5 + 0.5 * tanh((t - tstart) / tsmooth), length(F), stream()))
+end
+
+"∇γ!(state)  src/forcing.jl:423-432 (height === nothing)  |  ∇γ!(state, sys)  :434-447 (height, δ given)"
+function ∇γ!(dγ::CuArray{Float64,1}, γ::CuArray{Float64,1}; height::Union{Nothing,CuArray{Float64,1}} = nothing, δ = 0.0)
+    check(ccall((:swalbe_gradgamma_1d, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cint, Ptr{Cvoid}),
+        dγ, γ, height === nothing ? NULLF : pointer(height), δ, length(γ), stream()))
+end
+
+"""
+filmpressure!(state::State_gamma_1D, sys; γ)  src/pressure.jl:284-315 (γ scalar or device vector; `ftemp`: the L x 3
+populations that receive the two contributions, or nothing) and the active-matter array form with `rho`, `Gamma` (:318-338)
+"""
+function filmpressure_gamma!(output::CuArray{Float64,1}, f::CuArray{Float64,1}, γ, θ, n, m, hmin, hcrit;
+                             rho::Union{Nothing,CuArray{Float64,1}} = nothing, Gamma = 0.0,
+                             ftemp::Union{Nothing,CuArray{Float64,2}} = nothing)
+    ct, ctf, keep = theta_args(θ)
+    GC.@preserve keep check(ccall((:swalbe_filmpressure_gamma_1d, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cdouble, CuPtr{Float64}, Cint, Cint,
+         Cdouble, Cdouble, CuPtr{Float64}, Cint, Ptr{Cvoid}),
+        output, f, γ isa Number ? γ : 0.0, γ isa Number ? NULLF : pointer(γ), rho === nothing ? NULLF : pointer(rho), Gamma, ct, ctf,
+        n, m, hmin, hcrit, ftemp === nothing ? NULLF : pointer(ftemp), length(f), stream()))
+end
+
+"BGKandStream!(state::StateWithBound_1D, sys::SysConstWithBound_1D)  src/collide.jl:214-249; border = the device copies of sys.border"
+function BGKandStream_bound!(fout::CuArray{Float64,2}, feq, ftemp, fbound, F::CuArray{Float64,1}, border1, border2, τ)
+    check(ccall((:swalbe_bgk_stream_bound_d1q3, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cint,
+         Ptr{Cvoid}), fout, feq, ftemp, fbound, F, border1, border2, τ, length(F), stream()))
+end
+
+function Swalbe.update_rho!(rho::CuArray{Float64,1}, rho_int, height, dgrad, differentials; D = 1.0, M = 0.0)  # src/forcing.jl:399
+    check(ccall((:swalbe_update_rho_1d, lib), Cint,
+        (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cdouble, Cint, Ptr{Cvoid}),
+        rho, rho_int, height, differentials, D, M, length(rho), stream()))
+end
 
 function Swalbe.equilibrium!(feq::CuArray{Float64,2}, height::CuArray{Float64,1}, velocity, gravity)   # src/equilibrium.jl:169
     check(ccall((:swalbe_equilibrium_d1q3, lib), Cint, (CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cint, Ptr{Cvoid}),
@@ -713,11 +774,16 @@ function update!(s::CuState_1D)
 end
 
 """`nsteps` iterations of the 1-D loop body (src/simulate.jl:107-114) through swalbe_time_loop_1d."""
+# `incl = (α, factor)`: the inclination! callback slot of time_loop(sys, state, f, measure) (src/simulate.jl:159-179);
+# `γ`, `∇γ` (device vectors): the loop body of run_gamma (:541-547) -- per-site tension in the pressure, F = -h∇p - slip - ∇γ
 function fused_steps!(state::CuState_1D, sys::Swalbe.SysConst_1D, nsteps::Integer; θ = sys.param.θ,
-                      logs::Union{Nothing,CLogs} = nothing, flags = 0)
+                      logs::Union{Nothing,CLogs} = nothing, flags = 0, incl = nothing,
+                      γ::Union{Nothing,CuArray{Float64,1}} = nothing, ∇γ::Union{Nothing,CuArray{Float64,1}} = nothing)
     θargs = theta_args(θ)
-    prm = Ref(cparams(sys.param, θargs, PRESSURE_POWER_BROAD, SLIP[:standard], nothing, nothing))
-    st = Ref(cstate(state))
+    prm = Ref(cparams(sys.param, θargs, PRESSURE_POWER_BROAD, SLIP[:standard],
+                      incl === nothing ? nothing : ((incl[1], 0.0), incl[2]), nothing))
+    st = Ref(cstate(state; γ = γ === nothing ? NULLF : pointer(γ), ∇γ = ∇γ === nothing ? NULLF : pointer(∇γ)))
+    flags = Cint(flags) | (γ === nothing ? Cint(0) : LOOP_GAMMA_FIELD) | (∇γ === nothing ? Cint(0) : LOOP_MARANGONI)
     keep = θargs[3]
     if logs === nothing
         GC.@preserve keep prm st check(ccall((:swalbe_time_loop_1d, lib), Cint,

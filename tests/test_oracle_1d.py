@@ -99,8 +99,79 @@ def case_hgradp_1d(B):  # test/forcing.jl:125-138: pressure = height = 1..30 -> 
     assert np.array_equal(out, sol)
 
 
+def case_bounce_back_1d(B):  # test/collide.jl:133-150: walls at both ends, tau = 1, no forces, feq = ftemp = fout = 1 except
+    # feq[1, :] = 2 ... the reference's state there is the freshly allocated one (all zero), for which the known answer is
+    # fout[:, k] == circshift(feq[:, 1], c_k); the dummy-distribution case below adds the reflected populations
+    obst = np.zeros(30); obst[0] = obst[-1] = 1
+    interior, border = o1.obslist1D(obst)   # src/obstacle.jl:6-35
+    assert interior.sum() == 0 and np.array_equal(border[0], np.eye(30)[29]) and np.array_equal(border[1], np.eye(30)[0])
+    z = lambda *sh: np.zeros(sh, order="F")  # noqa: E731
+    fout, feq, ftemp, fb = z(30, 3), z(30, 3), z(30, 3), z(30, 3)
+    B.BGKandStream_bound(fout, feq, ftemp, fb, np.zeros(30), border, 1.0)
+    assert np.array_equal(fout[:, 0], feq[:, 0]) and np.array_equal(fout[:, 1], np.roll(feq[:, 0], 1))
+    # a uniform gas between two walls: what would leave through a wall link comes back in the opposite direction, the
+    # total is conserved (the property bounce-back exists for)
+    feq[...] = 1.0; ftemp[...] = 1.0
+    feq[3, :] = 2.0
+    B.BGKandStream_bound(fout, feq, ftemp, fb, np.full(30, 0.1), border, 0.75)
+    want_o, want_t, want_b = z(30, 3), ftemp.copy(), z(30, 3)
+    want_t[...] = 1.0
+    o1.BGKandStream_bound(want_o, feq, want_t, want_b, np.full(30, 0.1), border, 0.75)
+    assert np.array_equal(fout, want_o) and np.array_equal(ftemp, want_t) and np.array_equal(fb, want_b)
+    omega, it = 1 - 1 / 0.75, 1 / 0.75
+    total = (omega * 1.0 + it * feq).sum()
+    assert abs(fout.sum() - total) < 1e-12
+    assert fb[29, 1] == (omega + it) + 0.05 and fb[0, 2] == (omega + it) - 0.05 and fb[:, 0].sum() == 0
+
+
+def case_inclination_1d(B):  # test/forcing.jl:165-183
+    sols = {0: 0.05, 1: 0.1 * (0.5 + 0.5 * np.tanh(1.0))}
+    for t in (0, 1):
+        F = np.zeros(30)
+        B.inclination(F, np.ones(30), 0.1, t=t, tstart=0, tsmooth=1)
+        assert np.all(F == sols[t])
+
+
+def case_gradgamma_1d(B):  # test/forcing.jl:185-194
+    out = np.zeros(30)
+    B.gradgamma(out, np.arange(1.0, 31.0))
+    sol = np.full(30, 3 / 2); sol[0] = sol[-1] = -21.0
+    assert np.array_equal(out, sol)
+    # ∇γ!(state, sys) (src/forcing.jl:434-447) has no known answer upstream: flat film h = 1, δ = 1 -> (2+6+3)/6 * 1/2 * dγ
+    B.gradgamma(out, np.arange(1.0, 31.0), np.ones(30), 1.0)
+    sol = np.full(30, 11 / 6 * 1.0 / 2 * -1.0); sol[0] = sol[-1] = 11 / 6 * 1.0 / 2 * 14.0
+    assert np.array_equal(out, sol)
+
+
+def case_rho_update_1d(B):  # test/forcing.jl:196-204: constant fields stay constant
+    rho, out = np.ones(25), np.zeros(25)
+    B.update_rho(rho, out, np.ones(25), np.zeros((25, 4), order="F"))
+    assert np.all(rho == 1) and np.all(out == 0)
+
+
+def case_pressure_gamma_1d(B):  # test/pressure.jl:56-131
+    f = np.arange(1.0, 31.0)
+    sol = np.zeros(30); sol[0] = 30; sol[-1] = -30
+    res = np.zeros(30)
+    ft = np.zeros((30, 3), order="F")
+    B.filmpressure_gamma(res, f, 1.0, onp.cospi(0.0), 3, 2, 0.1, 0.0, ftemp=ft)       # state3, sys3 (θ = 0)   :73-79
+    assert np.all(res == -sol) and np.all(ft[:, 1] == 0.0) and np.array_equal(ft[:, 2], -sol)
+    B.filmpressure_gamma(res, f, np.full(30, 1.0), onp.cospi(1 / 2), 3, 2, 0.1, 0.0)   # γ as a per-site field   :81-88
+    assert np.allclose(res, -1 * (sol + 20 * ((0.1 / f) ** 3 - (0.1 / f) ** 2)), atol=1e-10, rtol=0)
+    B.filmpressure_gamma(res, np.ones(30), 1.0, onp.cospi(1 / 2), 3, 2, 0.1, 0.0)      # :90-100
+    assert np.allclose(res, -2 * (0.1 ** 2 - 0.1), atol=1e-10, rtol=0)
+    rho = np.full(30, 0.1)                                                            # active matter   :104-131
+    B.filmpressure_gamma(res, f, 1.0, onp.cospi(0.0), 3, 2, 0.1, 0.1, rho=rho)
+    assert np.all(res == -sol)
+    B.filmpressure_gamma(res, np.ones(30), 1.0, onp.cospi(1 / 2), 3, 2, 0.1, 0.0, rho=np.zeros(30), Gamma=0.0)
+    assert np.allclose(res, -2 * (0.1 ** 2 - 0.1), atol=1e-10, rtol=0)
+    B.filmpressure_gamma(res, f, 1.0, onp.cospi(1 / 2), 3, 2, 0.1, 0.0, rho=rho, Gamma=0.1)
+    assert np.allclose(res, -(1 + 0.01) * (sol + 20 * ((0.1 / f) ** 3 - (0.1 / f) ** 2)), atol=1e-10, rtol=0)
+
+
 ALL_1D_CASES = [case_collide_1d, case_equilibrium_1d, case_moments_1d, case_pressure_1d, case_stencils_1d, case_slippage_1d,
-                case_hgradp_1d]
+                case_hgradp_1d, case_bounce_back_1d, case_inclination_1d, case_gradgamma_1d, case_rho_update_1d,
+                case_pressure_gamma_1d]
 
 
 @pytest.mark.parametrize("case", ALL_1D_CASES, ids=lambda c: c.__name__)
