@@ -259,12 +259,13 @@ int swalbe_time_loop_host(swalbe_plan *plan, const swalbe_state *state, const sw
                           unsigned long long step0, int flags, const swalbe_loop_logs *logs, const double *height_in_host,
                           double *height_out_host, void *stream);
 
-/* self-test (host only, needs no device): the operation list of swalbe_time_loop_host for an Lx x Ly lattice -- six ints
- * per operation {kind (0 upload rows, 1 step launch, 2 download rows), step, jbeg, jend, band, seam}, in issue order --
- * so that the schedule can be replayed and checked on the CPU.  band_rows / kmax / min_sites <= 0: the defaults.
- * ops6 == NULL: only *nops is written. */
+/* self-test (host only, needs no device): the operation list of swalbe_time_loop_host for an Lx x Ly lattice -- seven ints
+ * per operation {kind (0 upload rows, 1 step launch, 2 download rows), step, jbeg, jend, band, seam, stage}, in issue
+ * order -- so that the schedule can be replayed and checked on the CPU.  Launches with stage >= 0 belong to band stage
+ * `stage` of a sweep: even and odd stages run on two streams, launch (stage, k-th step of the sweep) ordered after
+ * (stage, k-1) and (stage-1, k-1) only.  band_rows / kmax / min_sites <= 0: the defaults.  ops7 == NULL: only *nops. */
 int swalbe_selftest_host_loop_schedule(int Lx, int Ly, int nsteps, int has_in, int has_out, int band_rows, int kmax,
-                                       int min_sites, int *ops6, int max_ops, int *nops);
+                                       int min_sites, int *ops7, int max_ops, int *nops);
 
 /* ---------------------------------------------------------------------------------------------
  * The 1-D (D1Q3) family: State_1D / SysConst_1D, src/initialize.jl:587-598.  The reference runs it

@@ -269,8 +269,8 @@ struct swalbe_plan {
   GeomEntry geoms[96];
   int ngeoms;
   // swalbe_time_loop_host: copy streams (one per direction: PCIe is full duplex) and their events
-  cudaStream_t s_h2d, s_d2h;
-  cudaEvent_t ev_user, ev_dn, ev_done, ev_up[64];
+  cudaStream_t s_h2d, s_d2h, s_aux;  // s_aux: second compute stream of the sweeps (odd band stages)
+  cudaEvent_t ev_user, ev_dn, ev_done, ev_up[64], ev_join, ev_phase, ev_wave[2][33];
   bool have_host_streams;
 };
 
@@ -315,9 +315,12 @@ int swalbe_plan_destroy(swalbe_plan *plan) {
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
   if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
   if (plan->have_host_streams) {  // (copies still in flight are drained by cudaStreamDestroy's deferred release)
-    cudaStreamDestroy(plan->s_h2d); cudaStreamDestroy(plan->s_d2h);
+    cudaStreamDestroy(plan->s_h2d); cudaStreamDestroy(plan->s_d2h); cudaStreamDestroy(plan->s_aux);
     cudaEventDestroy(plan->ev_user); cudaEventDestroy(plan->ev_dn); cudaEventDestroy(plan->ev_done);
+    cudaEventDestroy(plan->ev_join); cudaEventDestroy(plan->ev_phase);
     for (cudaEvent_t ev : plan->ev_up) cudaEventDestroy(ev);
+    for (int q = 0; q < 2; ++q)
+      for (cudaEvent_t ev : plan->ev_wave[q]) cudaEventDestroy(ev);
   }
   cudaFree(plan->scratch);
   cudaFree(plan->rowsum);
@@ -651,6 +654,11 @@ static int host_streams(swalbe_plan *plan) {
   if (plan->have_host_streams) return 0;
   SW_CUDA(cudaStreamCreateWithFlags(&plan->s_h2d, cudaStreamNonBlocking));
   SW_CUDA(cudaStreamCreateWithFlags(&plan->s_d2h, cudaStreamNonBlocking));
+  SW_CUDA(cudaStreamCreateWithFlags(&plan->s_aux, cudaStreamNonBlocking));
+  SW_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&plan->ev_phase, cudaEventDisableTiming));
+  for (int q = 0; q < 2; ++q)
+    for (cudaEvent_t &ev : plan->ev_wave[q]) SW_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   SW_CUDA(cudaEventCreateWithFlags(&plan->ev_user, cudaEventDisableTiming));
   SW_CUDA(cudaEventCreateWithFlags(&plan->ev_dn, cudaEventDisableTiming));
   SW_CUDA(cudaEventCreateWithFlags(&plan->ev_done, cudaEventDisableTiming));
@@ -722,13 +730,15 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
   const int mass_planes = (logs && logs->hsum && logs->hsum_every > 0) ? kphase / logs->hsum_every + 2 : 1;
   if (int e = mass_log_setup(plan, logs, nsteps, &ml, mass_planes)) return e;
   std::vector<int> mass_rows_done(mass_planes, 0);
-  auto mass_piece = [&](int state, const double *h, int jbeg, int jend) -> int {
+  // (the piece that completes a state is always issued on the caller's stream after the two compute streams have
+  // joined: a seam strip, a whole-lattice step, or the last band of the upload)
+  auto mass_piece = [&](int state, const double *h, int jbeg, int jend, cudaStream_t on) -> int {
     const int pl = ((state - ml.first) / ml.every) % mass_planes;
-    if (int e = mass_rows(plan, h, jbeg, jend, stream, pl)) return e;
+    if (int e = mass_rows(plan, h, jbeg, jend, on, pl)) return e;
     mass_rows_done[pl] += jend - jbeg;
     if (mass_rows_done[pl] == Ly) {
       mass_rows_done[pl] = 0;
-      return mass_final(plan, ml.slot(state), stream, pl);
+      return mass_final(plan, ml.slot(state), on, pl);
     }
     return 0;
   };
@@ -778,23 +788,54 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
     a.hthresh = logs->hthresh;
   }
   if (ml.wants(0) && !hin)
-    if (int e = mass_piece(0, src0[0], 0, Ly)) return e;
-  for (const SweepOp &op : ops) {
+    if (int e = mass_piece(0, src0[0], 0, Ly, stream)) return e;
+  // Two compute streams inside a sweep (sweep.h): even band stages on the caller's stream, odd ones on the plan's second
+  // stream, launch (b, k) gated by one event from (b-1, k-1); everything else -- seam strips, whole-lattice steps, the
+  // end of the call -- runs on the caller's stream after the two have joined.  SWALBE_HOST_STREAMS=1: one stream.
+  const bool two_streams = env_int("SWALBE_HOST_STREAMS", 2) >= 2;
+  cudaStream_t lanes[2] = {stream, two_streams ? plan->s_aux : stream};
+  bool aux_busy = false;   // work on the second stream that the caller's stream has not waited for yet
+  int sweep_s0 = 0;        // first step of the sweep in progress
+  auto join = [&]() -> int {
+    if (!aux_busy) return 0;
+    SW_CUDA(cudaEventRecord(plan->ev_join, plan->s_aux));
+    SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_join, 0));
+    aux_busy = false;
+    return 0;
+  };
+  for (size_t qi = 0; qi < ops.size(); ++qi) {
+    const SweepOp &op = ops[qi];
     if (op.kind == SWEEP_UPLOAD) continue;
+    cudaStream_t on = op.stage >= 0 ? lanes[op.stage & 1] : stream;
+    if (op.stage < 0)
+      if (int e = join()) return e;
     if (op.kind == SWEEP_DOWNLOAD) {
       const size_t off = (size_t)op.jbeg * Lx, cnt = (size_t)(op.jend - op.jbeg) * Lx;
-      mark(stream, "rows [%d, %d) final", op.jbeg, op.jend);
-      SW_CUDA(cudaEventRecord(plan->ev_dn, stream));
+      mark(on, "rows [%d, %d) final", op.jbeg, op.jend);
+      SW_CUDA(cudaEventRecord(plan->ev_dn, on));
       SW_CUDA(cudaStreamWaitEvent(plan->s_d2h, plan->ev_dn, 0));
       if (!nocopy) SW_CUDA(cudaMemcpyAsync(hout + off, A[0] + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, plan->s_d2h));
       mark(plan->s_d2h, "download %d done", op.band, 0);
       continue;
     }
-    if (op.band >= 0) {
-      SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_up[op.band], 0));
-      if (ml.wants(0))
-        if (int e = mass_piece(0, src0[0], up_beg[op.band], up_end[op.band])) return e;
+    const int kk = op.stage >= 0 ? op.step - sweep_s0 + 1 : 0;  // k-th step of its sweep (set below for stage 0, k = 1)
+    if (op.stage == 0 && (qi == 0 || ops[qi - 1].stage != 0 || ops[qi - 1].kind != SWEEP_STEP)) {
+      // a sweep starts: the second stream must see everything the caller's stream has done so far
+      sweep_s0 = op.step;
+      if (two_streams) {
+        SW_CUDA(cudaEventRecord(plan->ev_phase, stream));
+        SW_CUDA(cudaStreamWaitEvent(plan->s_aux, plan->ev_phase, 0));
+      }
     }
+    const int k = op.stage >= 0 ? op.step - sweep_s0 + 1 : kk;
+    if (op.band >= 0) {
+      SW_CUDA(cudaStreamWaitEvent(on, plan->ev_up[op.band], 0));
+      if (ml.wants(0)) {  // (summed on the caller's stream: the last band completes the state there)
+        if (on != stream) SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_up[op.band], 0));
+        if (int e = mass_piece(0, src0[0], up_beg[op.band], up_end[op.band], stream)) return e;
+      }
+    }
+    if (two_streams && op.stage >= 1 && k >= 2) SW_CUDA(cudaStreamWaitEvent(on, plan->ev_wave[(op.stage - 1) & 1][k - 1], 0));
     if (op.jend <= op.jbeg) continue;
     const int s = op.step;
     const bool last = s == nsteps - 1;
@@ -820,15 +861,21 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
     const LaunchGeom &g = use_full ? *g_full[gq] : *g_mid[gq];
     b.rows_per_cta = g.rows_per_cta; b.W = g.W;
     b.jbeg = op.jbeg; b.jend = op.jend;
-    if (int e = launch_fused(g, b, use_full ? key_full : key_mid, stream)) return e;
+    if (int e = launch_fused(g, b, use_full ? key_full : key_mid, on)) return e;
+    if (two_streams && op.stage >= 0) {
+      SW_CUDA(cudaEventRecord(plan->ev_wave[op.stage & 1][k], on));
+      if (on != stream) aux_busy = true;
+    }
     if (ml.wants(s + 1))
-      if (int e = mass_piece(s + 1, dst[0], op.jbeg, op.jend)) return e;
+      if (int e = mass_piece(s + 1, dst[0], op.jbeg, op.jend, on)) return e;
     if (trace && (op.seam == 0) && (s == cfg.k_up - 1 || s == nsteps - 1 || op.jend - op.jbeg == Ly))
-      mark(stream, "step %d rows from %d done", s, op.jbeg);
+      mark(on, "step %d rows from %d done", s, op.jbeg);
   }
+  if (int e = join()) return e;
   if (trace) {
     mark(stream, "compute done", 0, 0);
     cudaStreamSynchronize(stream); cudaStreamSynchronize(plan->s_h2d); cudaStreamSynchronize(plan->s_d2h);
+    cudaStreamSynchronize(plan->s_aux);
     fprintf(stderr, "[swalbe] host loop %d x %d, %d steps: %d bands, sweeps of %d / %d steps%s\n", Lx, Ly, nsteps, cfg.nbands,
             cfg.k_up, cfg.k_dn, cfg.single ? " (single)" : "");
     for (size_t q = 0; q < marks.size(); ++q) {
@@ -857,17 +904,17 @@ int swalbe_time_loop_host(swalbe_plan *plan, const swalbe_state *st, const swalb
 }
 
 int swalbe_selftest_host_loop_schedule(int Lx, int Ly, int nsteps, int has_in, int has_out, int band_rows, int kmax,
-                                       int min_sites, int *ops6, int max_ops, int *nops) {
+                                       int min_sites, int *ops7, int max_ops, int *nops) {
   if (!nops) return set_error(SWALBE_ERR_ARG, "nops is NULL");
   if (int e = check_extent(Lx, Ly)) return e;
   const SweepConfig cfg = sweep_configure(Lx, Ly, nsteps, has_in != 0, has_out != 0, band_rows, kmax, min_sites);
   const std::vector<SweepOp> ops = sweep_schedule(cfg, Ly, nsteps, has_in != 0, has_out != 0);
   *nops = (int)ops.size();
-  if (!ops6) return 0;
+  if (!ops7) return 0;
   if ((int)ops.size() > max_ops) return set_error(SWALBE_ERR_ARG, "schedule has %d operations, room for %d", (int)ops.size(), max_ops);
   for (size_t q = 0; q < ops.size(); ++q) {
-    const int v[6] = {ops[q].kind, ops[q].step, ops[q].jbeg, ops[q].jend, ops[q].band, ops[q].seam};
-    memcpy(ops6 + 6 * q, v, sizeof(v));
+    const int v[7] = {ops[q].kind, ops[q].step, ops[q].jbeg, ops[q].jend, ops[q].band, ops[q].seam, ops[q].stage};
+    memcpy(ops7 + 7 * q, v, sizeof(v));
   }
   return 0;
 }

@@ -26,7 +26,13 @@ struct SweepOp {
   int band;        // SWEEP_UPLOAD: band index; SWEEP_STEP: band whose upload the launch has to wait for (-1: none);
                    // SWEEP_DOWNLOAD: running index of the download
   int seam;        // SWEEP_STEP: 1 = a seam launch (a few rows)
+  int stage;       // SWEEP_STEP / SWEEP_DOWNLOAD inside a sweep: the band stage b it belongs to; -1: whole lattice, seam
 };
+// What a launch depends on (besides its band's upload): launch (stage b, k-th step of the sweep) reads state k-1 of the rows
+// [Y_b - 3(k+1), Y_b+1 - 3(k-1)), produced by (b, k-1) and (b-1, k-1), and overwrites state k-2 of its own rows, last read by
+// those same two launches.  Nothing else: the stages of a sweep may run on two streams, even stages on one, odd stages on
+// the other, with one event from (b-1, k-1) to (b, k) -- the tail of one launch fills with the head of the next.
+// Seam launches and whole-lattice steps need everything before them.
 
 struct SweepConfig {
   int nbands;   // 0: not worth it / not possible -> plain copy, loop, copy
@@ -50,7 +56,7 @@ inline SweepConfig sweep_configure(int Lx, int Ly, int nsteps, bool has_in, bool
   if (nb < 2) nb = 2;
   if (nb > 64) nb = 64;
   const int minband = Ly / nb;  // bands are [b*Ly/nb, (b+1)*Ly/nb): never shorter than this
-  int kmax = kmax_req > 0 ? kmax_req : 12;
+  int kmax = kmax_req > 0 ? (kmax_req < 32 ? kmax_req : 32) : 12;
   if (kmax > (minband - 2) / 6) kmax = (minband - 2) / 6;  // band 0 shrinks by 3 rows at both ends with every step
   if (kmax < 1) return c;
   c.nbands = nb;
@@ -65,22 +71,22 @@ inline SweepConfig sweep_configure(int Lx, int Ly, int nsteps, bool has_in, bool
 inline void sweep_phase(std::vector<SweepOp> &ops, int Ly, int nbands, int s0, int K, bool upload, bool download, int *ndown) {
   for (int b = 0; b < nbands; ++b) {
     const int y0 = sweep_band_begin(b, nbands, Ly), y1 = sweep_band_begin(b + 1, nbands, Ly);
-    if (upload) ops.push_back({SWEEP_UPLOAD, 0, y0, y1, b, 0});
+    if (upload) ops.push_back({SWEEP_UPLOAD, 0, y0, y1, b, 0, -1});
     int lo = 0, hi = 0;
     for (int k = 1; k <= K; ++k) {
       lo = b == 0 ? 3 * k : y0 - 3 * k;
       hi = y1 - 3 * k;
-      ops.push_back({SWEEP_STEP, s0 + k - 1, lo, hi, upload && k == 1 ? b : -1, 0});
+      ops.push_back({SWEEP_STEP, s0 + k - 1, lo, hi, upload && k == 1 ? b : -1, 0, b});
     }
-    if (download) ops.push_back({SWEEP_DOWNLOAD, 0, lo, hi, (*ndown)++, 0});
+    if (download) ops.push_back({SWEEP_DOWNLOAD, 0, lo, hi, (*ndown)++, 0, b});
   }
   for (int k = 1; k <= K; ++k) {
-    ops.push_back({SWEEP_STEP, s0 + k - 1, Ly - 3 * k, Ly, -1, 1});
-    ops.push_back({SWEEP_STEP, s0 + k - 1, 0, 3 * k, -1, 1});
+    ops.push_back({SWEEP_STEP, s0 + k - 1, Ly - 3 * k, Ly, -1, 1, -1});
+    ops.push_back({SWEEP_STEP, s0 + k - 1, 0, 3 * k, -1, 1, -1});
   }
   if (download) {
-    ops.push_back({SWEEP_DOWNLOAD, 0, Ly - 3 * K, Ly, (*ndown)++, 0});
-    ops.push_back({SWEEP_DOWNLOAD, 0, 0, 3 * K, (*ndown)++, 0});
+    ops.push_back({SWEEP_DOWNLOAD, 0, Ly - 3 * K, Ly, (*ndown)++, 0, -1});
+    ops.push_back({SWEEP_DOWNLOAD, 0, 0, 3 * K, (*ndown)++, 0, -1});
   }
 }
 
@@ -89,9 +95,9 @@ inline std::vector<SweepOp> sweep_schedule(const SweepConfig &c, int Ly, int nst
   std::vector<SweepOp> ops;
   int ndown = 0;
   if (c.nbands == 0) {
-    if (has_in) ops.push_back({SWEEP_UPLOAD, 0, 0, Ly, 0, 0});
-    for (int s = 0; s < nsteps; ++s) ops.push_back({SWEEP_STEP, s, 0, Ly, s == 0 && has_in ? 0 : -1, 0});
-    if (has_out) ops.push_back({SWEEP_DOWNLOAD, 0, 0, Ly, ndown++, 0});
+    if (has_in) ops.push_back({SWEEP_UPLOAD, 0, 0, Ly, 0, 0, -1});
+    for (int s = 0; s < nsteps; ++s) ops.push_back({SWEEP_STEP, s, 0, Ly, s == 0 && has_in ? 0 : -1, 0, -1});
+    if (has_out) ops.push_back({SWEEP_DOWNLOAD, 0, 0, Ly, ndown++, 0, -1});
     return ops;
   }
   if (c.single) {
@@ -99,11 +105,11 @@ inline std::vector<SweepOp> sweep_schedule(const SweepConfig &c, int Ly, int nst
     return ops;
   }
   if (c.k_up > 0) sweep_phase(ops, Ly, c.nbands, 0, c.k_up, true, false, &ndown);
-  else if (has_in) ops.push_back({SWEEP_UPLOAD, 0, 0, Ly, 0, 0});
+  else if (has_in) ops.push_back({SWEEP_UPLOAD, 0, 0, Ly, 0, 0, -1});
   for (int s = c.k_up; s < nsteps - c.k_dn; ++s)
-    ops.push_back({SWEEP_STEP, s, 0, Ly, s == 0 && has_in ? 0 : -1, 0});
+    ops.push_back({SWEEP_STEP, s, 0, Ly, s == 0 && has_in ? 0 : -1, 0, -1});
   if (c.k_dn > 0) sweep_phase(ops, Ly, c.nbands, nsteps - c.k_dn, c.k_dn, false, true, &ndown);
-  else if (has_out) ops.push_back({SWEEP_DOWNLOAD, 0, 0, Ly, ndown++, 0});
+  else if (has_out) ops.push_back({SWEEP_DOWNLOAD, 0, 0, Ly, ndown++, 0, -1});
   return ops;
 }
 

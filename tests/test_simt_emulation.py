@@ -431,11 +431,37 @@ def _host_loop_ops(Lx, Ly, nsteps, has_in, has_out, band_rows, kmax):
     lib = _lib.load()
     n = C.c_int(0)
     _lib.call("swalbe_selftest_host_loop_schedule", Lx, Ly, nsteps, int(has_in), int(has_out), band_rows, kmax, 1, None, 0, C.byref(n))
-    buf = (C.c_int * (6 * n.value))()
+    buf = (C.c_int * (7 * n.value))()
     _lib.call("swalbe_selftest_host_loop_schedule", Lx, Ly, nsteps, int(has_in), int(has_out), band_rows, kmax, 1, buf, n.value,
               C.byref(n))
     assert lib is not None
-    return [tuple(buf[6 * q:6 * q + 6]) for q in range(n.value)]
+    return [tuple(buf[7 * q:7 * q + 7]) for q in range(n.value)]
+
+
+def _columns_order(ops):
+    """The other extreme of what the two compute streams of a sweep allow: inside every sweep, step k of ALL band stages
+    before step k+1 of any (the schedule lists stage after stage).  Legal because launch (stage b, k) is only ordered
+    after (b, k-1) and (b-1, k-1); uploads first, downloads last."""
+    out, run = [], []
+
+    def flush():
+        if run:
+            kmin = min(o[1] for o in run)
+            out.extend(sorted(run, key=lambda o: (o[1] - kmin, o[6])))
+            run.clear()
+
+    for o in ops:
+        if o[0] != 1:
+            continue
+        if o[6] >= 0:
+            if run and o[6] == 0 and run[-1][6] != 0:  # a new sweep starts
+                flush()
+            run.append(o)
+        else:
+            flush()
+            out.append(o)
+    flush()
+    return [o for o in ops if o[0] == 0] + out + [o for o in ops if o[0] == 2]
 
 
 def _replay_host_loop(simt, ops, st, p, nsteps, h_host, out_host, early_copies, lazy, W=40, rows=16):
@@ -455,10 +481,10 @@ def _replay_host_loop(simt, ops, st, p, nsteps, h_host, out_host, early_copies, 
     ups = [o for o in ops if o[0] == 0]
     downs = [o for o in ops if o[0] == 2]
     if early_copies:
-        for _, _, j0, j1, _, _ in ups:
+        for _, _, j0, j1, _, _, _ in ups:
             src0[0][:, j0:j1] = h_host[:, j0:j1]
     arrived = set()
-    for kind, s, j0, j1, band, seam in ops:
+    for kind, s, j0, j1, band, seam, _stage in ops:
         if kind == 0:
             if not early_copies:
                 src0[0][:, j0:j1] = h_host[:, j0:j1]
@@ -489,7 +515,7 @@ def _replay_host_loop(simt, ops, st, p, nsteps, h_host, out_host, early_copies, 
                     setattr(q, name, _ptr(fld))
             assert simt.simt_step(C.byref(q)) == 0
     if early_copies:
-        for _, _, j0, j1, _, _ in downs:
+        for _, _, j0, j1, _, _, _ in downs:
             out_host[:, j0:j1] = A[0][:, j0:j1]
 
 
@@ -505,7 +531,7 @@ def test_host_loop_sweeps_on_cpu(simt, nsteps, has_in, has_out):
     # every step covers every row exactly once
     for s in range(nsteps):
         cover = np.zeros(Ly, dtype=int)
-        for _, ss, j0, j1, _, _ in steps:
+        for _, ss, j0, j1, _, _, _ in steps:
             if ss == s and j1 > j0:
                 cover[j0:j1] += 1
         assert (cover == 1).all(), (s, cover)
@@ -519,12 +545,14 @@ def test_host_loop_sweeps_on_cpu(simt, nsteps, has_in, has_out):
     ref = _state(Lx, Ly, 11)
     h0 = ref.height.copy()
     oc.time_loop(ref, p, nsteps=nsteps)
-    for early, lazy in ((False, False), (True, True)):
+    cols = _columns_order(ops)
+    assert sorted(cols) == sorted(ops) and cols != ops
+    for early, lazy, order in ((False, False, ops), (True, True, cols)):
         st = _state(Lx, Ly, 11)
         if has_in:
             st.height[...] = 7.0  # the device plane holds something else: the job starts from the host plane
         out = np.full((Lx, Ly), np.nan)
-        _replay_host_loop(simt, ops, st, p, nsteps, h0 if has_in else None, out if has_out else None, early, lazy)
+        _replay_host_loop(simt, order, st, p, nsteps, h0 if has_in else None, out if has_out else None, early, lazy)
         _same(st, ref, FIELDS + AUX)
         if has_out:
             assert np.array_equal(out, ref.height)
