@@ -585,6 +585,7 @@ def main():
         dist.barrier()
         launches = int(lib.swalbe_launch_count() - l0)
         sampler.stop()
+        extra["halo_transport"] = "peer-memory stores over NVLink (k_halo_push)" if sim.uses_peer_memory() else "NCCL send/recv"
         if not moving:  # device time of the K-step loop on rank 0's own streams (edge strips + halo exchange + interior):
             # next to the single-GPU kernel time it shows whether the exchange is hidden behind the interior update
             extra["dist_loop_ms_per_step_rank0"] = round(sim.last_loop_ms() / K, 4)

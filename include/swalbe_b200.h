@@ -354,7 +354,8 @@ int swalbe_time_loop_1d(const swalbe_state_1d *state, const swalbe_params *param
                         const swalbe_loop_logs *logs, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Multi-GPU: row-slab decomposition along j (Ly), one process per GPU, halo rows over NCCL send/recv.
+ * Multi-GPU: row-slab decomposition along j (Ly), one process per GPU; halo rows as peer-memory stores over NVLink
+ * (one kernel per step; see swalbe_dist_uses_peer_memory) or, where that is not available, over NCCL send/recv.
  * The reference has no multi-GPU path; this is new.  Rank r owns global rows
  * [r*Ly/nranks, (r+1)*Ly/nranks) of every plane; Ly % nranks must be 0.
  * ------------------------------------------------------------------------------------------- */
@@ -387,6 +388,10 @@ int swalbe_dist_height_stats(swalbe_dist *dist, double *out4, double thresh, voi
 int swalbe_dist_time_loop(swalbe_dist *dist, int nsteps, unsigned long long step0, void *stream);
 /* copy this rank's slab rows of height/velx/vely and (optional, may be NULL) the nine population planes out */
 int swalbe_dist_get_state(swalbe_dist *dist, double *height, double *velx, double *vely, double *fout, void *stream);
+/* *yes = 1 when the halo rows of the time loop travel as stores into the neighbours' memory (CUDA IPC mapping over
+ * NVLink, one kernel per step, tau == 1), 0 when they go through NCCL send/recv (SWALBE_DIST_P2P=0, tau != 1, or the
+ * ranks cannot map each other's memory) */
+int swalbe_dist_uses_peer_memory(const swalbe_dist *dist, int *yes);
 /* device time (ms) spent in the last swalbe_dist_time_loop call, measured with CUDA events on its streams */
 int swalbe_dist_last_loop_ms(swalbe_dist *dist, float *ms);
 

@@ -117,6 +117,7 @@ SIGNATURES = {
     "swalbe_dist_height_stats": [_vp, _vp, _d, _vp],
     "swalbe_dist_time_loop": [_vp, _i, _u64, _vp],
     "swalbe_dist_get_state": [_vp, _vp, _vp, _vp, _vp, _vp],
+    "swalbe_dist_uses_peer_memory": [_vp, C.POINTER(_i)],
     "swalbe_dist_last_loop_ms": [_vp, C.POINTER(C.c_float)],
 }
 _RESTYPES = {"swalbe_last_error": C.c_char_p, "swalbe_launch_count": _u64}

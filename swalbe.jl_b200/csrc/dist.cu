@@ -15,9 +15,24 @@
 // the interior update of the same step.
 // With nranks == 1 the exchange degenerates to two device-to-device copies (self-neighbour), which also lets
 // the ghost-row kernel path be tested on a single GPU.
+//
+// Peer-memory halos (tau == 1, default when the ranks can map each other's memory; SWALBE_DIST_P2P=0: NCCL).  All six
+// moment planes of a rank and three 64-bit flags live in ONE allocation whose CUDA IPC handle the ranks all-gather at
+// create time.  Per step, instead of the NCCL group, ONE kernel on the communication stream stores the freshly computed
+// edge rows straight into the two neighbours' ghost rows over NVLink, fences, and publishes the step's sequence number
+// in their flags; the next step's edge kernels are preceded by a one-warp kernel that waits for both of its own flags.
+// No receive side, no rendezvous, no proxy thread.  Why no "ready to receive" handshake is needed: a neighbour can only
+// compute the edge strips of step s+1 -- and push them into the ghost rows my step-s edge kernels read -- after it has
+// seen my push of step s, which my stream issues after those kernels.  A wait that does not come true within 20 s sets a
+// sticky error flag and gives up (reported by swalbe_dist_last_loop_ms) instead of hanging the device.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "fused.cuh"
 #include "launch.h"
@@ -35,6 +50,7 @@ struct NcclApi {
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -50,7 +66,7 @@ static int load_nccl() {
   *(void **)(&g_nccl.name) = dlsym(h, "nccl" #name);                                      \
   if (!g_nccl.name) return set_error(SWALBE_ERR_NCCL, "libnccl.so.2 lacks symbol nccl" #name)
   SW_SYM(GetUniqueId); SW_SYM(CommInitRank); SW_SYM(CommDestroy); SW_SYM(Send); SW_SYM(Recv);
-  SW_SYM(GroupStart); SW_SYM(GroupEnd); SW_SYM(GetErrorString);
+  SW_SYM(GroupStart); SW_SYM(GroupEnd); SW_SYM(AllGather); SW_SYM(GetErrorString);
 #undef SW_SYM
   g_nccl.handle = h;
   return 0;
@@ -74,7 +90,15 @@ struct swalbe_dist {
   size_t mplane;          // elements of one moment plane incl. ghosts
   size_t fplane;          // elements of one population plane incl. ghosts
   int gh_f;
+  double *arena;          // the six moment planes + the halo flags in one allocation (one IPC handle)
   double *m[2][3];        // ping-pong sets of (h, ux, uy)
+  // peer-memory halos
+  bool p2p;               // halo rows are stored into the neighbours' ghost rows by k_halo_push
+  bool ghost_via_p2p;     // the ghost rows of the current set were (are being) filled by the neighbours' pushes
+  void *peer_base[2];     // mapped arena of the rank below [0] / above [1] (the same mapping when they are one rank)
+  unsigned long long *flags;        // own: [0] pushes received from below, [1] from above, [2] sticky time-out flag
+  unsigned long long seq;           // pushes issued so far (every rank issues one per step)
+  unsigned int *push_count;         // last-block detection of k_halo_push
   double *f[2];           // population sets (tau == 1: only f[0], no ghosts)
   double *ct;             // cospi(theta) slab with GH ghost rows (NULL: scalar theta)
   double *ct_spare;       // a slab released by swalbe_dist_set_theta(NULL), kept for the next field (no free in the loop)
@@ -91,6 +115,18 @@ struct swalbe_dist {
   float last_ms;
 };
 
+static int env_flag(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+static void close_peer_memory(swalbe_dist *d) {
+  if (d->peer_base[1] && d->peer_base[1] != d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[1]);
+  if (d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[0]);
+  d->peer_base[0] = d->peer_base[1] = nullptr;
+  d->p2p = false;
+  cudaGetLastError();
+}
+
 // dst[j, i] = src[j - sy, i - sx] for the owned rows j in [0, Ly_loc) of a ghosted slab plane (|sy| <= GH: the source rows
 // come from the ghost rows, which the last exchange made current); x is periodic inside the slab
 __global__ void k_shift_slab(double *__restrict__ dst, const double *__restrict__ src, int sx, int sy, int Lx, int Ly_loc) {
@@ -100,6 +136,50 @@ __global__ void k_shift_slab(double *__restrict__ dst, const double *__restrict_
   int is = i - sx;
   is += is < 0 ? Lx : 0;
   dst[(size_t)(j + GH) * Lx + i] = src[(size_t)(j + GH - sy) * Lx + is];
+}
+
+struct PushArgs {
+  const double *src[6];  // own rows: [q] top GH rows of plane q (go up), [3 + q] bottom GH rows (go down)
+  double *dst[6];        // [q] ghost rows below row 0 of the rank above, [3 + q] ghost rows above the slab of the rank below
+  size_t n;              // doubles per part (GH * Lx)
+  unsigned long long *flag_up, *flag_down;  // the rank above counts pushes "from below", the rank below "from above"
+  unsigned long long seq;
+  unsigned int *count;
+};
+
+// Stores the six edge-row blocks into the neighbours' memory; the last CTA to finish publishes the sequence number.
+__global__ void __launch_bounds__(256) k_halo_push(const PushArgs a) {
+  const int part = blockIdx.y;
+  const double *__restrict__ src = a.src[part];
+  double *__restrict__ dst = a.dst[part];
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+  __threadfence_system();  // this thread's rows are visible system-wide before the CTA reports in
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    if (atomicAdd(a.count, 1u) == total - 1u) {
+      *a.count = 0u;
+      __threadfence_system();
+      *(volatile unsigned long long *)a.flag_up = a.seq;
+      *(volatile unsigned long long *)a.flag_down = a.seq;
+      __threadfence_system();
+    }
+  }
+}
+
+// One warp: wait until both neighbours have published push number `seq` (or the sticky time-out flag is set).
+__global__ void k_halo_wait(unsigned long long *flags, unsigned long long seq) {
+  if (threadIdx.x != 0) return;
+  volatile unsigned long long *f = flags;
+  if (f[2]) return;
+  unsigned long long t0 = 0, t1 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (f[0] < seq || f[1] < seq) {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) { f[2] = 1ull; break; }  // 20 s: the neighbour is gone; do not hang the device
+  }
+  __threadfence_system();
 }
 
 static int exchange_rows(swalbe_dist *d, double *plane, int gh, size_t rows_total) {
@@ -133,6 +213,30 @@ static int exchange_halos(swalbe_dist *d, int set, int fset) {
     for (int k = 0; k < 9; ++k)
       if (int e = exchange_rows(d, d->f[fset] + k * d->fplane, 1, d->Ly_loc + 2)) return e;
   if (d->nranks > 1) SW_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
+// the peer-memory exchange of moment set `set`: one kernel, no receive side
+static int push_halos(swalbe_dist *d, int set) {
+  PushArgs a;
+  const size_t row0 = (size_t)GH * d->Lx;                    // first owned row inside a ghosted plane
+  const size_t top = (size_t)d->Ly_loc * d->Lx;              // rows [Ly_loc - GH, Ly_loc)
+  const size_t ghost_hi = (size_t)(d->Ly_loc + GH) * d->Lx;  // rows [Ly_loc, Ly_loc + GH)
+  double *down_arena = (double *)d->peer_base[0], *up_arena = (double *)d->peer_base[1];
+  for (int q = 0; q < 3; ++q) {
+    const size_t plane = (size_t)(set * 3 + q) * d->mplane;
+    a.src[q] = d->m[set][q] + top;      a.dst[q] = up_arena + plane;                 // my top rows -> ghost rows below its row 0
+    a.src[3 + q] = d->m[set][q] + row0; a.dst[3 + q] = down_arena + plane + ghost_hi;  // my bottom rows -> ghost rows above its slab
+  }
+  a.n = (size_t)GH * d->Lx;
+  a.flag_up = (unsigned long long *)(up_arena + 6 * d->mplane) + 0;      // "received from below"
+  a.flag_down = (unsigned long long *)(down_arena + 6 * d->mplane) + 1;  // "received from above"
+  a.seq = ++d->seq;
+  a.count = d->push_count;
+  const unsigned nb = (unsigned)std::min<size_t>(8, (a.n + 2047) / 2048);
+  k_halo_push<<<dim3(nb, 6), 256, 0, d->s_comm>>>(a);
+  SW_LAUNCH_CHECK();
+  d->ghost_via_p2p = true;
   return 0;
 }
 
@@ -179,16 +283,65 @@ int swalbe_dist_create(swalbe_dist **out, const void *id128, int rank, int nrank
   return 0;
 }
 
+// Map the neighbours' arenas: all-gather the IPC handles over the communicator that exists anyway, open the two that
+// matter, then all-gather whether that worked -- every rank must take the same transport, or one would wait for flags
+// that nobody writes.  Any failure (no peer access, IPC not permitted in this container) leaves the NCCL path in charge.
+static int setup_peer_memory(swalbe_dist *d) {
+  d->p2p = false;
+  if (!d->tau1 || !env_flag("SWALBE_DIST_P2P", 1)) return 0;
+  const int n = d->nranks;
+  const int up = (d->rank + 1) % n, down = (d->rank + n - 1) % n;
+  unsigned char *dev = nullptr;
+  SW_CUDA(cudaMalloc((void **)&dev, 64 * (size_t)(n + 1)));
+  std::vector<unsigned char> host(64 * (size_t)n);
+  unsigned char mine[64] = {0};
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle size");
+  bool ok = cudaIpcGetMemHandle(&h, d->arena) == cudaSuccess;
+  cudaGetLastError();
+  memcpy(mine, &h, sizeof(h));
+  SW_CUDA(cudaMemcpyAsync(dev, mine, 64, cudaMemcpyHostToDevice, d->s_comm));
+  SW_NCCL(g_nccl.AllGather(dev, dev + 64, 64, ncclChar, d->comm, d->s_comm));
+  SW_CUDA(cudaMemcpyAsync(host.data(), dev + 64, 64 * (size_t)n, cudaMemcpyDeviceToHost, d->s_comm));
+  SW_CUDA(cudaStreamSynchronize(d->s_comm));
+  const int peers[2] = {down, up};
+  for (int q = 0; q < 2 && ok; ++q) {
+    if (q == 1 && up == down) { d->peer_base[1] = d->peer_base[0]; break; }
+    cudaIpcMemHandle_t ph;
+    memcpy(&ph, host.data() + 64 * (size_t)peers[q], sizeof(ph));
+    ok = cudaIpcOpenMemHandle(&d->peer_base[q], ph, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); d->peer_base[q] = nullptr; }
+  }
+  memset(mine, 0, 64);
+  mine[0] = ok ? 1 : 0;
+  SW_CUDA(cudaMemcpyAsync(dev, mine, 64, cudaMemcpyHostToDevice, d->s_comm));
+  SW_NCCL(g_nccl.AllGather(dev, dev + 64, 64, ncclChar, d->comm, d->s_comm));
+  SW_CUDA(cudaMemcpyAsync(host.data(), dev + 64, 64 * (size_t)n, cudaMemcpyDeviceToHost, d->s_comm));
+  SW_CUDA(cudaStreamSynchronize(d->s_comm));
+  SW_CUDA(cudaFree(dev));
+  bool all = true;
+  for (int r = 0; r < n; ++r) all = all && host[64 * (size_t)r] == 1;
+  if (!all) {
+    close_peer_memory(d);
+    if (env_flag("SWALBE_DEBUG", 0)) fprintf(stderr, "[swalbe] rank %d: peer memory unavailable, halos go through NCCL\n", d->rank);
+    return 0;
+  }
+  d->p2p = true;
+  return 0;
+}
+
 static int dist_allocate(swalbe_dist *d, const void *id128, int rank, int nranks, int Lx, int Ly_loc,
                          const swalbe_params *prm) {
   d->mplane = (size_t)(Ly_loc + 2 * GH) * Lx;
   d->gh_f = d->tau1 ? 0 : 1;
   d->fplane = (size_t)(Ly_loc + 2 * d->gh_f) * Lx;
+  const size_t arena_bytes = 6 * d->mplane * sizeof(double) + 64;
+  SW_CUDA(cudaMalloc((void **)&d->arena, arena_bytes));
+  SW_CUDA(cudaMemset(d->arena, 0, arena_bytes));
   for (int s = 0; s < 2; ++s)
-    for (int q = 0; q < 3; ++q) {
-      SW_CUDA(cudaMalloc((void **)&d->m[s][q], d->mplane * sizeof(double)));
-      SW_CUDA(cudaMemset(d->m[s][q], 0, d->mplane * sizeof(double)));
-    }
+    for (int q = 0; q < 3; ++q) d->m[s][q] = d->arena + (size_t)(s * 3 + q) * d->mplane;
+  d->flags = (unsigned long long *)(d->arena + 6 * d->mplane);
+  d->push_count = (unsigned int *)(d->flags + 4);
   for (int s = 0; s < (d->tau1 ? 1 : 2); ++s) {
     SW_CUDA(cudaMalloc((void **)&d->f[s], 9 * d->fplane * sizeof(double)));
     SW_CUDA(cudaMemset(d->f[s], 0, 9 * d->fplane * sizeof(double)));
@@ -209,6 +362,7 @@ static int dist_allocate(swalbe_dist *d, const void *id128, int rank, int nranks
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     SW_NCCL(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
+    if (int e = setup_peer_memory(d)) return e;
   }
   d->key = make_key(*prm, d->base.pc.pmode, true);
   d->key_edge = d->key;
@@ -225,11 +379,10 @@ int swalbe_dist_destroy(swalbe_dist *d) {
   if (d->s_comp) cudaStreamSynchronize(d->s_comp);
   if (d->s_edge) cudaStreamSynchronize(d->s_edge);
   if (d->s_comm) cudaStreamSynchronize(d->s_comm);
+  close_peer_memory(d);
   if (d->comm) g_nccl.CommDestroy(d->comm);
-  for (int s = 0; s < 2; ++s) {
-    for (int q = 0; q < 3; ++q) cudaFree(d->m[s][q]);
-    cudaFree(d->f[s]);
-  }
+  cudaFree(d->arena);
+  for (int s = 0; s < 2; ++s) cudaFree(d->f[s]);
   cudaFree(d->ct);
   cudaFree(d->ct_alt);
   cudaFree(d->ct_spare);
@@ -258,6 +411,7 @@ int swalbe_dist_set_state(swalbe_dist *d, const double *height, const double *ve
   const size_t n = (size_t)d->Ly_loc * d->Lx;
   const double *src[3] = {height, velx, vely};
   d->cur = 0; d->fcur = 0;
+  d->ghost_via_p2p = false;  // the exchange below is a NCCL group whose completion is a local event
   for (int q = 0; q < 3; ++q)
     SW_CUDA(cudaMemcpyAsync(d->m[0][q] + (size_t)GH * d->Lx, src[q], n * sizeof(double), cudaMemcpyDeviceToDevice, user));
   if (ftemp)
@@ -302,6 +456,10 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     a.step = step0 + (unsigned long long)s;
     // edge strips: need the ghost rows of `src` (previous exchange) and the rows the previous interior kernel wrote
     SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_halo, 0));
+    if (d->p2p && d->ghost_via_p2p) {  // ... which the neighbours' push number `seq` filled: wait for both flags
+      k_halo_wait<<<1, 32, 0, d->s_edge>>>(d->flags, d->seq);
+      SW_LAUNCH_CHECK();
+    }
     SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_int, 0));
     // interior rows: need the edge rows of `src` written by the previous step's edge kernels, no ghost row
     SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_edges, 0));
@@ -313,7 +471,9 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     SW_CUDA(cudaEventRecord(d->ev_edges, d->s_edge));
     // halo exchange of the freshly written edge rows of `dst`
     SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_edges, 0));
-    if (int e = exchange_halos(d, dst, fdst)) return e;
+    if (d->p2p) {
+      if (int e = push_halos(d, dst)) return e;
+    } else if (int e = exchange_halos(d, dst, fdst)) return e;
     SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
     if (Ly > 2 * GH) {
       a.W = d->g_int.W; a.rows_per_cta = d->g_int.rows_per_cta;
@@ -420,9 +580,20 @@ int swalbe_dist_height_stats(swalbe_dist *d, double *out4, double thresh, void *
   return swalbe_field_stats(out4, d->m[d->cur][0] + (size_t)GH * d->Lx, thresh, d->Lx, d->Ly_loc, stream_);
 }
 
+int swalbe_dist_uses_peer_memory(const swalbe_dist *d, int *yes) {
+  if (!d || !yes) return set_error(SWALBE_ERR_ARG, "NULL argument");
+  *yes = d->p2p ? 1 : 0;
+  return 0;
+}
+
 int swalbe_dist_last_loop_ms(swalbe_dist *d, float *ms) {
   if (!d || !ms) return set_error(SWALBE_ERR_ARG, "NULL argument");
   SW_CUDA(cudaEventSynchronize(d->ev_t1));
+  if (d->p2p) {
+    unsigned long long err = 0;
+    SW_CUDA(cudaMemcpy(&err, d->flags + 2, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) return set_error(SWALBE_ERR_NCCL, "peer-memory halo exchange: a neighbour's rows did not arrive within 20 s");
+  }
   SW_CUDA(cudaEventElapsedTime(ms, d->ev_t0, d->ev_t1));
   d->last_ms = *ms;
   return 0;

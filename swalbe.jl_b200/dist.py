@@ -142,6 +142,12 @@ class DistSim:
         p = lambda f: f.ptr if f is not None else None  # noqa: E731
         _lib.call("swalbe_dist_get_state", self.handle, p(height), p(velx), p(vely), p(fout), self._stream())
 
+    def uses_peer_memory(self) -> bool:
+        """True when the halo rows travel as stores into the neighbours' memory (NVLink), False when through NCCL."""
+        yes = C.c_int()
+        _lib.call("swalbe_dist_uses_peer_memory", self.handle, C.byref(yes))
+        return bool(yes.value)
+
     def last_loop_ms(self) -> float:
         ms = C.c_float()
         _lib.call("swalbe_dist_last_loop_ms", self.handle, C.byref(ms))

@@ -624,6 +624,13 @@ function height_stats(sim::DistSim; thresh = 0.055)
     return (min = mn, max = mx, sum = sm, count = Int(cnt))
 end
 
+"true when the halo rows travel as stores into the neighbours' memory (NVLink), false when through NCCL"
+function uses_peer_memory(sim::DistSim)
+    yes = Ref{Cint}(0)
+    check(ccall((:swalbe_dist_uses_peer_memory, lib), Cint, (Ptr{Cvoid}, Ptr{Cint}), sim.ptr, yes))
+    return yes[] != 0
+end
+
 """Device time (ms) of the last `time_loop!` call, from CUDA events on the runtime's own streams (blocks until done)."""
 function last_loop_ms(sim::DistSim)
     ms = Ref{Cfloat}(0)
