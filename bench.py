@@ -604,19 +604,22 @@ def main():
             out_host = torch.empty_like(h_host).pin_memory()
             torch.cuda.synchronize(); dist.barrier()
             t0 = time.perf_counter()
-            hd.t.copy_(h_host, non_blocking=True)
-            sim.set_state(hd, zero, zero)
             set_theta()
-            dist_run(K, 0)
-            sim.get_state(hd)
-            out_host.copy_(hd.t, non_blocking=True)
+            segs = segments(0, K) if moving else [(0, K, False)]
+            for q, (s0_, cnt, move) in enumerate(segs):  # the slab's rows travel in bands behind / ahead of the steps
+                sim.time_loop_host(cnt, host_in=h_host if q == 0 else None, host_out=out_host if q == len(segs) - 1 else None,
+                                   step0=s0_)
+                if move:
+                    sim.shift_theta(1, 1)
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             plane = L * rows * 8
             e2e = {"value": round(lu / dt.item() / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": plane * world * (2 if moving else 1) // K,
                    "d2h_bytes_per_step": plane * world // K,
-                   "what": f"per-rank pinned-host slab -> H2D -> {K} fused steps with NCCL halos -> D2H slab; max over ranks"}
+                   "what": f"per-rank pinned-host slab -> H2D -> {K} fused steps with halo exchange -> D2H slab into pinned host "
+                           "memory, both copies inside the timed region, travelling in row bands behind / ahead of the first / last "
+                           "steps (swalbe_dist_time_loop_host); wall clock, max over ranks"}
         sim.close()
         del hd, zero
         torch.cuda.empty_cache()

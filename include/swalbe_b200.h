@@ -386,6 +386,15 @@ int swalbe_dist_shift_theta(swalbe_dist *d, int sx, int sy, void *stream);
 int swalbe_dist_height_stats(swalbe_dist *dist, double *out4, double thresh, void *stream);
 /* nsteps fused steps with halo exchange overlapped with the interior update */
 int swalbe_dist_time_loop(swalbe_dist *dist, int nsteps, unsigned long long step0, void *stream);
+/* The slab's time loop from / to HOST memory (tau == 1): the counterpart of swalbe_time_loop_host on a rank's rows.
+ * height_in_host != NULL: the state is replaced -- this rank's rows of the height come from page-locked host memory
+ * (Lx * j_count doubles), the velocities from the device slabs velx / vely (NULL: zero) -- and the ghost rows are
+ * exchanged; height_out_host != NULL: the rows of the final height go back to host memory.  On large slabs the planes
+ * travel in row bands while the first steps run behind the upload and the last ones ahead of the download (csrc/sweep.h;
+ * the strips next to the slab boundaries are stepped last, with one halo exchange per step).  Bit for bit what
+ * set_state + time_loop + get_state give.  Collective: every rank calls it with the same nsteps. */
+int swalbe_dist_time_loop_host(swalbe_dist *dist, int nsteps, unsigned long long step0, const double *height_in_host,
+                               const double *velx, const double *vely, double *height_out_host, void *stream);
 /* copy this rank's slab rows of height/velx/vely and (optional, may be NULL) the nine population planes out */
 int swalbe_dist_get_state(swalbe_dist *dist, double *height, double *velx, double *vely, double *fout, void *stream);
 /* *yes = 1 when the halo rows of the time loop travel as stores into the neighbours' memory (CUDA IPC mapping over

@@ -116,6 +116,7 @@ SIGNATURES = {
     "swalbe_dist_shift_theta": [_vp, _i, _i, _vp],
     "swalbe_dist_height_stats": [_vp, _vp, _d, _vp],
     "swalbe_dist_time_loop": [_vp, _i, _u64, _vp],
+    "swalbe_dist_time_loop_host": [_vp, _i, _u64, _vp, _vp, _vp, _vp, _vp],
     "swalbe_dist_get_state": [_vp, _vp, _vp, _vp, _vp, _vp],
     "swalbe_dist_uses_peer_memory": [_vp, C.POINTER(_i)],
     "swalbe_dist_last_loop_ms": [_vp, C.POINTER(C.c_float)],

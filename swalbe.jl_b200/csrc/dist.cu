@@ -36,6 +36,7 @@
 
 #include "fused.cuh"
 #include "launch.h"
+#include "sweep.h"
 
 namespace swalbe {
 
@@ -99,6 +100,10 @@ struct swalbe_dist {
   unsigned long long *flags;        // own: [0] pushes received from below, [1] from above, [2] sticky time-out flag
   unsigned long long seq;           // pushes issued so far (every rank issues one per step)
   unsigned int *push_count;         // last-block detection of k_halo_push
+  // swalbe_dist_time_loop_host: copy streams and events, created on first use
+  cudaStream_t s_h2d, s_d2h;
+  cudaEvent_t ev_up[64], ev_dn, ev_done, ev_seam;
+  bool have_host_streams;
   double *f[2];           // population sets (tau == 1: only f[0], no ghosts)
   double *ct;             // cospi(theta) slab with GH ghost rows (NULL: scalar theta)
   double *ct_spare;       // a slab released by swalbe_dist_set_theta(NULL), kept for the next field (no free in the loop)
@@ -379,6 +384,12 @@ int swalbe_dist_destroy(swalbe_dist *d) {
   if (d->s_comp) cudaStreamSynchronize(d->s_comp);
   if (d->s_edge) cudaStreamSynchronize(d->s_edge);
   if (d->s_comm) cudaStreamSynchronize(d->s_comm);
+  if (d->have_host_streams) {
+    cudaStreamSynchronize(d->s_h2d); cudaStreamSynchronize(d->s_d2h);
+    cudaStreamDestroy(d->s_h2d); cudaStreamDestroy(d->s_d2h);
+    for (cudaEvent_t ev : d->ev_up) cudaEventDestroy(ev);
+    cudaEventDestroy(d->ev_dn); cudaEventDestroy(d->ev_done); cudaEventDestroy(d->ev_seam);
+  }
   close_peer_memory(d);
   if (d->comm) g_nccl.CommDestroy(d->comm);
   cudaFree(d->arena);
@@ -431,14 +442,22 @@ int swalbe_dist_set_state(swalbe_dist *d, const double *height, const double *ve
   return 0;
 }
 
-int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, void *stream_) {
-  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
-  if (nsteps <= 0) return 0;
-  cudaStream_t user = (cudaStream_t)stream_;
-  SW_CUDA(cudaEventRecord(d->ev_user, user));
-  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_user, 0));
-  SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_user, 0));
-  SW_CUDA(cudaEventRecord(d->ev_t0, d->s_comp));
+static void slab_args(const swalbe_dist *d, int src, int dst, unsigned long long step, FusedArgs &a) {
+  a = d->base;
+  a.Lx = d->Lx; a.Ly = d->Ly_loc; a.wrap_y = 0;  // ghost rows: pointers are handed over at logical row 0
+  a.jglobal0 = d->j_begin; a.Ly_global = d->Ly_global;
+  const size_t mo = (size_t)GH * d->Lx;
+  a.h_in = d->m[src][0] + mo; a.ux_in = d->m[src][1] + mo; a.uy_in = d->m[src][2] + mo;
+  a.h_out = d->m[dst][0] + mo; a.ux_out = d->m[dst][1] + mo; a.uy_out = d->m[dst][2] + mo;
+  a.f_in = nullptr; a.f_out = d->f[0];
+  a.fstride_in = a.fstride_out = a.fstride_out2 = d->fplane;
+  a.ct_field = d->ct ? d->ct + mo : nullptr;
+  a.step = step;
+}
+
+// nsteps steps on the handle's own streams (edge strips, exchange and interior overlapped); the caller has ordered the
+// streams after its input and orders its output after ev_halo / ev_edges / ev_int
+static int dist_steps(swalbe_dist *d, int nsteps, unsigned long long step0) {
   const int Ly = d->Ly_loc;
   for (int s = 0; s < nsteps; ++s) {
     const int src = d->cur, dst = d->cur ^ 1;
@@ -484,10 +503,177 @@ int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, 
     d->cur = dst;
     if (!d->tau1) d->fcur = fdst;
   }
+  return 0;
+}
+
+int swalbe_dist_time_loop(swalbe_dist *d, int nsteps, unsigned long long step0, void *stream_) {
+  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
+  if (nsteps <= 0) return 0;
+  cudaStream_t user = (cudaStream_t)stream_;
+  SW_CUDA(cudaEventRecord(d->ev_user, user));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_user, 0));
+  SW_CUDA(cudaStreamWaitEvent(d->s_edge, d->ev_user, 0));
+  SW_CUDA(cudaEventRecord(d->ev_t0, d->s_comp));
+  if (int e = dist_steps(d, nsteps, step0)) return e;
   SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
   SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_edges, 0));
   SW_CUDA(cudaEventRecord(d->ev_t1, d->s_comp));
   SW_CUDA(cudaStreamWaitEvent(user, d->ev_t1, 0));
+  d->looped = true;
+  return 0;
+}
+
+// ---- the slab's time loop from / to host memory --------------------------------------------------------------------
+// Same sweeps as swalbe_time_loop_host (sweep.h) on the rows of one slab: the band stages never touch a ghost row (band 0
+// shrinks away from the lower edge by 3 rows per step, the last band from the upper edge), and what is a periodic seam
+// on one GPU is here the slab boundary: after the last band, step k of the strips [0, 3k) and [Ly_loc - 3k, Ly_loc) is
+// computed from the neighbours' rows of step k-1, exchanged after every strip pair like in the ordinary loop.
+static int dist_host_streams(swalbe_dist *d) {
+  if (d->have_host_streams) return 0;
+  SW_CUDA(cudaStreamCreateWithFlags(&d->s_h2d, cudaStreamNonBlocking));
+  SW_CUDA(cudaStreamCreateWithFlags(&d->s_d2h, cudaStreamNonBlocking));
+  for (cudaEvent_t &ev : d->ev_up) SW_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&d->ev_dn, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
+  SW_CUDA(cudaEventCreateWithFlags(&d->ev_seam, cudaEventDisableTiming));
+  d->have_host_streams = true;
+  return 0;
+}
+
+// exchange of the ghost rows of moment set `set` after the work queued on s_comp so far; `rendezvous`: through NCCL even
+// when peer memory is on (the first exchange of a call: a neighbour may still be inside its previous loop)
+static int seam_exchange(swalbe_dist *d, int set, bool rendezvous) {
+  SW_CUDA(cudaEventRecord(d->ev_seam, d->s_comp));
+  SW_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_seam, 0));
+  if (d->p2p && !rendezvous) {
+    if (int e = push_halos(d, set)) return e;
+  } else {
+    if (int e = exchange_halos(d, set, d->fcur)) return e;
+    d->ghost_via_p2p = false;
+  }
+  SW_CUDA(cudaEventRecord(d->ev_halo, d->s_comm));
+  return 0;
+}
+static int seam_wait(swalbe_dist *d) {  // the ghost rows of the last exchange are there (s_comp)
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+  if (d->p2p && d->ghost_via_p2p) {
+    k_halo_wait<<<1, 32, 0, d->s_comp>>>(d->flags, d->seq);
+    SW_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int swalbe_dist_time_loop_host(swalbe_dist *d, int nsteps, unsigned long long step0, const double *h_in_host,
+                               const double *velx, const double *vely, double *h_out_host, void *stream_) {
+  if (!d) return set_error(SWALBE_ERR_ARG, "dist is NULL");
+  if (nsteps < 0) return set_error(SWALBE_ERR_ARG, "nsteps < 0");
+  if (!d->tau1) return set_error(SWALBE_ERR_ARG, "swalbe_dist_time_loop_host: tau == 1 only (the populations of a tau != 1 state "
+                                                  "do not travel with the height; use set_state / time_loop / get_state)");
+  if (int e = dist_host_streams(d)) return e;
+  cudaStream_t user = (cudaStream_t)stream_;
+  const int Lx = d->Lx, Ly = d->Ly_loc;
+  const size_t mo = (size_t)GH * Lx, nown = (size_t)Ly * Lx;
+  SW_CUDA(cudaEventRecord(d->ev_user, user));
+  for (cudaStream_t st : {d->s_comp, d->s_edge, d->s_comm, d->s_h2d, d->s_d2h}) SW_CUDA(cudaStreamWaitEvent(st, d->ev_user, 0));
+  SW_CUDA(cudaEventRecord(d->ev_t0, d->s_comp));
+  const bool hin = h_in_host != nullptr, hout = h_out_host != nullptr;
+  auto envi = [](const char *n) { return env_flag(n, 0); };
+  SweepConfig cfg = {0, 0, 0, 0};
+  if (env_flag("SWALBE_HOST_STREAM", 1))
+    cfg = sweep_configure(Lx, Ly, nsteps, hin, hout, envi("SWALBE_BAND_ROWS"), envi("SWALBE_HOST_KMAX"), envi("SWALBE_HOST_MIN_SITES"));
+  const std::vector<SweepOp> ops = sweep_schedule(cfg, Ly, nsteps, hin, hout);
+  if (hin) {  // the state is replaced: height from the host (band by band), velocities from the caller's slabs or zero
+    d->cur = 0; d->fcur = 0;
+    const double *vel[2] = {velx, vely};
+    for (int q = 0; q < 2; ++q) {
+      if (vel[q]) SW_CUDA(cudaMemcpyAsync(d->m[0][q + 1] + mo, vel[q], nown * sizeof(double), cudaMemcpyDeviceToDevice, d->s_comp));
+      else SW_CUDA(cudaMemsetAsync(d->m[0][q + 1], 0, d->mplane * sizeof(double), d->s_comp));
+    }
+    for (const SweepOp &op : ops)
+      if (op.kind == SWEEP_UPLOAD) {
+        const size_t off = (size_t)op.jbeg * Lx, cnt = (size_t)(op.jend - op.jbeg) * Lx;
+        SW_CUDA(cudaMemcpyAsync(d->m[0][0] + mo + off, h_in_host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, d->s_h2d));
+        SW_CUDA(cudaEventRecord(d->ev_up[op.band], d->s_h2d));
+      }
+  }
+  const int src0 = d->cur;
+  bool ghosts_current = !hin;  // (the runtime keeps the ghost rows of its current set current between calls)
+  LaunchGeom g_band = d->g_int, g_seam = d->g_edge;
+  if (cfg.nbands > 0) {
+    if (int e = choose_geometry(Lx, Ly / cfg.nbands, d->key, &g_band)) return e;
+    if (int e = choose_geometry(Lx, std::max(GH, 3 * std::max(cfg.k_up, cfg.k_dn) / 2 + 1), d->key_edge, &g_seam)) return e;
+  }
+  // the streams of the ordinary loop hang on three events; keep them meaningful around every piece issued here
+  auto publish = [&]() -> int {
+    SW_CUDA(cudaEventRecord(d->ev_int, d->s_comp));
+    SW_CUDA(cudaEventRecord(d->ev_edges, d->s_comp));
+    return 0;
+  };
+  int seam_launches = 0;
+  for (size_t qi = 0; qi < ops.size(); ++qi) {
+    const SweepOp &op = ops[qi];
+    if (op.kind == SWEEP_UPLOAD) continue;
+    if (op.kind == SWEEP_DOWNLOAD) {
+      const size_t off = (size_t)op.jbeg * Lx, cnt = (size_t)(op.jend - op.jbeg) * Lx;
+      const int fin = src0 ^ (nsteps & 1);
+      if (nsteps == 0 && hin)
+        for (const SweepOp &u : ops)
+          if (u.kind == SWEEP_UPLOAD) SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_up[u.band], 0));
+      SW_CUDA(cudaEventRecord(d->ev_dn, d->s_comp));
+      SW_CUDA(cudaStreamWaitEvent(d->s_d2h, d->ev_dn, 0));
+      SW_CUDA(cudaMemcpyAsync(h_out_host + off, d->m[fin][0] + mo + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, d->s_d2h));
+      continue;
+    }
+    if (op.band >= 0) SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_up[op.band], 0));
+    const int s = op.step;
+    if (op.stage < 0 && !op.seam) {  // a run of whole-slab steps: the ordinary loop (edge strips, exchange, interior)
+      int n = 1;
+      while (qi + n < ops.size() && ops[qi + n].kind == SWEEP_STEP && ops[qi + n].stage < 0 && !ops[qi + n].seam) ++n;
+      if (!ghosts_current) {
+        if (int e = seam_exchange(d, src0 ^ (s & 1), true)) return e;
+        ghosts_current = true;
+      }
+      if (int e = publish()) return e;
+      d->cur = src0 ^ (s & 1);
+      if (int e = dist_steps(d, n, step0 + (unsigned long long)s)) return e;
+      SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_edges, 0));  // the pieces below are issued on s_comp alone
+      qi += (size_t)n - 1;
+      continue;
+    }
+    const int src = src0 ^ (s & 1), dst = src ^ 1;
+    FusedArgs a;
+    slab_args(d, src, dst, step0 + (unsigned long long)s, a);
+    if (op.seam) {
+      if (!ghosts_current) {  // first strip of an upload sweep: the input state's ghost rows
+        if (int e = seam_exchange(d, src, true)) return e;
+        ghosts_current = true;
+      }
+      if ((seam_launches & 1) == 0)
+        if (int e = seam_wait(d)) return e;
+      a.W = g_seam.W; a.rows_per_cta = g_seam.rows_per_cta; a.jbeg = op.jbeg; a.jend = op.jend;
+      if (int e = launch_fused(g_seam, a, d->key_edge, d->s_comp)) return e;
+      if ((++seam_launches & 1) == 0)  // both strips of this step are queued: their rows travel
+        if (int e = seam_exchange(d, dst, false)) return e;
+      continue;
+    }
+    if (op.jend <= op.jbeg) continue;
+    a.W = g_band.W; a.rows_per_cta = g_band.rows_per_cta; a.jbeg = op.jbeg; a.jend = op.jend;
+    if (int e = launch_fused(g_band, a, d->key, d->s_comp)) return e;
+  }
+  d->cur = src0 ^ (nsteps & 1);
+  if (!ghosts_current) {  // (nsteps == 0: the uploaded state still owes its ghost rows)
+    for (const SweepOp &op : ops)
+      if (op.kind == SWEEP_UPLOAD) SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_up[op.band], 0));
+    if (int e = seam_exchange(d, d->cur, true)) return e;
+  }
+  SW_CUDA(cudaStreamWaitEvent(d->s_comp, d->ev_halo, 0));
+  if (int e = publish()) return e;
+  SW_CUDA(cudaEventRecord(d->ev_t1, d->s_comp));
+  SW_CUDA(cudaStreamWaitEvent(user, d->ev_t1, 0));
+  if (hout) {
+    SW_CUDA(cudaEventRecord(d->ev_done, d->s_d2h));
+    SW_CUDA(cudaStreamWaitEvent(user, d->ev_done, 0));
+  }
   d->looped = true;
   return 0;
 }

@@ -138,6 +138,20 @@ class DistSim:
     def time_loop(self, nsteps: int, step0: int = 0):
         _lib.call("swalbe_dist_time_loop", self.handle, int(nsteps), int(step0), self._stream())
 
+    def time_loop_host(self, nsteps: int, host_in=None, host_out=None, velx=None, vely=None, step0: int = 0):
+        """time_loop with this rank's rows of the height coming from / going to pinned host memory (CPU torch tensors of
+        Lx * j_count float64): the state is replaced by (host_in, velx, vely) -- velocities device Fields or None for zero
+        -- and the final height lands in host_out once the current stream has been synchronised (swalbe_dist_time_loop_host)."""
+        def hp(x):
+            if x is None:
+                return None
+            if x.device.type != "cpu" or not x.is_contiguous() or x.numel() != self.sysc.Lx * self.j_count:
+                raise ValueError("host plane: contiguous float64 CPU tensor of Lx * j_count elements expected")
+            return C.c_void_p(x.data_ptr())
+
+        _lib.call("swalbe_dist_time_loop_host", self.handle, int(nsteps), int(step0), hp(host_in),
+                  velx.ptr if velx is not None else None, vely.ptr if vely is not None else None, hp(host_out), self._stream())
+
     def get_state(self, height=None, velx=None, vely=None, fout=None):
         p = lambda f: f.ptr if f is not None else None  # noqa: E731
         _lib.call("swalbe_dist_get_state", self.handle, p(height), p(velx), p(vely), p(fout), self._stream())

@@ -606,6 +606,22 @@ function time_loop!(sim::DistSim, nsteps::Integer; step0::Integer = 0)
     return sim
 end
 
+"""
+    time_loop_host!(sim, nsteps; host_in, host_out, velx, vely, step0)
+
+`time_loop!` with this rank's rows of the height coming from / going to host matrices (`Lx x j_count`, page-locked for the
+overlap): the state is replaced by (`host_in`, `velx`, `vely`; velocities `nothing` = zero) and the final height lands in
+`host_out` after `synchronize()`.  The planes travel in row bands behind / ahead of the first / last steps.
+"""
+function time_loop_host!(sim::DistSim, nsteps::Integer; host_in::Union{Nothing,Array{Float64,2}} = nothing,
+                         host_out::Union{Nothing,Array{Float64,2}} = nothing, velx = nothing, vely = nothing, step0::Integer = 0)
+    GC.@preserve host_in host_out velx vely check(ccall((:swalbe_dist_time_loop_host, lib), Cint,
+        (Ptr{Cvoid}, Cint, Culonglong, Ptr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+        sim.ptr, nsteps, step0, host_in === nothing ? Ptr{Float64}(C_NULL) : pointer(host_in), _optptr(velx), _optptr(vely),
+        host_out === nothing ? Ptr{Float64}(C_NULL) : pointer(host_out), stream()))
+    return sim
+end
+
 """Copy this rank's slab out into device arrays (any of them may be `nothing`)."""
 function get_state!(sim::DistSim; height = nothing, velx = nothing, vely = nothing, fout = nothing)
     check(ccall((:swalbe_dist_get_state, lib), Cint,

@@ -32,11 +32,26 @@ def main():
     if mode in ("theta_field", "moving_theta_thermal"):
         ct = sw.cospi_field(sw.Field(Lx, Ly).set(theta)).numpy()  # same device cospi.(θ) as the single-GPU run
         sim.set_theta(sw.Field(Lx, n).set(slab_of(ct, sim.decomp, rank)))
-    sim.time_loop(5)
-    if mode == "moving_theta_thermal":
-        sim.shift_theta(1, 1)
-    sim.time_loop(4, step0=5)
-    sim.get_state(h)
+    if mode.startswith("host_loop"):  # the slab's loop from / to pinned host memory: banded sweeps, strips at the slab edges
+        os.environ["SWALBE_HOST_MIN_SITES"], os.environ["SWALBE_BAND_ROWS"] = "1", "16"
+        hin = torch.from_numpy(np.ascontiguousarray(slab_of(hg, sim.decomp, rank).transpose())).pin_memory()
+        hout = torch.full_like(hin, float("nan")).pin_memory()
+        junk = sw.Field(Lx, n).set(7.0)
+        sim.set_state(junk, junk, junk)            # whatever the runtime held before is replaced
+        if mode == "host_loop_two_calls":           # upload sweep + whole-slab steps, then whole-slab steps + download sweep
+            sim.time_loop_host(5, host_in=hin)
+            sim.time_loop_host(4, host_out=hout)
+        else:
+            sim.time_loop_host(9, host_in=hin, host_out=hout)
+        torch.cuda.synchronize()
+        sim.get_state(h)
+        assert torch.equal(hout.cuda(), h.t), "downloaded rows differ from the runtime's height"
+    else:
+        sim.time_loop(5)
+        if mode == "moving_theta_thermal":
+            sim.shift_theta(1, 1)
+        sim.time_loop(4, step0=5)
+        sim.get_state(h)
     parts = [torch.empty_like(h.t) for _ in range(world)]
     dist.all_gather(parts, h.t)
     if rank == 0:

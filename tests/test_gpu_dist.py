@@ -109,6 +109,42 @@ def test_single_rank_slab_bulk_copy_variant(monkeypatch):
     sim.close()
 
 
+@pytest.mark.parametrize("nsteps,rows", [(9, 16), (3, 24), (14, 12), (6, 0)])
+def test_single_rank_slab_host_loop_matches_oracle(monkeypatch, nsteps, rows):
+    """swalbe_dist_time_loop_host on one rank (the ring neighbour is the slab itself): height from pinned host memory in
+    row bands, the strips at the slab boundary stepped last with an exchange per step, height back to the host;
+    rows = 0: slabs too small for bands take the plain path (copy, exchange, loop, copy)."""
+    import torch
+
+    import swalbe_b200 as sw
+    from swalbe_b200.dist import DistSim
+
+    monkeypatch.setenv("SWALBE_HOST_MIN_SITES", "1" if rows else str(1 << 30))
+    monkeypatch.setenv("SWALBE_BAND_ROWS", str(rows or 16))
+    Lx, Ly = 130, 72
+    rng = np.random.default_rng(nsteps)
+    h0 = np.asfortranarray(np.abs(1.0 + 0.2 * rng.standard_normal((Lx, Ly))) + 0.06)
+    ux0 = np.asfortranarray(0.01 * rng.standard_normal((Lx, Ly)))
+    sysc = sw.SysConst(Lx=Lx, Ly=Ly, param=sw.Taumucs(g=-0.001))
+    sim = DistSim(sysc, 0, 1, None)
+    junk = sw.Field(Lx, Ly).set(5.0)
+    sim.set_state(junk, junk, junk)
+    hin = torch.from_numpy(np.ascontiguousarray(h0.transpose())).pin_memory()
+    hout = torch.full_like(hin, float("nan")).pin_memory()
+    sim.time_loop_host(nsteps, host_in=hin, host_out=hout, velx=sw.Field(Lx, Ly).set(ux0))
+    torch.cuda.synchronize()
+    ref = onp.State(Lx, Ly)
+    ref.height[...] = h0; ref.velx[...] = ux0
+    oc.time_loop(ref, onp.Params(g=-0.001), nsteps=nsteps)
+    assert np.array_equal(hout.numpy().transpose(), ref.height)
+    h, ux, uy = sw.Field(Lx, Ly), sw.Field(Lx, Ly), sw.Field(Lx, Ly)
+    sim.time_loop(2)  # the runtime is left consistent (current set, ghost rows): two more ordinary steps
+    sim.get_state(h, ux, uy)
+    oc.time_loop(ref, onp.Params(g=-0.001), nsteps=2)
+    assert np.array_equal(h.numpy(), ref.height) and np.array_equal(ux.numpy(), ref.velx) and np.array_equal(uy.numpy(), ref.vely)
+    sim.close()
+
+
 def test_slab_too_thin_is_rejected():
     import swalbe_b200 as sw
     from swalbe_b200.dist import DistSim
@@ -123,7 +159,7 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("mode", ["plain", "thermal", "theta_field", "moving_theta_thermal"])
+@pytest.mark.parametrize("mode", ["plain", "thermal", "theta_field", "moving_theta_thermal", "host_loop", "host_loop_two_calls"])
 def test_two_rank_nccl_matches_single_gpu(tmp_path, mode):
     """2 ranks over NCCL == 1 GPU, bit for bit -- including the thermal noise (counter-based on the global cell) and a
     contact-angle field whose ghost rows travel through the same exchange."""
@@ -146,7 +182,9 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path, mode):
     from swalbe_b200 import _lib
 
     kw = dict(thermal_seed=77 if thermal else None, pressure_variant=_lib.PRESSURE_POWER_BROAD)
-    if mode == "moving_theta_thermal":  # C4: noise + a contact-angle pattern that moves by (1,1) between the two loops
+    if mode.startswith("host_loop"):
+        sw.fused_steps(st, sysc, 9, **kw)
+    elif mode == "moving_theta_thermal":  # C4: noise + a contact-angle pattern that moves by (1,1) between the two loops
         th, inp = sw.Field(Lx, Ly).set(theta), sw.Field(Lx, Ly).set(theta)
         sw.fused_steps(st, sysc, 5, θ=th, **kw)
         sw.move_substrate(th, inp, 98, 98)

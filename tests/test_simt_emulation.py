@@ -556,3 +556,91 @@ def test_host_loop_sweeps_on_cpu(simt, nsteps, has_in, has_out):
         _same(st, ref, FIELDS + AUX)
         if has_out:
             assert np.array_equal(out, ref.height)
+
+
+@pytest.mark.parametrize("nsteps,has_in,has_out", [(3, True, True), (9, True, True), (5, False, True)])
+def test_slab_host_loop_sweeps_on_cpu(simt, nsteps, has_in, has_out):
+    """swalbe_dist_time_loop_host (csrc/dist.cu) on two emulated ranks: the same schedule on the rows of one slab, planes
+    with ghost rows (wrap_y = 0); band stages never touch a ghost row, the strips next to the slab boundaries are stepped
+    after the last band with one halo exchange per strip pair; whole-slab steps in between exchange after every step.
+    Rows that have not been uploaded and ghost rows that have not been exchanged are NaN.  Global oracle, bit for bit."""
+    Lx, n, ranks, GH, band, kmax = 40, 66, 2, 3, 22, 3
+    Ly = n * ranks
+    ops = _host_loop_ops(Lx, n, nsteps, has_in, has_out, band, kmax)
+    assert any(o[5] for o in ops) and any(o[6] >= 0 for o in ops)
+    p = onp.Params(g=-0.001, gamma=0.0005)
+    ref = _state(Lx, Ly, 23)
+    h0, ux0, uy0 = ref.height.copy(), ref.velx.copy(), ref.vely.copy()
+    oc.time_loop(ref, p, nsteps=nsteps)
+
+    def padded(a, r, ghosts=True):
+        out = np.asfortranarray(np.take(a, np.arange(r * n - GH, (r + 1) * n + GH), axis=1, mode="wrap"))
+        if not ghosts:
+            out[:, :GH] = np.nan; out[:, n + GH:] = np.nan
+        return out
+
+    # two moment sets per rank; state 0 lives in set 0.  With an upload only the velocities are there (their ghost rows
+    # too: zero / caller-provided slabs are exchanged with the height at the first exchange -- here they start un-exchanged)
+    sets = [[[padded(a, r, ghosts=not has_in) for a in (h0, ux0, uy0)], [np.full((Lx, n + 2 * GH), np.nan, order="F") for _ in range(3)]]
+            for r in range(ranks)]
+    if has_in:
+        for r in range(ranks):
+            sets[r][0][0][...] = np.nan
+    fout = [np.zeros((Lx, n, 9), order="F") for _ in range(ranks)]
+    out = [np.full((Lx, n), np.nan) for _ in range(ranks)]
+
+    def exchange(si):
+        for r in range(ranks):
+            lo, hi = (r - 1) % ranks, (r + 1) % ranks
+            for k in range(3):
+                sets[r][si][k][:, :GH] = sets[lo][si][k][:, n:n + GH]
+                sets[r][si][k][:, n + GH:] = sets[hi][si][k][:, GH:2 * GH]
+
+    def launch(r, s, j0, j1, rows):
+        src, dst = sets[r][s & 1], sets[r][(s & 1) ^ 1]
+        off = GH * Lx * 8
+        q = SimtStep()
+        q.flavour, q.Lx, q.Ly, q.jbeg, q.jend, q.W, q.rows_per_cta, q.wrap_y = STRICT, Lx, n, j0, j1, 40, rows, 0
+        q.tau, q.mu, q.delta, q.gamma, q.hmin, q.hcrit, q.g = p.tau, p.mu, p.delta, p.gamma, p.hmin, p.hcrit, p.g
+        q.cospi_theta, q.n, q.m = onp.cospi(p.theta), p.n, p.m
+        q.h_in, q.ux_in, q.uy_in = (C.c_void_p(a.ctypes.data + off) for a in src)
+        q.h_out, q.ux_out, q.uy_out = (C.c_void_p(a.ctypes.data + off) for a in dst)
+        q.f_out, q.fstride = _ptr(fout[r]), Lx * n
+        assert simt.simt_step(C.byref(q)) == 0
+
+    ghosts_current, seam_launches = not has_in, 0
+    for kind, s, j0, j1, b, seam, stage in ops:
+        if kind == 0:
+            for r in range(ranks):
+                sets[r][0][0][:, GH + j0:GH + j1] = h0[:, r * n + j0:r * n + j1]
+        elif kind == 2:
+            for r in range(ranks):
+                out[r][:, j0:j1] = sets[r][nsteps & 1][0][:, GH + j0:GH + j1]
+        elif stage < 0 and not seam:  # whole-slab step of the ordinary loop: edge strips, interior, exchange
+            if not ghosts_current:
+                exchange(s & 1); ghosts_current = True
+            for r in range(ranks):
+                for a, c, rows in ((0, GH, GH), (n - GH, n, GH), (GH, n - GH, 16)):
+                    launch(r, s, a, c, rows)
+            exchange((s & 1) ^ 1)
+        elif seam:
+            if not ghosts_current:
+                exchange(s & 1); ghosts_current = True
+            for r in range(ranks):
+                launch(r, s, j0, j1, 4)
+            seam_launches += 1
+            if seam_launches % 2 == 0:
+                exchange((s & 1) ^ 1)
+        elif j1 > j0:
+            for r in range(ranks):
+                launch(r, s, j0, j1, 16)
+    fin = nsteps & 1
+    got_h = np.concatenate([sets[r][fin][0][:, GH:GH + n] for r in range(ranks)], axis=1)
+    assert np.array_equal(got_h, ref.height)
+    assert np.array_equal(np.concatenate(fout, axis=1), ref.fout)
+    for r in range(ranks):  # the runtime's invariant: the ghost rows of the current set are current on return
+        lo, hi = (r - 1) % ranks, (r + 1) % ranks
+        assert np.array_equal(sets[r][fin][0][:, :GH], sets[lo][fin][0][:, n:n + GH])
+        assert np.array_equal(sets[r][fin][0][:, n + GH:], sets[hi][fin][0][:, GH:2 * GH])
+    if has_out:
+        assert np.array_equal(np.concatenate(out, axis=1), ref.height)
