@@ -17,9 +17,12 @@
  *  - Every call is asynchronous on the caller's `stream` (a cudaStream_t passed as void*; NULL = the
  *    legacy default stream), so it is ordered with the caller's own device work.  No hidden
  *    cudaDeviceSynchronize.  The only host-blocking entry points are the ones that own memory:
- *    swalbe_plan_create / swalbe_dist_create (cudaMalloc, NCCL communicator set-up), their destroy
- *    counterparts (swalbe_dist_destroy waits for the handle's own three streams before freeing) and
- *    swalbe_dist_last_loop_ms (waits for the loop's end event, by definition).
+ *    swalbe_plan_create / swalbe_dist_create (cudaMalloc, NCCL communicator set-up, IPC mapping of the
+ *    neighbours' memory), their destroy counterparts (swalbe_dist_destroy waits for the handle's own
+ *    streams before freeing), swalbe_dist_last_loop_ms (waits for the loop's end event, by definition)
+ *    and, once per handle, the FIRST call that needs library-owned resources created lazily: the copy
+ *    streams of swalbe_time_loop_host / swalbe_dist_time_loop_host and the row-sum buffer of the mass log
+ *    (swalbe_loop_logs.hsum).
  *  - Every function returns 0 on success or a swalbe_status code; swalbe_last_error() gives the
  *    message (thread-local).  Nothing throws across the ABI.
  *  - Arithmetic is IEEE-754 double with NO fused multiply-add contraction and the reference's exact
