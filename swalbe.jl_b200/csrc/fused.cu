@@ -729,16 +729,20 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
   MassLog ml;
   const int mass_planes = (logs && logs->hsum && logs->hsum_every > 0) ? kphase / logs->hsum_every + 2 : 1;
   if (int e = mass_log_setup(plan, logs, nsteps, &ml, mass_planes)) return e;
-  std::vector<int> mass_rows_done(mass_planes, 0);
-  // (the piece that completes a state is always issued on the caller's stream after the two compute streams have
-  // joined: a seam strip, a whole-lattice step, or the last band of the upload)
+  std::vector<int> mass_rows_done(mass_planes, 0), mass_pending(mass_planes, -1);
+  bool aux_busy = false;   // work on the second compute stream that the caller's stream has not waited for yet
+  // The rows of a state are summed on the stream of the launch (or upload wait) that makes them final -- before the next
+  // launches of the same band stage overwrite them.  The fold over the row sums needs all of them: it is issued on the
+  // caller's stream, at once when no piece can still be in flight on the second stream, else at the next join.
   auto mass_piece = [&](int state, const double *h, int jbeg, int jend, cudaStream_t on) -> int {
     const int pl = ((state - ml.first) / ml.every) % mass_planes;
     if (int e = mass_rows(plan, h, jbeg, jend, on, pl)) return e;
+    if (on != stream && jend > jbeg) aux_busy = true;
     mass_rows_done[pl] += jend - jbeg;
     if (mass_rows_done[pl] == Ly) {
       mass_rows_done[pl] = 0;
-      return mass_final(plan, ml.slot(state), on, pl);
+      if (on == stream && !aux_busy) return mass_final(plan, ml.slot(state), stream, pl);
+      mass_pending[pl] = state;
     }
     return 0;
   };
@@ -794,13 +798,18 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
   // end of the call -- runs on the caller's stream after the two have joined.  SWALBE_HOST_STREAMS=1: one stream.
   const bool two_streams = env_int("SWALBE_HOST_STREAMS", 2) >= 2;
   cudaStream_t lanes[2] = {stream, two_streams ? plan->s_aux : stream};
-  bool aux_busy = false;   // work on the second stream that the caller's stream has not waited for yet
   int sweep_s0 = 0;        // first step of the sweep in progress
   auto join = [&]() -> int {
-    if (!aux_busy) return 0;
-    SW_CUDA(cudaEventRecord(plan->ev_join, plan->s_aux));
-    SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_join, 0));
-    aux_busy = false;
+    if (aux_busy) {
+      SW_CUDA(cudaEventRecord(plan->ev_join, plan->s_aux));
+      SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_join, 0));
+      aux_busy = false;
+    }
+    for (int pl = 0; pl < mass_planes; ++pl)
+      if (mass_pending[pl] >= 0) {
+        if (int e = mass_final(plan, ml.slot(mass_pending[pl]), stream, pl)) return e;
+        mass_pending[pl] = -1;
+      }
     return 0;
   };
   for (size_t qi = 0; qi < ops.size(); ++qi) {
@@ -830,10 +839,8 @@ static int enqueue_steps_host(swalbe_plan *plan, const swalbe_state *st, const s
     const int k = op.stage >= 0 ? op.step - sweep_s0 + 1 : kk;
     if (op.band >= 0) {
       SW_CUDA(cudaStreamWaitEvent(on, plan->ev_up[op.band], 0));
-      if (ml.wants(0)) {  // (summed on the caller's stream: the last band completes the state there)
-        if (on != stream) SW_CUDA(cudaStreamWaitEvent(stream, plan->ev_up[op.band], 0));
-        if (int e = mass_piece(0, src0[0], up_beg[op.band], up_end[op.band], stream)) return e;
-      }
+      if (ml.wants(0))  // (on the stage's own stream, ahead of the launches that will overwrite the band)
+        if (int e = mass_piece(0, src0[0], up_beg[op.band], up_end[op.band], on)) return e;
     }
     if (two_streams && op.stage >= 1 && k >= 2) SW_CUDA(cudaStreamWaitEvent(on, plan->ev_wave[(op.stage - 1) & 1][k - 1], 0));
     if (op.jend <= op.jbeg) continue;
