@@ -569,8 +569,12 @@ def viewneighbors(f: Field):
 
 
 def power_broad(arg, n: int):
-    """power_broad(arg, n)   src/pressure.jl:363-385 -- temp = 1; temp *= arg, n times (host scalar helper)."""
-    temp = 1.0 if isinstance(arg, float) else 1
+    """power_broad(arg, n)   src/pressure.jl:363-385 -- temp = 1; temp *= arg, n times (host scalar helper), with the
+    reference's three methods: Float64 (:363), Float32 (:371, every product rounded to single precision) and Int (:379)."""
+    if isinstance(arg, np.float32):
+        temp = np.float32(1.0)
+    else:
+        temp = 1.0 if isinstance(arg, (float, np.floating)) else 1
     for _ in range(n):
         temp = temp * arg
     return temp

@@ -132,3 +132,18 @@ def test_cluster_kernel_division_free_row_index():
         inv = np.float32(1.0) / np.float32(Lx)
         got = ((idx.astype(np.float32) + np.float32(0.5)) * inv).astype(np.int64)
         assert np.array_equal(got, idx // Lx), Lx
+
+
+def test_power_broad_methods():
+    """power_broad(arg::Float64 | Float32 | Int, n)   src/pressure.jl:363-385 and its doctest (:344-356)"""
+    import numpy as np
+
+    assert sw.power_broad(3, 3) == 27 and isinstance(sw.power_broad(3, 3), int)
+    assert [sw.power_broad(x, 2) for x in (2.0, 5.0, 6.0)] == [4.0, 25.0, 36.0]
+    x32 = np.float32(0.1)
+    got = sw.power_broad(x32, 9)
+    want = np.float32(1.0)
+    for _ in range(9):
+        want = np.float32(want * x32)  # every product rounded to single precision, as `temp = 1.0f0; temp *= arg` does
+    assert isinstance(got, np.float32) and got == want and float(got) != sw.power_broad(0.1, 9)
+    assert sw.fast_93(0.5) == (0.5 ** 3) ** 3 - 0.5 ** 3 and sw.fast_32(0.5) == 0.5 ** 3 - 0.5 ** 2
