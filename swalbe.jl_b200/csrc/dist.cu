@@ -296,8 +296,12 @@ static int setup_peer_memory(swalbe_dist *d) {
   if (!d->tau1 || !env_flag("SWALBE_DIST_P2P", 1)) return 0;
   const int n = d->nranks;
   const int up = (d->rank + 1) % n, down = (d->rank + n - 1) % n;
-  unsigned char *dev = nullptr;
-  SW_CUDA(cudaMalloc((void **)&dev, 64 * (size_t)(n + 1)));
+  struct DevBuf {  // (freed on every return path)
+    unsigned char *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+  } buf;
+  SW_CUDA(cudaMalloc((void **)&buf.p, 64 * (size_t)(n + 1)));
+  unsigned char *const dev = buf.p;
   std::vector<unsigned char> host(64 * (size_t)n);
   unsigned char mine[64] = {0};
   cudaIpcMemHandle_t h;
@@ -323,7 +327,6 @@ static int setup_peer_memory(swalbe_dist *d) {
   SW_NCCL(g_nccl.AllGather(dev, dev + 64, 64, ncclChar, d->comm, d->s_comm));
   SW_CUDA(cudaMemcpyAsync(host.data(), dev + 64, 64 * (size_t)n, cudaMemcpyDeviceToHost, d->s_comm));
   SW_CUDA(cudaStreamSynchronize(d->s_comm));
-  SW_CUDA(cudaFree(dev));
   bool all = true;
   for (int r = 0; r < n; ++r) all = all && host[64 * (size_t)r] == 1;
   if (!all) {
