@@ -271,6 +271,7 @@ function destroy!(h::PlanHandle)
     end
     return nothing
 end
+const ONE_CALL_SITES = 1 << 21   # lattices from this size on run a non-verbose time_loop as one library call
 const plans = Dict{UInt,PlanHandle}()
 function plan(state::GPUState)
     key = objectid(state.height)
@@ -359,6 +360,18 @@ function _loop(sys, state, verbose; θ = sys.param.θ, incl = nothing, hmin = no
                host_in = nothing, host_out = nothing)
     t, Tmax, tdump = 1, sys.param.Tmax, max(1, sys.param.tdump)
     lazy = sys.param.τ == 1 ? LOOP_LAZY_POPULATIONS : Cint(0)
+    if !verbose && Tmax >= 1 && length(state.height) >= ONE_CALL_SITES
+        # Large lattices, nothing to print: the whole loop is ONE library call (the reference computes `mass` at the dump
+        # steps and drops it), so the sweeps of a host loop are not cut at dump steps and no chunk boundary costs a launch
+        # gap.  A verbose loop keeps the chunks below and reads the mass between them like upstream.
+        logs = nothing
+        if hmin !== nothing || wet !== nothing
+            logs = CLogs(hmin === nothing ? NULLF : pointer(hmin, 1), hmax === nothing ? NULLF : pointer(hmax, 1),
+                         wet === nothing ? CuPtr{Culonglong}(0) : pointer(wet, 1), 0.055)
+        end
+        fused_steps!(state, sys, Tmax; θ = θ, incl = incl, logs = logs, flags = lazy, host_in = host_in, host_out = host_out)
+        return state
+    end
     while t <= Tmax
         if t % tdump == 0
             mass = sum(state.height)
