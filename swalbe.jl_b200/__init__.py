@@ -672,15 +672,25 @@ def fused_steps(st: CuState, sys_: SysConst, nsteps: int, *, θ=None, slip_varia
 
 
 def _host_ptr(x, st):
-    """address of a host plane of Lx*Ly float64 (torch CPU tensor, ideally pinned, or NumPy array)"""
+    """address of a host plane of Lx*Ly float64 in the memory order of ``state.height`` (i fastest): a NumPy array of
+    shape (Lx, Ly) in Fortran order, of shape (Ly, Lx) in C order, or flat; a torch CPU tensor (ideally pinned) of shape
+    (Ly, Lx) or flat.  Anything whose memory order would silently transpose the lattice is refused."""
     if x is None:
         return None
+    Lx, Ly = st.Lx, st.Ly
+    shape = tuple(x.shape)
     if isinstance(x, np.ndarray):
-        if x.dtype != np.float64 or x.size != st.Lx * st.Ly or not (x.flags.c_contiguous or x.flags.f_contiguous):
-            raise ValueError("host plane: contiguous float64 array of Lx*Ly elements expected")
+        ok = x.dtype == np.float64 and ((shape == (Lx * Ly,) and x.flags.c_contiguous) or
+                                        (shape == (Ly, Lx) and x.flags.c_contiguous) or (shape == (Lx, Ly) and x.flags.f_contiguous))
+        if not ok:
+            raise ValueError(f"host plane: float64 array of shape ({Lx}, {Ly}) in Fortran order, ({Ly}, {Lx}) in C order or flat "
+                             f"expected, got shape {shape}, C-contiguous={x.flags.c_contiguous}, F-contiguous={x.flags.f_contiguous}")
         return C.c_void_p(x.ctypes.data)
-    if x.device.type != "cpu" or x.dtype != _torch().float64 or x.numel() != st.Lx * st.Ly or not x.is_contiguous():
-        raise ValueError("host plane: contiguous float64 CPU tensor of Lx*Ly elements expected")
+    import torch  # (the layout check itself needs no device)
+
+    ok = (x.device.type == "cpu" and x.dtype == torch.float64 and x.is_contiguous() and shape in ((Lx * Ly,), (Ly, Lx)))
+    if not ok:
+        raise ValueError(f"host plane: contiguous float64 CPU tensor of shape ({Ly}, {Lx}) or flat expected, got {shape}")
     return C.c_void_p(x.data_ptr())
 
 

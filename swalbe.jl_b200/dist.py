@@ -145,8 +145,13 @@ class DistSim:
         def hp(x):
             if x is None:
                 return None
-            if x.device.type != "cpu" or not x.is_contiguous() or x.numel() != self.sysc.Lx * self.j_count:
-                raise ValueError("host plane: contiguous float64 CPU tensor of Lx * j_count elements expected")
+            import torch
+
+            Lx, n = self.sysc.Lx, self.j_count
+            if (x.device.type != "cpu" or x.dtype != torch.float64 or not x.is_contiguous()
+                    or tuple(x.shape) not in ((n, Lx), (Lx * n,))):
+                raise ValueError(f"host plane: contiguous float64 CPU tensor of shape ({n}, {Lx}) or flat expected (the memory "
+                                 f"order of the slab: i fastest), got {tuple(x.shape)}")
             return C.c_void_p(x.data_ptr())
 
         _lib.call("swalbe_dist_time_loop_host", self.handle, int(nsteps), int(step0), hp(host_in),

@@ -147,3 +147,24 @@ def test_power_broad_methods():
         want = np.float32(want * x32)  # every product rounded to single precision, as `temp = 1.0f0; temp *= arg` does
     assert isinstance(got, np.float32) and got == want and float(got) != sw.power_broad(0.1, 9)
     assert sw.fast_93(0.5) == (0.5 ** 3) ** 3 - 0.5 ** 3 and sw.fast_32(0.5) == 0.5 ** 3 - 0.5 ** 2
+
+
+def test_host_plane_layout_is_checked():
+    """host_in / host_out of the host loop: only memory orders that match state.height (i fastest) are accepted"""
+    import numpy as np
+    import torch
+
+    class S:
+        Lx, Ly = 6, 4
+
+    f = np.zeros((6, 4), order="F")
+    assert sw._host_ptr(f, S).value == f.ctypes.data
+    c = np.zeros((4, 6))
+    assert sw._host_ptr(c, S).value == c.ctypes.data
+    assert sw._host_ptr(np.zeros(24), S) is not None and sw._host_ptr(None, S) is None
+    t = torch.zeros(4, 6, dtype=torch.float64)
+    assert sw._host_ptr(t, S).value == t.data_ptr() and sw._host_ptr(torch.zeros(24, dtype=torch.float64), S) is not None
+    for bad in (np.zeros((6, 4)), np.zeros((4, 6), order="F"), np.zeros((6, 4), dtype=np.float32, order="F"), np.zeros(23),
+                torch.zeros(6, 4, dtype=torch.float64), torch.zeros(4, 6), torch.zeros(4, 6, dtype=torch.float64).t()):
+        with pytest.raises(ValueError):
+            sw._host_ptr(bad, S)
