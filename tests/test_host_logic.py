@@ -168,3 +168,136 @@ def test_host_plane_layout_is_checked():
                 torch.zeros(6, 4, dtype=torch.float64), torch.zeros(4, 6), torch.zeros(4, 6, dtype=torch.float64).t()):
         with pytest.raises(ValueError):
             sw._host_ptr(bad, S)
+
+
+def _schedule(Lx, Ly, nsteps, has_in, has_out, band, kmax):
+    import ctypes as C
+
+    from swalbe_b200 import _lib
+
+    n = C.c_int(0)
+    _lib.call("swalbe_selftest_host_loop_schedule", Lx, Ly, nsteps, int(has_in), int(has_out), band, kmax, 1, None, 0, C.byref(n))
+    buf = (C.c_int * (7 * max(1, n.value)))()
+    _lib.call("swalbe_selftest_host_loop_schedule", Lx, Ly, nsteps, int(has_in), int(has_out), band, kmax, 1, buf, n.value, C.byref(n))
+    return [tuple(buf[7 * q:7 * q + 7]) for q in range(n.value)]
+
+
+def _symbolic_run(ops, Ly, nsteps, has_in, has_out, order, early_uploads):
+    """Execute a host-loop schedule on row LABELS instead of numbers: each of the two moment buffers holds, per row, the
+    index of the state it contains (-1: garbage).  A launch of step s over [j0, j1) must find state s in rows
+    [j0 - 3, j1 + 3) (periodic) of its source buffer and leaves state s + 1 in [j0, j1) of the other one; a download must
+    find the final state.  Any read of a row that has not been produced yet, or that a later step already overwrote,
+    fails -- for whichever order of the operations the streams allow."""
+    import numpy as np
+
+    buf = [np.full(Ly, -1), np.full(Ly, -1)]  # [A (the state's planes), B (scratch)]
+    src0 = 0 if nsteps % 2 == 0 else 1
+    if not has_in:
+        buf[src0][:] = 0
+    ups = [o for o in ops if o[0] == 0]
+    if early_uploads:
+        for _, _, j0, j1, *_ in ups:
+            buf[src0][j0:j1] = 0
+    got = np.full(Ly, -1)
+    for kind, s, j0, j1, band, seam, stage in order:
+        if kind == 0:
+            if not early_uploads:
+                buf[src0][j0:j1] = 0
+        elif kind == 2:
+            assert (buf[0][j0:j1] == nsteps).all(), ("download of rows that are not final", j0, j1)
+            got[j0:j1] = nsteps
+        elif kind == 3:  # mass log: the rows of state s, summed behind the launch (or upload wait) that made them final
+            holder = buf[0] if (nsteps - s) % 2 == 0 else buf[1]  # state s lives in the buffer step s reads
+            assert (holder[j0:j1] == s).all(), ("row sums of state", s, "rows", j0, j1, "find", sorted(set(holder[j0:j1].tolist())))
+        elif j1 > j0:
+            reads_A = (nsteps - s) % 2 == 0
+            src, dst = (buf[0], buf[1]) if reads_A else (buf[1], buf[0])
+            rows = np.arange(j0 - 3, j1 + 3) % Ly
+            assert (src[rows] == s).all(), ("step", s, "rows", j0, j1, "stage", stage, "finds", sorted(set(src[rows].tolist())))
+            dst[j0:j1] = s + 1
+    assert (buf[0] == nsteps).all()
+    if has_out:
+        assert (got == nsteps).all()
+
+
+def test_host_loop_schedule_symbolic():
+    """csrc/sweep.h over a few hundred lattice / band / sweep-length / step-count combinations, executed symbolically in the
+    listed order (uploads as late as possible) and in the step-major order the two compute streams allow (uploads first)"""
+    import random
+
+    rnd = random.Random(7)
+    nswept = 0
+    for trial in range(400):
+        Ly = rnd.choice([24, 61, 97, 128, 200, 301, 1000, 4096])
+        band = rnd.choice([0, 8, 16, 31, 50, 64, 100, 512, 1024])
+        kmax = rnd.choice([0, 1, 2, 3, 5, 12, 32])
+        nsteps = rnd.choice([1, 2, 3, 4, 7, 12, 13, 24, 25, 40])
+        has_in, has_out = rnd.choice([(True, True), (True, False), (False, True)])
+        ops = _schedule(64, Ly, nsteps, has_in, has_out, band, kmax)
+        steps = [o for o in ops if o[0] == 1]
+        assert sorted({o[1] for o in steps}) == list(range(nsteps))
+        nswept += any(o[6] >= 0 for o in steps)
+        _symbolic_run(ops, Ly, nsteps, has_in, has_out, ops, early_uploads=False)
+        # step-major inside every sweep (what two streams make possible), uploads first, downloads last
+        out, run = [], []
+
+        def flush():
+            if run:
+                k0 = min(o[1] for o in run)
+                out.extend(sorted(run, key=lambda o: (o[1] - k0, o[6])))
+                run.clear()
+
+        for o in steps:
+            if o[6] >= 0:
+                if run and o[6] == 0 and run[-1][6] != 0:
+                    flush()
+                run.append(o)
+            else:
+                flush()
+                out.append(o)
+        flush()
+        order = [o for o in ops if o[0] == 0] + out + [o for o in ops if o[0] == 2]
+        _symbolic_run(ops, Ly, nsteps, has_in, has_out, order, early_uploads=True)
+        # random interleavings of the two lanes (even / odd band stages, each in issue order) that respect the one
+        # cross-lane dependency the library enforces with an event: (stage b, k) after (stage b-1, k-1)
+        band_rows = {o[4]: (o[2], o[3]) for o in ops if o[0] == 0}
+        for _ in range(3):
+            out, run = [], []
+
+            def interleave():
+                if not run:
+                    return
+                k0 = min(o[1] for o in run)
+                lanes = [[], []]
+                for o in run:  # every launch is followed, on its own lane, by the row sums of the rows it produced; the first
+                    ln = lanes[o[6] % 2]  # launch of a band stage that waits for an upload is preceded by those of the band
+                    if o[4] >= 0:
+                        ln.append((3, 0, band_rows[o[4]][0], band_rows[o[4]][1], -1, 0, o[6]))
+                    ln.append(o)
+                    if o[1] + 1 < nsteps:
+                        ln.append((3, o[1] + 1, o[2], o[3], -1, 0, o[6]))
+                done = set()
+                while lanes[0] or lanes[1]:
+                    ready = [ln for ln in lanes if ln and (ln[0][0] == 3 or ln[0][6] == 0 or ln[0][1] == k0 or
+                                                          (ln[0][6] - 1, ln[0][1] - 1) in done)]
+                    assert ready, "the two lanes deadlock"
+                    ln = rnd.choice(ready)
+                    o = ln.pop(0)
+                    if o[0] == 1:
+                        done.add((o[6], o[1]))
+                    out.append(o)
+                run.clear()
+
+            for o in steps:
+                if o[6] >= 0:
+                    if run and o[6] == 0 and run[-1][6] != 0:
+                        interleave()
+                    run.append(o)
+                else:
+                    interleave()
+                    out.append(o)
+            interleave()
+            order = [o for o in ops if o[0] == 0] + out + [o for o in ops if o[0] == 2]
+            assert sorted(o for o in order if o[0] != 3) == sorted(ops)
+            _symbolic_run(ops, Ly, nsteps, has_in, has_out, order, early_uploads=True)
+    assert nswept > 150  # (most of the combinations really are banded sweeps, not the plain fallback)
