@@ -1024,7 +1024,8 @@ def run_dropletforced(sys_: SysConst, device: str = "GPU", radius=20, θ0=1 / 6,
 
 gradgamma, update_rho, obslist, run_gamma, two_droplets = (one_d.gradgamma, one_d.update_rho, one_d.obslist, one_d.run_gamma,
                                                            one_d.two_droplets)
-from .io import dump_height_slab, load_height_slab, restart_from_height, save_heights  # noqa: E402
+from .io import (dump_height_slab, load_height_slab, load_heights_bson, restart_from_height, save_heights,  # noqa: E402
+                 save_heights_bson)
 
 JULIA_NAMES = {
     "equilibrium!": equilibrium, "BGKandStream!": BGKandStream, "moments!": moments, "filmpressure!": filmpressure,

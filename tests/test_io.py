@@ -22,7 +22,7 @@ def test_restart_from_height_like_the_reference(tmp_path):
     with pytest.raises(ValueError):
         io.restart_from_height(path, timestep=1, size=(10, 11))
     with pytest.raises(ValueError):
-        io.restart_from_height(path, kind="jld2", timestep=1, size=(10, 10))
+        io.restart_from_height(path, kind="jld2", timestep=1, size=(10, 10))  # (an HDF5 dialect: no library for it here)
     # a name without the suffix reads back under the same name; "last column" = highest time step, not insertion order
     bare = str(tmp_path / "run7")
     assert io.save_heights(bare, {"h_10": h2.ravel(order="F"), "h_9": h1.ravel(order="F"), "h_2": h1.ravel(order="F")}) == bare + ".npz"
@@ -56,3 +56,32 @@ def test_slab_parallel_dump_roundtrip(tmp_path):
         io.dump_height_slab(path, h[:, :3], Lx, Ly, j_begin=18)
     with pytest.raises(ValueError):
         io.load_height_slab(path, Lx, Ly + 1)
+
+
+def test_bson_container_and_restart(tmp_path):
+    """kind = "bson" (src/initialvalues.jl:369-376).  The container layer against the BSON specification's own example
+    (bsonspec.org: {"hello": "world"}), the height columns through BSON.jl's documented array layout (round trip; parity with
+    a Julia-written file is unpinned: no BSON.jl here), tolerant reading of plain arrays and back references."""
+    spec = b"\x16\x00\x00\x00\x02hello\x00\x06\x00\x00\x00world\x00\x00"
+    assert io._bson_document(spec)[0] == {"hello": "world"} and io._bson_encode_document({"hello": "world"}) == spec
+    spec2 = (b"\x31\x00\x00\x00\x04BSON\x00\x26\x00\x00\x00\x020\x00\x08\x00\x00\x00awesome\x00\x011\x00\x33\x33\x33\x33\x33\x33"
+             b"\x14\x40\x102\x00\xc2\x07\x00\x00\x00\x00")  # {"BSON": ["awesome", 5.05, 1986]}
+    assert io._bson_document(spec2)[0] == {"BSON": ["awesome", 5.05, 1986]}
+    rng = np.random.default_rng(3)
+    h1, h2 = rng.random((10, 7)), rng.random((10, 7))
+    path = str(tmp_path / "file.bson")
+    io.save_heights_bson(path, {"h_1": h1, "h_20": h2})
+    assert np.array_equal(io.restart_from_height(path, kind="bson", timestep=1, size=(10, 7)), h1)
+    assert np.array_equal(io.restart_from_height(path, kind="bson", timestep=0, size=(10, 7)), h2)
+    doc = io._bson_document(open(path, "rb").read())[0]
+    assert doc["h_1"]["tag"] == "array" and doc["h_1"]["type"]["name"] == ["Core", "Float64"] and doc["h_1"]["size"] == [70]
+    assert doc["h_1"]["data"] == h1.ravel(order="F").astype("<f8").tobytes()
+    # what other writers may produce: a plain array of doubles, a back reference to a shared array
+    raw = io._bson_encode_document({"h_3": [1.0, 2.0, 3.0, 4.0], "h_4": {"tag": "backref", "ref": 1},
+                                    "_backrefs": [io._bson_lower_vector(np.arange(4.0))]})
+    p2 = tmp_path / "other.bson"
+    p2.write_bytes(raw)
+    assert np.array_equal(io.restart_from_height(str(p2), kind="bson", timestep=3, size=(2, 2)), np.array([[1.0, 3.0], [2.0, 4.0]]))
+    assert np.array_equal(io.restart_from_height(str(p2), kind="bson", timestep=4, size=(2, 2)), np.array([[0.0, 2.0], [1.0, 3.0]]))
+    with pytest.raises(ValueError):
+        io._bson_document(spec[:-1] + b"\x01")
