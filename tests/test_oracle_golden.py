@@ -247,3 +247,27 @@ def test_lowmem_fused_restatement_equals_the_pass_structured_oracle(case):
         oc.time_loop(full, p, nsteps=steps, threads=threads, **kw)
         assert np.array_equal(h, full.height) and np.array_equal(ux, full.velx) and np.array_equal(uy, full.vely)
         assert np.array_equal(f, full.fout) and np.array_equal(pr, full.pressure)
+
+
+def test_appendix_a_constants_bit_patterns():
+    """SURVEY.md Appendix A lists the IEEE-754 bit patterns of the literals the reference's broadcasts fold (2/3, 1/6, 10/3,
+    -1/3, 1/12, 1/3, 1/24, 1/9, 1/36, 5/6), of c_s = 1/sqrt(3.0) and of the default viscosity mu = (c_s*c_s)*(tau - 0.5), which
+    is 2 ulp above 1/6.  The oracle's Python expressions and the host mirror's Taumucs must produce exactly these doubles."""
+    import math
+    import struct
+
+    import swalbe_b200 as sw
+
+    def bits(x):
+        return struct.pack(">d", float(x)).hex().upper()
+
+    want = {2 / 3: "3FE5555555555555", 1 / 6: "3FC5555555555555", 10 / 3: "400AAAAAAAAAAAAB", -1 / 3: "BFD5555555555555",
+            1 / 12: "3FB5555555555555", 1 / 3: "3FD5555555555555", 1 / 24: "3FA5555555555555", 1 / 9: "3FBC71C71C71C71C",
+            1 / 36: "3F9C71C71C71C71C", 5 / 6: "3FEAAAAAAAAAAAAB"}
+    for value, pattern in want.items():
+        assert bits(value) == pattern, (value, bits(value))
+    cs = 1 / math.sqrt(3.0)
+    assert bits(cs) == "3FE279A74590331D" and bits(cs * cs) == "3FD5555555555557"
+    for prm in (onp.Params(), sw.Taumucs()):
+        assert bits(prm.cs) == "3FE279A74590331D"
+        assert bits(prm.mu) == "3FC5555555555557" and prm.mu != 1 / 6  # (cs*cs)*(1 - 0.5): 2 ulp above 1/6
