@@ -6,7 +6,8 @@
 One "step" = one pass of the hot path (src/simulate.jl:15-22) over the whole lattice.  Default workload: the
 8192 x 8192 thin film the north_star target is quoted on (tau = 1, Taumucs defaults, flat film + perturbation,
 SURVEY.md 8d C5/C4 geometry); at N > 1 every rank owns an L x L slab (weak scaling, global lattice L x N*L) and the
-ranks exchange halo rows over NCCL.  Prints ONE JSON line (rank 0).
+ranks exchange halo rows as peer-memory stores over NVLink (`halo_transport` in the line says which transport ran; NCCL
+send/recv where the ranks cannot map each other's memory).  Prints ONE JSON line (rank 0).
 
   value     MLUPS with the state resident in HBM, CUDA-event timed, max over ranks.  The timed steps are the same at every
             N: one fused step kernel per step, no materialisation of the reference's intermediate fields (the last
@@ -15,8 +16,10 @@ ranks exchange halo rows over NCCL.  Prints ONE JSON line (rank 0).
   parity_vs_1gpu   after the timed region: a 2048 x (256 N) lattice stepped 8 times by the N-rank slab runtime and by the
             single-GPU loop on rank 0 -- film, thermal (seeded) and thermal + moving contact-angle pattern -- gathered
             and compared BITWISE (height, velocities, populations)
-  e2e       MLUPS of a whole user-level job through the public API: pinned-host initial height -> H2D ->
-            time_loop (K steps, fused kernels, per-tdump mass read-back) -> D2H of the final height
+  e2e       MLUPS of a whole user-level job through the public API (run_host; DistSim.time_loop_host at N > 1): pinned-host
+            initial height -> H2D -> time_loop (K steps, fused kernels, mass of every dump step, every field materialised
+            on return) -> D2H of the final height into pinned host memory; wall clock around the job, both copies inside
+            it -- they travel in row bands behind the first and ahead of the last steps (swalbe_time_loop_host)
   roofline  144 B/LU (9 populations read + 9 written) x L^2 per launch / mean kernel time, against
             the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline  the C oracle (restated reference CPU path; Julia is not installable here) on the host cores,
