@@ -17,7 +17,9 @@ for r in rows:
     except ValueError:
         continue
     v *= {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}.get(r[ui], 1e-6)
-    name = re.sub(r"\(.*", "", r[ki]).strip()
+    name = r[ki].strip()
+    name = name[:name.rfind(">") + 1] if ">" in name else re.sub(r"\(.*", "", name)  # drop the parameter list, keep template args
+    name = re.sub(r"\(swalbe::\w+\)", "", name)
     tot[name] += v
     cnt[name] += 1
 allms = sum(tot.values())
